@@ -1,0 +1,471 @@
+// C ABI of the dsx sampler (include/dsx.h): handle, weight loading, schedule, workspace, and the host
+// side of the sampling loops.  The K-step loops run as a fixed sequence of kernel launches on the
+// caller's stream -- no host synchronisation and no PyTorch op inside the loop
+// (usr/diff/shallow_diffusion_tts.py:261-270 is a Python loop of ~300 ATen launches per step).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "dsx_internal.h"
+
+namespace dsx {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int dev_alloc(dsx_handle* h, void** p, size_t bytes, bool model_owned) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? DSX_E_NOMEM : DSX_E_CUDA;
+  }
+  if (model_owned) h->owned.push_back(q);
+  *p = q;
+  return DSX_OK;
+}
+
+static void free_ws(Workspace& w) {
+  void* ptrs[] = {w.X, w.SKIP, w.CONDF, w.G1, w.Zf, w.Y, w.CONDH, w.DTAB, w.EMB, w.TVALS, w.EPS, w.XTMP};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  w = Workspace();
+}
+
+int ensure_workspace(dsx_handle* h, const Geom& g, int rows) {
+  Workspace& w = h->ws;
+  const ModelDev& m = h->m;
+  const bool tc = h->precision != DSX_PREC_FP32_SIMT;
+  const bool have_tc = w.Y != nullptr, have_simt = w.CONDF != nullptr;
+  if (w.X && w.g.B == g.B && w.g.T == g.T && w.rows_cap >= rows && (tc ? have_tc : have_simt)) return DSX_OK;
+  const int keep_rows = std::max(rows, w.rows_cap);
+  free_ws(w);
+  const size_t nf = g.frames_padded();
+  size_t total = 0;
+  auto A = [&](void** p, size_t bytes) -> int {
+    total += bytes;
+    DSX_TRY(dev_alloc(h, p, bytes, false));
+    DSX_CUDA(cudaMemset(*p, 0, bytes));
+    return DSX_OK;
+  };
+  DSX_TRY(A(reinterpret_cast<void**>(&w.X), nf * m.C * 4));
+  DSX_TRY(A(reinterpret_cast<void**>(&w.SKIP), nf * m.C * 4));
+  DSX_TRY(A(reinterpret_cast<void**>(&w.G1), nf * 2 * m.C * 4));
+  DSX_TRY(A(reinterpret_cast<void**>(&w.Zf), nf * m.C * 4));
+  if (tc) {
+    DSX_TRY(A(reinterpret_cast<void**>(&w.Y), nf * m.C * 2 * 4));
+    DSX_TRY(A(reinterpret_cast<void**>(&w.CONDH), nf * m.H * 2 * 2));
+  } else {
+    DSX_TRY(A(reinterpret_cast<void**>(&w.CONDF), nf * m.H * 4));
+  }
+  DSX_TRY(A(reinterpret_cast<void**>(&w.DTAB), static_cast<size_t>(keep_rows) * m.L * m.C * 4));
+  DSX_TRY(A(reinterpret_cast<void**>(&w.EMB), static_cast<size_t>(keep_rows) * m.C * 4));
+  DSX_TRY(A(reinterpret_cast<void**>(&w.TVALS), static_cast<size_t>(keep_rows) * 8));
+  const size_t mel = static_cast<size_t>(g.B) * m.M * g.T;
+  DSX_TRY(A(reinterpret_cast<void**>(&w.EPS), 5 * mel * 4));
+  DSX_TRY(A(reinterpret_cast<void**>(&w.XTMP), mel * 4));
+  w.g = g;
+  w.rows_cap = keep_rows;
+  w.bytes = total;
+  return DSX_OK;
+}
+
+int check_status(dsx_handle* h, cudaStream_t s, const char* what) {
+  DSX_CUDA(cudaMemcpyAsync(h->status_host, h->status_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+  DSX_CUDA(cudaStreamSynchronize(s));
+  if (*h->status_host != 0) {
+    int code = *h->status_host;
+    cudaMemsetAsync(h->status_dev, 0, sizeof(int), s);
+    set_error("%s: in-kernel watchdog tripped (code %d: 1xx producer, 2xx MMA issuer, 3xx epilogue wait)", what, code);
+    return DSX_E_KERNEL;
+  }
+  return DSX_OK;
+}
+
+// One DiffNet evaluation on the internal state: x (any strides) -> eps (contiguous [B,1,M,T]).
+static int run_eval(dsx_handle* h, const float* x, dsx_strides xs, const Geom& g, int row0, int row_per_b, float* eps,
+                    cudaStream_t s) {
+  const bool tc = h->precision != DSX_PREC_FP32_SIMT;
+  DSX_TRY(launch_inproj(h, x, xs, g, row0, row_per_b, s));
+  const int nl = (h->layer_limit >= 0) ? std::min(h->layer_limit, h->m.L) : h->m.L;
+  for (int l = 0; l < nl; ++l) {
+    if (tc)
+      DSX_TRY(launch_tc_layer(h, l, g, row0, row_per_b, s));
+    else
+      DSX_TRY(launch_simt_layer(h, l, g, row0, row_per_b, s));
+  }
+  if (nl == h->m.L) DSX_TRY(launch_head(h, g, eps, s));
+  return DSX_OK;
+}
+
+static int prepare(dsx_handle* h, const float* cond, dsx_strides cs, int B, int T, int rows, Geom& g, cudaStream_t s) {
+  DSX_CHECK(h && h->loaded, DSX_E_STATE, "dsx_load_diffnet has not been called");
+  DSX_CHECK(B > 0 && T > 0, DSX_E_INVALID, "B and T must be positive (got %d, %d)", B, T);
+  DSX_CUDA(cudaSetDevice(h->device));
+  g.set(B, T);
+  DSX_TRY(ensure_workspace(h, g, rows));
+  if (h->precision != DSX_PREC_FP32_SIMT) DSX_TRY(tc_prepare_maps(h, g));
+  DSX_TRY(launch_pack_cond(h, cond, cs, g, s));
+  return DSX_OK;
+}
+
+static dsx_strides contiguous_mel(int M, int T) {
+  dsx_strides xs;
+  xs.b = static_cast<int64_t>(M) * T;
+  xs.c = T;
+  xs.t = 1;
+  return xs;
+}
+
+static int sample_ddpm_impl(dsx_handle* h, float* x, const Geom& g, int t_start, int n_steps, const float* noise,
+                            uint64_t seed, cudaStream_t s) {
+  const size_t mel = static_cast<size_t>(g.B) * h->m.M * g.T;
+  std::vector<int64_t> tv(n_steps);
+  for (int j = 0; j < n_steps; ++j) tv[j] = t_start - 1 - j;
+  DSX_CUDA(cudaMemcpyAsync(h->ws.TVALS, tv.data(), n_steps * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  DSX_CUDA(cudaStreamSynchronize(s));   // tv is a stack-owned staging buffer
+  DSX_TRY(launch_embed_table(h, h->ws.TVALS, n_steps, s));
+  const dsx_strides xs = contiguous_mel(h->m.M, g.T);
+  for (int j = 0; j < n_steps; ++j) {
+    const int t = t_start - 1 - j;
+    DSX_TRY(run_eval(h, x, xs, g, j, 0, h->ws.EPS, s));
+    DdpmCoef c;
+    c.A = h->sched[DSX_SCH_SQRT_RECIP_ALPHAS_CUMPROD][t];
+    c.Bc = h->sched[DSX_SCH_SQRT_RECIPM1_ALPHAS_CUMPROD][t];
+    c.c1 = h->sched[DSX_SCH_POSTERIOR_MEAN_COEF1][t];
+    c.c2 = h->sched[DSX_SCH_POSTERIOR_MEAN_COEF2][t];
+    c.sigma = (t == 0) ? 0.f : expf(0.5f * h->sched[DSX_SCH_POSTERIOR_LOG_VARIANCE_CLIPPED][t]);
+    DSX_TRY(launch_ddpm_update(h, x, h->ws.EPS, noise ? noise + static_cast<size_t>(j) * mel : nullptr, seed,
+                               static_cast<uint64_t>(j), c, mel, s));
+  }
+  return DSX_OK;
+}
+
+// get_x_pred coefficients (usr/diff/shallow_diffusion_tts.py:174-185), fp32 op by op
+static void plms_coefs(const dsx_handle* h, int t, int interval, PlmsCoef& c) {
+  const std::vector<float>& ac = h->sched[DSX_SCH_ALPHAS_CUMPROD];
+  const float a_t = ac[t];
+  const float a_prev = (t < interval) ? 1.0f : ac[std::max(t - interval, 0)];
+  const float a_t_sq = sqrtf(a_t), a_prev_sq = sqrtf(a_prev);
+  c.a_diff = a_prev - a_t;
+  c.kx = 1.0f / (a_t_sq * (a_t_sq + a_prev_sq));
+  c.ke = 1.0f / (a_t_sq * (sqrtf((1.0f - a_prev) * a_t) + sqrtf((1.0f - a_t) * a_prev)));
+}
+
+static int sample_plms_impl(dsx_handle* h, float* x, const Geom& g, int t_start, int interval, cudaStream_t s) {
+  const size_t mel = static_cast<size_t>(g.B) * h->m.M * g.T;
+  std::vector<int> steps;
+  for (int t = 0; t < t_start; t += interval) steps.push_back(t);
+  std::reverse(steps.begin(), steps.end());
+  const int n = static_cast<int>(steps.size());
+  DSX_CHECK(n > 0, DSX_E_INVALID, "empty PLMS schedule");
+  // table rows: 0..n-1 = the steps, row n = the extra warm-up evaluation at max(t0 - interval, 0)
+  std::vector<int64_t> tv(n + 1);
+  for (int j = 0; j < n; ++j) tv[j] = steps[j];
+  tv[n] = std::max(steps[0] - interval, 0);
+  DSX_CUDA(cudaMemcpyAsync(h->ws.TVALS, tv.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  DSX_CUDA(cudaStreamSynchronize(s));
+  DSX_TRY(launch_embed_table(h, h->ws.TVALS, n + 1, s));
+  const dsx_strides xs = contiguous_mel(h->m.M, g.T);
+  float* E[5];
+  for (int i = 0; i < 5; ++i) E[i] = h->ws.EPS + static_cast<size_t>(i) * mel;
+  // history ring: hist[0] = most recent eps_t
+  float* hist[4] = {nullptr, nullptr, nullptr, nullptr};
+  int nh = 0, slot = 0;
+  for (int j = 0; j < n; ++j) {
+    const int t = steps[j];
+    float* e0 = E[slot];
+    DSX_TRY(run_eval(h, x, xs, g, j, 0, e0, s));
+    PlmsCoef c{};
+    plms_coefs(h, t, interval, c);
+    if (nh == 0) {
+      // x' = phi(x, eps_t, t); eps' = net(x', max(t - interval, 0)); eps* = (eps_t + eps') / 2
+      PlmsCoef c1 = c;
+      c1.w0 = 1.f; c1.denom = 1.f;
+      DSX_TRY(launch_plms_update(h, h->ws.XTMP, x, e0, nullptr, nullptr, nullptr, c1, mel, s));
+      float* e1 = E[4];
+      DSX_TRY(run_eval(h, h->ws.XTMP, xs, g, n, 0, e1, s));
+      c.w0 = 1.f; c.w1 = 1.f; c.denom = 2.f;
+      DSX_TRY(launch_plms_update(h, x, x, e0, e1, nullptr, nullptr, c, mel, s));
+    } else if (nh == 1) {
+      c.w0 = 3.f; c.w1 = -1.f; c.denom = 2.f;
+      DSX_TRY(launch_plms_update(h, x, x, e0, hist[0], nullptr, nullptr, c, mel, s));
+    } else if (nh == 2) {
+      c.w0 = 23.f; c.w1 = -16.f; c.w2 = 5.f; c.denom = 12.f;
+      DSX_TRY(launch_plms_update(h, x, x, e0, hist[0], hist[1], nullptr, c, mel, s));
+    } else {
+      c.w0 = 55.f; c.w1 = -59.f; c.w2 = 37.f; c.w3 = -9.f; c.denom = 24.f;
+      DSX_TRY(launch_plms_update(h, x, x, e0, hist[0], hist[1], hist[2], c, mel, s));
+    }
+    hist[3] = hist[2]; hist[2] = hist[1]; hist[1] = hist[0]; hist[0] = e0;
+    nh = std::min(nh + 1, 4);
+    slot = (slot + 1) % 4;
+  }
+  return DSX_OK;
+}
+
+}  // namespace dsx
+
+using namespace dsx;
+
+extern "C" {
+
+int dsx_version(void) { return DSX_VERSION; }
+const char* dsx_last_error(void) { return g_err; }
+
+int dsx_create(int device, dsx_handle** out) {
+  DSX_CHECK(out, DSX_E_INVALID, "out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available (%s); dsx has no CPU fallback", cudaGetErrorString(e));
+    return DSX_E_CUDA;
+  }
+  DSX_CHECK(device >= 0 && device < ndev, DSX_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+  DSX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DSX_CUDA(cudaGetDeviceProperties(&prop, device));
+  dsx_handle* h = new dsx_handle();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->tc_group = 2;
+  if (prop.major != 10) {
+    // the tcgen05 kernels are sm_100a-only; other devices can still run the fp32 path
+    h->tc_group = 0;
+  }
+  if (cudaMalloc(&h->status_dev, sizeof(int)) != cudaSuccess ||
+      cudaMallocHost(&h->status_host, sizeof(int)) != cudaSuccess) {
+    set_error("status word allocation failed");
+    delete h;
+    return DSX_E_CUDA;
+  }
+  cudaMemset(h->status_dev, 0, sizeof(int));
+  *h->status_host = 0;
+  *out = h;
+  return DSX_OK;
+}
+
+static void free_model(dsx_handle* h) {
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear();
+  h->loaded = false;
+}
+
+void dsx_destroy(dsx_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_model(h);
+  free_ws(h->ws);
+  if (h->status_dev) cudaFree(h->status_dev);
+  if (h->status_host) cudaFreeHost(h->status_host);
+  delete h;
+}
+
+int dsx_load_diffnet(dsx_handle* h, const dsx_diffnet_params* p, int M, int C, int H, int L, int dilation_cycle,
+                     int precision, void* stream) {
+  DSX_CHECK(h && p, DSX_E_INVALID, "null handle or params");
+  DSX_CHECK(M > 0 && C > 0 && H > 0 && L > 0 && dilation_cycle > 0, DSX_E_INVALID, "bad model dimensions");
+  DSX_CHECK(C % 16 == 0 && H % 16 == 0 && M % 16 == 0, DSX_E_INVALID, "M, C, H must be multiples of 16 (got %d %d %d)", M, C, H);
+  DSX_CHECK(precision == DSX_PREC_FP32_SIMT || precision == DSX_PREC_FP16 || precision == DSX_PREC_FP16X3,
+            DSX_E_INVALID, "unknown precision %d", precision);
+  DSX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  free_model(h);
+  free_ws(h->ws);
+  h->tm_geom = Geom();
+  memset(&h->m, 0, sizeof(h->m));
+  h->m.M = M; h->m.C = C; h->m.H = H; h->m.L = L; h->m.cycle = dilation_cycle;
+  h->precision = precision;
+  if (precision != DSX_PREC_FP32_SIMT) {
+    DSX_CHECK(h->tc_group != 0, DSX_E_INVALID, "tcgen05 precisions need an sm_100 device");
+    DSX_CHECK(tc_supported(h), DSX_E_INVALID, "tcgen05 path needs residual_channels == hidden_size == 256");
+  }
+  DSX_TRY(simt_pack_model(h, p, s));
+  if (precision != DSX_PREC_FP32_SIMT) DSX_TRY(tc_pack_model(h, s));
+  DSX_CUDA(cudaStreamSynchronize(s));
+  h->loaded = true;
+  return DSX_OK;
+}
+
+int dsx_set_schedule(dsx_handle* h, const float* const* bufs, int T) {
+  DSX_CHECK(h && bufs && T > 0, DSX_E_INVALID, "bad schedule arguments");
+  for (int i = 0; i < DSX_SCH_COUNT; ++i) {
+    DSX_CHECK(bufs[i], DSX_E_INVALID, "schedule buffer %d is NULL", i);
+    h->sched[i].assign(bufs[i], bufs[i] + T);
+  }
+  h->sched_T = T;
+  return DSX_OK;
+}
+
+int dsx_diffnet_forward(dsx_handle* h, const float* x, dsx_strides xs, const int64_t* t, const float* cond,
+                        dsx_strides cs, float* eps, int B, int T, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DSX_CHECK(x && t && cond && eps, DSX_E_INVALID, "null tensor pointer");
+  Geom g;
+  DSX_TRY(prepare(h, cond, cs, B, T, B, g, s));
+  DSX_TRY(launch_embed_table(h, t, B, s));
+  DSX_TRY(run_eval(h, x, xs, g, 0, 1, eps, s));
+  return check_status(h, s, "dsx_diffnet_forward");
+}
+
+int dsx_sample_ddpm(dsx_handle* h, float* x_inout, const float* cond, dsx_strides cs, int B, int T, int t_start,
+                    int n_steps, const float* noise, uint64_t seed, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DSX_CHECK(x_inout && cond, DSX_E_INVALID, "null tensor pointer");
+  DSX_CHECK(h && h->sched_T > 0, DSX_E_STATE, "dsx_set_schedule has not been called");
+  DSX_CHECK(n_steps > 0 && t_start <= h->sched_T && t_start - n_steps >= 0, DSX_E_INVALID,
+            "steps t_start=%d n_steps=%d outside schedule of %d", t_start, n_steps, h->sched_T);
+  Geom g;
+  DSX_TRY(prepare(h, cond, cs, B, T, n_steps + 1, g, s));
+  DSX_TRY(sample_ddpm_impl(h, x_inout, g, t_start, n_steps, noise, seed, s));
+  return check_status(h, s, "dsx_sample_ddpm");
+}
+
+int dsx_sample_plms(dsx_handle* h, float* x_inout, const float* cond, dsx_strides cs, int B, int T, int t_start,
+                    int interval, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DSX_CHECK(x_inout && cond, DSX_E_INVALID, "null tensor pointer");
+  DSX_CHECK(h && h->sched_T > 0, DSX_E_STATE, "dsx_set_schedule has not been called");
+  DSX_CHECK(interval > 0 && t_start > 0 && t_start <= h->sched_T, DSX_E_INVALID, "bad PLMS arguments");
+  Geom g;
+  const int rows = (t_start + interval - 1) / interval + 2;
+  DSX_TRY(prepare(h, cond, cs, B, T, rows, g, s));
+  DSX_TRY(sample_plms_impl(h, x_inout, g, t_start, interval, s));
+  return check_status(h, s, "dsx_sample_plms");
+}
+
+int dsx_infer(dsx_handle* h, const float* cond, dsx_strides cs, const float* fs2_mel, const float* start_noise,
+              const float* x_start, const float* step_noise, uint64_t seed, const int64_t* mel2ph,
+              const float* spec_min, const float* spec_max, int B, int T, int K_step, int pndm_interval,
+              float* mel_out, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DSX_CHECK(cond && mel_out && spec_min && spec_max, DSX_E_INVALID, "null tensor pointer");
+  DSX_CHECK(fs2_mel || x_start, DSX_E_INVALID, "need fs2_mel (shallow start) or x_start (gaussian start)");
+  DSX_CHECK(h && h->sched_T > 0, DSX_E_STATE, "dsx_set_schedule has not been called");
+  DSX_CHECK(K_step > 0 && K_step <= h->sched_T, DSX_E_INVALID, "K_step %d outside schedule of %d", K_step, h->sched_T);
+  Geom g;
+  const int rows = pndm_interval > 0 ? (K_step + pndm_interval - 1) / pndm_interval + 2 : K_step + 1;
+  DSX_TRY(prepare(h, cond, cs, B, T, rows, g, s));
+  const int M = h->m.M;
+  const size_t mel = static_cast<size_t>(B) * M * T;
+  float* state = nullptr;   // x_t, [B,1,M,T]
+  DSX_TRY(dev_alloc(h, reinterpret_cast<void**>(&state), mel * 4, false));
+  float* x = state;
+  int rc = DSX_OK;
+  if (x_start) {
+    cudaError_t e = cudaMemcpyAsync(x, x_start, mel * 4, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) { set_error("copy of x_start failed: %s", cudaGetErrorString(e)); rc = DSX_E_CUDA; }
+  } else {
+    rc = launch_prologue(h, x, fs2_mel, start_noise, seed ^ 0x9E3779B97F4A7C15ull, spec_min, spec_max,
+                         h->sched[DSX_SCH_SQRT_ALPHAS_CUMPROD][K_step - 1],
+                         h->sched[DSX_SCH_SQRT_ONE_MINUS_ALPHAS_CUMPROD][K_step - 1], B, T, M, s);
+  }
+  if (rc == DSX_OK)
+    rc = pndm_interval > 0 ? sample_plms_impl(h, x, g, K_step, pndm_interval, s)
+                           : sample_ddpm_impl(h, x, g, K_step, K_step, step_noise, seed, s);
+  if (rc == DSX_OK) rc = launch_epilogue(h, x, mel2ph, spec_min, spec_max, mel_out, B, T, M, s);
+  if (rc == DSX_OK) rc = check_status(h, s, "dsx_infer");
+  cudaStreamSynchronize(s);
+  cudaFree(state);
+  return rc;
+}
+
+int dsx_infer_host(dsx_handle* h, const float* cond_host, dsx_strides cs, const float* fs2_mel_host,
+                   const float* x_start_host, uint64_t seed, const int64_t* mel2ph_host, const float* spec_min_host,
+                   const float* spec_max_host, int B, int T, int K_step, int pndm_interval, float* mel_out_host,
+                   void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DSX_CHECK(h && h->loaded, DSX_E_STATE, "dsx_load_diffnet has not been called");
+  DSX_CHECK(cond_host && mel_out_host && spec_min_host && spec_max_host, DSX_E_INVALID, "null host pointer");
+  DSX_CUDA(cudaSetDevice(h->device));
+  const int M = h->m.M, H = h->m.H;
+  const size_t mel = static_cast<size_t>(B) * M * T;
+  // the host cond tensor must be dense in some permutation of [B,H,T]; copy its full extent
+  const size_t cond_elems = static_cast<size_t>(B) * H * T;
+  float *d_cond = nullptr, *d_fs2 = nullptr, *d_x = nullptr, *d_min = nullptr, *d_max = nullptr, *d_out = nullptr;
+  int64_t* d_m2p = nullptr;
+  int rc = DSX_OK;
+  auto up = [&](void** d, const void* src, size_t bytes) {
+    if (rc != DSX_OK || !src) return;
+    rc = dev_alloc(h, d, bytes, false);
+    if (rc == DSX_OK && cudaMemcpyAsync(*d, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+      set_error("host->device copy failed");
+      rc = DSX_E_CUDA;
+    }
+  };
+  up(reinterpret_cast<void**>(&d_cond), cond_host, cond_elems * 4);
+  up(reinterpret_cast<void**>(&d_fs2), fs2_mel_host, mel * 4);
+  up(reinterpret_cast<void**>(&d_x), x_start_host, mel * 4);
+  up(reinterpret_cast<void**>(&d_min), spec_min_host, M * 4);
+  up(reinterpret_cast<void**>(&d_max), spec_max_host, M * 4);
+  up(reinterpret_cast<void**>(&d_m2p), mel2ph_host, static_cast<size_t>(B) * T * 8);
+  if (rc == DSX_OK) rc = dev_alloc(h, reinterpret_cast<void**>(&d_out), mel * 4, false);
+  if (rc == DSX_OK)
+    rc = dsx_infer(h, d_cond, cs, d_fs2, nullptr, d_x, nullptr, seed, d_m2p, d_min, d_max, B, T, K_step, pndm_interval,
+                   d_out, stream);
+  if (rc == DSX_OK && cudaMemcpyAsync(mel_out_host, d_out, mel * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) {
+    set_error("device->host copy failed");
+    rc = DSX_E_CUDA;
+  }
+  cudaStreamSynchronize(s);
+  void* frees[] = {d_cond, d_fs2, d_x, d_min, d_max, d_m2p, d_out};
+  for (void* p : frees)
+    if (p) cudaFree(p);
+  return rc;
+}
+
+int dsx_get_info(dsx_handle* h, int what, int64_t* out) {
+  DSX_CHECK(h && out, DSX_E_INVALID, "null argument");
+  switch (what) {
+    case DSX_INFO_PRECISION: *out = h->precision; break;
+    case DSX_INFO_KERNEL_LAUNCHES: *out = h->launches; break;
+    case DSX_INFO_WORKSPACE_BYTES: *out = static_cast<int64_t>(h->ws.bytes); break;
+    case DSX_INFO_SM_COUNT: *out = h->sm_count; break;
+    case DSX_INFO_TC_CTA_GROUP: *out = h->tc_group; break;
+    default: set_error("unknown info %d", what); return DSX_E_INVALID;
+  }
+  return DSX_OK;
+}
+
+int dsx_set_option(dsx_handle* h, int what, int64_t value) {
+  DSX_CHECK(h, DSX_E_INVALID, "null handle");
+  switch (what) {
+    case DSX_OPT_TC_CTA_GROUP:
+      DSX_CHECK(value == 1 || value == 2, DSX_E_INVALID, "cta_group must be 1 or 2");
+      DSX_CHECK(h->tc_group != 0, DSX_E_INVALID, "no tcgen05 on this device");
+      h->tc_group = static_cast<int>(value);
+      break;
+    case DSX_OPT_USE_GRAPH: h->use_graph = value ? 1 : 0; break;
+    default: set_error("unknown option %d", what); return DSX_E_INVALID;
+  }
+  return DSX_OK;
+}
+
+int dsx_debug_read(dsx_handle* h, int which, float* out, int B, int T, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DSX_CHECK(h && out && h->ws.X, DSX_E_STATE, "no workspace");
+  DSX_CHECK(B == h->ws.g.B && T == h->ws.g.T, DSX_E_INVALID, "geometry mismatch");
+  const float* src = which == 0 ? h->ws.X : h->ws.SKIP;
+  const int C = h->m.C;
+  DSX_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(T) * C * 4, src, static_cast<size_t>(h->ws.g.Tp) * C * 4,
+                             static_cast<size_t>(T) * C * 4, B, cudaMemcpyDeviceToDevice, s));
+  return DSX_OK;
+}
+
+int dsx_debug_set_layer_limit(dsx_handle* h, int n_layers) {
+  DSX_CHECK(h, DSX_E_INVALID, "null handle");
+  h->layer_limit = n_layers;
+  return DSX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// Internal declarations shared by the dsx translation units (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dsx.h"
+
+namespace dsx {
+
+void set_error(const char* fmt, ...);
+#define DSX_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::dsx::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DSX_E_CUDA;                                                                      \
+    }                                                                                         \
+  } while (0)
+#define DSX_CHECK(cond, code, ...)     \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::dsx::set_error(__VA_ARGS__);   \
+      return (code);                   \
+    }                                  \
+  } while (0)
+#define DSX_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != DSX_OK) return _r; \
+  } while (0)
+
+constexpr int kTile = 128;  // frames per tile (= UMMA M per CTA)
+
+// Geometry of one call: B utterances of T frames, stored frames-major with the frame axis
+// padded to a multiple of the tile so tiles never straddle utterances.
+struct Geom {
+  int B = 0, T = 0, Tp = 0, tiles_per_utt = 0, tiles = 0;
+  void set(int b, int t) {
+    B = b;
+    T = t;
+    tiles_per_utt = (t + kTile - 1) / kTile;
+    Tp = tiles_per_utt * kTile;
+    tiles = B * tiles_per_utt;
+  }
+  size_t frames_padded() const { return static_cast<size_t>(B) * Tp; }
+};
+
+// Device-side model description handed to kernels.
+struct ModelDev {
+  int M, C, H, L, cycle;
+  // fp32, SIMT layouts
+  const float* in_w;   // [C][M]
+  const float* in_b;   // [C]
+  const float* mlp0_w; // [4C][C]
+  const float* mlp0_b;
+  const float* mlp2_w; // [C][4C]
+  const float* mlp2_b;
+  const float* dif_w;  // [L][C][C]
+  const float* dif_b;  // [L][C]
+  const float* w1f;    // [L][2C][3C+H]   k = tap*C + c | 3C + h
+  const float* b1f;    // [L][2C]         dil_b + cond_b
+  const float* w2f;    // [L][2C][C]
+  const float* b2f;    // [L][2C]
+  const float* skip_w; // [C][C]
+  const float* skip_b;
+  const float* fin_w;  // [M][C]
+  const float* fin_b;
+  // tcgen05 packs (fp16, 128-byte rows of 64 k-values; see dsx_tc.cu for the tile order)
+  const __half* wpack; // [L][20480 rows][64]
+  const float* b1p;    // [L][2 chunks][256]  gate(128) | filter(128) per chunk
+};
+
+struct Workspace {
+  Geom g;               // capacity geometry (B, Tp) currently allocated
+  int rows_cap = 0;     // step-table rows
+  float* X = nullptr;       // [B][Tp][C] residual stream
+  float* SKIP = nullptr;    // [B][Tp][C]
+  float* CONDF = nullptr;   // [B][Tp][H] fp32 (SIMT path)
+  float* G1 = nullptr;      // [B][Tp][2C] SIMT GEMM output scratch
+  float* Zf = nullptr;      // [B][Tp][C]  SIMT gate output
+  __half* Y = nullptr;      // [2 buffers][2 planes][B][Tp][C]
+  __half* CONDH = nullptr;  // [2 planes][B][Tp][H]
+  float* DTAB = nullptr;    // [rows][L][C]
+  float* EMB = nullptr;     // [rows][C] scratch (mlp output)
+  int64_t* TVALS = nullptr; // [rows]
+  float* EPS = nullptr;     // [5][B][M][T] current + PLMS history ring
+  float* XTMP = nullptr;    // [B][M][T] PLMS warm-up state
+  size_t bytes = 0;
+};
+
+}  // namespace dsx
+
+struct dsx_handle {
+  int device = 0;
+  int sm_count = 0;
+  bool loaded = false;
+  int precision = DSX_PREC_FP32_SIMT;
+  int tc_group = 1;
+  int use_graph = 0;
+  int layer_limit = -1;
+  int64_t launches = 0;
+  dsx::ModelDev m{};
+  std::vector<void*> owned;   // device allocations of the model
+  int sched_T = 0;
+  std::vector<float> sched[DSX_SCH_COUNT];
+  dsx::Workspace ws;
+  int* status_dev = nullptr;   // kernel watchdog / self-check word
+  int* status_host = nullptr;  // pinned mirror
+  CUtensorMap tm_w{}, tm_y[2][2]{}, tm_cond[2]{};
+  dsx::Geom tm_geom;           // geometry the activation maps were built for
+  int tm_group = 0;
+  void* tm_base_y = nullptr;
+  void* tm_base_cond = nullptr;
+};
+
+namespace dsx {
+
+// ---- dsx_simt.cu -------------------------------------------------------------------------
+int simt_pack_model(dsx_handle* h, const dsx_diffnet_params* p, cudaStream_t s);
+int launch_embed_table(dsx_handle* h, const int64_t* t_dev, int rows, cudaStream_t s);
+int launch_pack_cond(dsx_handle* h, const float* cond, dsx_strides cs, const Geom& g, cudaStream_t s);
+int launch_inproj(dsx_handle* h, const float* x, dsx_strides xs, const Geom& g, int row0, int row_per_b,
+                  cudaStream_t s);
+int launch_simt_layer(dsx_handle* h, int layer, const Geom& g, int row0, int row_per_b, cudaStream_t s);
+int launch_head(dsx_handle* h, const Geom& g, float* eps, cudaStream_t s);
+struct DdpmCoef { float A, Bc, c1, c2, sigma; };
+int launch_ddpm_update(dsx_handle* h, float* x, const float* eps, const float* noise, uint64_t seed,
+                       uint64_t offset, DdpmCoef c, size_t n, cudaStream_t s);
+struct PlmsCoef { float kx, ke, a_diff, denom, w0, w1, w2, w3; };   // see k_plms_update
+int launch_plms_update(dsx_handle* h, float* x_out, const float* x_in, const float* e0, const float* e1,
+                       const float* e2, const float* e3, PlmsCoef c, size_t n, cudaStream_t s);
+int launch_prologue(dsx_handle* h, float* x, const float* fs2_mel, const float* start_noise, uint64_t seed,
+                    const float* spec_min, const float* spec_max, float sa, float s1a, int B, int T, int M,
+                    cudaStream_t s);
+int launch_epilogue(dsx_handle* h, const float* x, const int64_t* mel2ph, const float* spec_min,
+                    const float* spec_max, float* mel_out, int B, int T, int M, cudaStream_t s);
+
+// ---- dsx_tc.cu ---------------------------------------------------------------------------
+int tc_pack_model(dsx_handle* h, cudaStream_t s);
+int tc_prepare_maps(dsx_handle* h, const Geom& g);
+int launch_tc_layer(dsx_handle* h, int layer, const Geom& g, int row0, int row_per_b, cudaStream_t s);
+bool tc_supported(const dsx_handle* h);
+
+int dev_alloc(dsx_handle* h, void** p, size_t bytes, bool model_owned);
+int ensure_workspace(dsx_handle* h, const Geom& g, int rows);
+int check_status(dsx_handle* h, cudaStream_t s, const char* what);
+
+}  // namespace dsx

@@ -1,0 +1,209 @@
+// Hardware self-tests of the encodings the tcgen05 path depends on: the SWIZZLE_128B K-major shared
+// memory descriptor, the kind::f16 instruction descriptor, TMA boxes with negative / out-of-range
+// coordinates (zero fill), cta_group::1 and cta_group::2 MMA + multicast commit, and the 32x32b TMEM
+// load mapping.  One tiny GEMM per variant: D[128*G x 256] = A[128*G x 128] . W[256 x 128]^T with A
+// fetched from frame offset t0 = -3 (so the first rows must come back as zeros), checked exactly
+// against a host computation (all values are small dyadic rationals, exact in fp16 / fp32).
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "dsx_internal.h"
+#include "dsx_ptx.cuh"
+
+namespace dsx {
+
+struct SelfParams {
+  CUtensorMap tm_a;   // 3D [1][T][128] fp16, box 64 x 128 x 1
+  CUtensorMap tm_w;   // 2D [512 rows][64] fp16, box 64 x (256/G)
+  float* out;         // [128*G][256]
+  int t0;
+  int* status;
+};
+
+template <int G>
+__global__ void __launch_bounds__(256, 1) k_selftest(const __grid_constant__ SelfParams p) {
+  constexpr int A_BYTES = 128 * 128, W_BYTES = (256 / G) * 128, STAGE = A_BYTES + W_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + 2 * STAGE);
+  uint64_t* tfull = full + 2;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (G == 2) ? cluster_ctarank() : 0;
+  if (warp == 1 && lane == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<G>(slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  if (G == 2) { cluster_arrive(); cluster_wait(); }
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(slot);
+  Watchdog wd{p.status, globaltimer_ns() + 500000000ull};
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < 2; ++kb) {
+      if (rank == 0) mbar_arrive_expect_tx(&full[kb], G * STAGE);
+      tma_load_3d<G>(&p.tm_a, &full[kb], base + kb * STAGE, kb * 64, p.t0 + 128 * static_cast<int>(rank), 0);
+      tma_load_2d<G>(&p.tm_w, &full[kb], base + kb * STAGE + A_BYTES, 0, kb * 256 + rank * (256 / G));
+    }
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    constexpr uint32_t idesc = umma_idesc_f16(128 * G, 256);
+    uint32_t acc = 0;
+    bool ok = true;
+    for (int kb = 0; kb < 2 && ok; ++kb) {
+      ok = mbar_wait(&full[kb], 0, wd, 901);
+      if (!ok) break;
+      tc_fence_after();
+      const uint64_t ad = umma_desc_sw128(smem_u32(base + kb * STAGE));
+      const uint64_t bd = umma_desc_sw128(smem_u32(base + kb * STAGE + A_BYTES));
+      for (int k4 = 0; k4 < 4; ++k4) {
+        umma_f16<G>(tmem_base, ad + 2 * k4, bd + 2 * k4, idesc, acc);
+        acc = 1;
+      }
+    }
+    if (ok) umma_commit<G>(tfull);
+  } else if (warp >= 4) {
+    const int quad = warp & 3, r = quad * 32 + lane;
+    if (mbar_wait(tfull, 0, wd, 902)) {
+      tc_fence_after();
+      for (int j = 0; j < 256; j += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + j, v);
+        tmem_ld_wait();
+        float* o = p.out + (static_cast<size_t>(rank) * 128 + r) * 256 + j;
+        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (G == 2) { cluster_arrive(); cluster_wait(); }
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<G>(tmem_base, 256);
+  }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+template <int G>
+static int run_selftest(std::string& report) {
+  const int T = 300, CH = 128, t0 = -3, M = 128 * G;
+  std::vector<__half> ha(static_cast<size_t>(T) * CH), hw(512 * 64);
+  auto aval = [](int t, int c) { return static_cast<float>((t * 131 + c * 71) % 61 - 30) / 64.f; };
+  auto wval = [](int n, int k) { return static_cast<float>((n * 37 + k * 11) % 53 - 26) / 128.f; };
+  for (int t = 0; t < T; ++t)
+    for (int c = 0; c < CH; ++c) ha[static_cast<size_t>(t) * CH + c] = __float2half(aval(t, c));
+  for (int kb = 0; kb < 2; ++kb)
+    for (int n = 0; n < 256; ++n)
+      for (int kk = 0; kk < 64; ++kk) hw[(static_cast<size_t>(kb) * 256 + n) * 64 + kk] = __float2half(wval(n, kb * 64 + kk));
+  __half *da = nullptr, *dw = nullptr;
+  float* dout = nullptr;
+  int* dstatus = nullptr;
+  DSX_CUDA(cudaMalloc(&da, ha.size() * 2));
+  DSX_CUDA(cudaMalloc(&dw, hw.size() * 2));
+  DSX_CUDA(cudaMalloc(&dout, static_cast<size_t>(M) * 256 * 4));
+  DSX_CUDA(cudaMalloc(&dstatus, 4));
+  DSX_CUDA(cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice));
+  DSX_CUDA(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  DSX_CUDA(cudaMemset(dout, 0xff, static_cast<size_t>(M) * 256 * 4));
+  DSX_CUDA(cudaMemset(dstatus, 0, 4));
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  DSX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
+  DSX_CHECK(fp && q == cudaDriverEntryPointSuccess, DSX_E_CUDA, "no cuTensorMapEncodeTiled");
+  PFN_tmapEncodeTiled enc = reinterpret_cast<PFN_tmapEncodeTiled>(fp);
+  SelfParams prm;
+  memset(&prm, 0, sizeof(prm));
+  {
+    cuuint64_t dims[3] = {CH, T, 1};
+    cuuint64_t strides[2] = {CH * 2, static_cast<cuuint64_t>(T) * CH * 2};
+    cuuint32_t box[3] = {64, 128, 1}, es[3] = {1, 1, 1};
+    CUresult r = enc(&prm.tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, da, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSX_CHECK(r == CUDA_SUCCESS, DSX_E_CUDA, "selftest: encode A map failed %d", static_cast<int>(r));
+    cuuint64_t d2[2] = {64, 512};
+    cuuint64_t s2[1] = {128};
+    cuuint32_t b2[2] = {64, 256 / G}, e2[2] = {1, 1};
+    r = enc(&prm.tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dw, d2, s2, b2, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSX_CHECK(r == CUDA_SUCCESS, DSX_E_CUDA, "selftest: encode W map failed %d", static_cast<int>(r));
+  }
+  prm.out = dout;
+  prm.t0 = t0;
+  prm.status = dstatus;
+  const int smem = 1024 + 2 * (128 * 128 + (256 / G) * 128) + 64;
+  DSX_CUDA(cudaFuncSetAttribute(k_selftest<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(G);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = G;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DSX_CUDA(cudaLaunchKernelEx(&cfg, k_selftest<G>, prm));
+  DSX_CUDA(cudaDeviceSynchronize());
+  std::vector<float> out(static_cast<size_t>(M) * 256);
+  int status = 0;
+  DSX_CUDA(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+  DSX_CUDA(cudaMemcpy(&status, dstatus, 4, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(dw); cudaFree(dout); cudaFree(dstatus);
+  double maxerr = 0;
+  int bad = 0, first_bad_m = -1, first_bad_n = -1;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < 256; ++n) {
+      double ref = 0;
+      int t = t0 + m;
+      if (t >= 0 && t < T)
+        for (int k = 0; k < CH; ++k) ref += static_cast<double>(aval(t, k)) * wval(n, k);
+      double e = fabs(ref - out[static_cast<size_t>(m) * 256 + n]);
+      if (!(e <= 1e-4)) {
+        if (!bad) { first_bad_m = m; first_bad_n = n; }
+        bad++;
+      }
+      if (e > maxerr || e != e) maxerr = e;
+    }
+  char line[256];
+  snprintf(line, sizeof(line), "umma_cta_group%d: status=%d bad=%d/%d maxerr=%.3g first_bad=(%d,%d)\n", G, status, bad,
+           M * 256, maxerr, first_bad_m, first_bad_n);
+  report += line;
+  return (status == 0 && bad == 0) ? DSX_OK : DSX_E_KERNEL;
+}
+
+}  // namespace dsx
+
+extern "C" int dsx_selftest(int device, int which, char* report, int report_bytes) {
+  using namespace dsx;
+  DSX_CUDA(cudaSetDevice(device));
+  std::string rep;
+  int rc = DSX_OK;
+  std::string failed;
+  if (which < 0 || which == 0) {
+    int r = run_selftest<1>(rep);
+    if (r != DSX_OK) { rc = DSX_E_KERNEL; failed += " umma_cta_group1"; }
+  }
+  if (which < 0 || which == 1) {
+    int r = run_selftest<2>(rep);
+    if (r != DSX_OK) { rc = DSX_E_KERNEL; failed += " umma_cta_group2"; }
+  }
+  if (report && report_bytes > 0) {
+    strncpy(report, rep.c_str(), static_cast<size_t>(report_bytes) - 1);
+    report[report_bytes - 1] = 0;
+  }
+  if (rc != DSX_OK) set_error("selftest failed:%s | %s", failed.c_str(), rep.c_str());
+  return rc;
+}

@@ -1,0 +1,61 @@
+"""Utterance sharding across GPUs: batch rows are independent for the whole
+K-step loop, so each rank samples a contiguous slice of the batch with no per-step communication and
+ONE all-gather of the finished mel shards at the end (NCCL over NVLink / NVSwitch; gloo on CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items, world_size, rank):
+    """Contiguous, balanced split: the first (n % world) ranks hold one extra item."""
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(tensor, world_size=None, rank=None, dim=0):
+    world_size = dist.get_world_size() if world_size is None else world_size
+    rank = dist.get_rank() if rank is None else rank
+    lo, hi = shard_bounds(tensor.shape[dim], world_size, rank)
+    return tensor.narrow(dim, lo, hi - lo)
+
+
+def all_gather_batch(local, n_items, group=None):
+    """local: this rank's [b_r, ...] shard -> [n_items, ...] on every rank (one collective)."""
+    world = dist.get_world_size(group)
+    cap = (n_items + world - 1) // world
+    pad = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group) if hasattr(dist, "all_gather_into_tensor") and local.is_cuda \
+        else _all_gather_list(out, pad, world, group)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_items, world, r)
+        parts.append(out[r * cap: r * cap + (hi - lo)])
+    return torch.cat(parts, 0)
+
+
+def _all_gather_list(out, pad, world, group):
+    chunks = list(out.chunk(world, 0))
+    dist.all_gather(chunks, pad, group=group)
+
+
+def sharded_infer(sampler, cond, K_step, spec_min, spec_max, group=None, **kw):
+    """Runs DsxSampler.infer on this rank's utterances and all-gathers mel_out [B,T,M].
+    Per-utterance keyword tensors (fs2_mel, x_start, start_noise, mel2ph) are sliced like cond;
+    step_noise [K,B,...] is sliced on dim 1."""
+    B = cond.shape[0]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(B, world, rank)
+    sl = {}
+    for k, v in kw.items():
+        if torch.is_tensor(v) and k in ("fs2_mel", "x_start", "start_noise", "mel2ph"):
+            sl[k] = v[lo:hi]
+        elif torch.is_tensor(v) and k == "step_noise":
+            sl[k] = v[:, lo:hi]
+        else:
+            sl[k] = v
+    local = sampler.infer(cond[lo:hi], K_step, spec_min, spec_max, **sl) if hi > lo else \
+        torch.zeros((0, cond.shape[2], spec_min.numel()), device=cond.device)
+    return all_gather_batch(local, B, group)
