@@ -8,8 +8,9 @@ LIB_PATH = os.environ.get("DSX_LIB", os.path.join(_HERE, "lib", "libdsx.so"))
 
 PREC_FP32_SIMT, PREC_FP16, PREC_FP16X3 = 0, 1, 3
 PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "fp16": PREC_FP16, "fp16x3": PREC_FP16X3}
-INFO_PRECISION, INFO_KERNEL_LAUNCHES, INFO_WORKSPACE_BYTES, INFO_SM_COUNT, INFO_TC_CTA_GROUP = range(5)
-OPT_TC_CTA_GROUP, OPT_USE_GRAPH = 0, 1
+(INFO_PRECISION, INFO_KERNEL_LAUNCHES, INFO_WORKSPACE_BYTES, INFO_SM_COUNT, INFO_TC_CTA_GROUP, INFO_LAYER_KERNEL_NS,
+ INFO_LAYER_KERNEL_LAUNCHES) = range(7)
+OPT_TC_CTA_GROUP, OPT_USE_GRAPH, OPT_PROFILE = 0, 1, 2
 SCHEDULE_BUFFERS = (
     "betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
     "sqrt_one_minus_alphas_cumprod", "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
@@ -20,7 +21,7 @@ SCHEDULE_BUFFERS = (
 SYMBOLS = (
     "dsx_version", "dsx_last_error", "dsx_create", "dsx_destroy", "dsx_load_diffnet", "dsx_set_schedule",
     "dsx_diffnet_forward", "dsx_sample_ddpm", "dsx_sample_plms", "dsx_infer", "dsx_infer_host", "dsx_get_info",
-    "dsx_set_option", "dsx_debug_read", "dsx_debug_set_layer_limit", "dsx_selftest",
+    "dsx_set_option", "dsx_debug_read", "dsx_debug_trace", "dsx_debug_set_layer_limit", "dsx_selftest",
 )
 
 
@@ -45,7 +46,7 @@ class DiffNetParams(ctypes.Structure):
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        f"dsx CUDA library not found at {LIB_PATH}; build it with `python -m diffsinger_b200.build` "
+        f"dsx CUDA library not found at {LIB_PATH}; build it with `python diffsinger_b200/build.py` "
         "(nvcc, sm_100a).  There is no CPU fallback.")
 lib = ctypes.CDLL(LIB_PATH)
 
@@ -66,6 +67,7 @@ lib.dsx_get_info.argtypes = [_vp, _i, ctypes.POINTER(_i64)]
 lib.dsx_set_option.argtypes = [_vp, _i, _i64]
 lib.dsx_debug_read.argtypes = [_vp, _i, _vp, _i, _i, _vp]
 lib.dsx_debug_set_layer_limit.argtypes = [_vp, _i]
+lib.dsx_debug_trace.argtypes = [_vp, _i, _vp]
 lib.dsx_selftest.argtypes = [_i, _i, ctypes.c_char_p, _i]
 for _n in SYMBOLS:
     if getattr(lib, _n).restype is ctypes.c_int or _n not in ("dsx_last_error", "dsx_destroy"):

@@ -1,7 +1,7 @@
 """Builds the C-ABI CUDA library in-tree (diffsinger_b200/lib/libdsx.so) with nvcc for sm_100a.
 
-    python -m diffsinger_b200.build            # incremental (skips when sources are older than the .so)
-    python -m diffsinger_b200.build --force
+    python diffsinger_b200/build.py            # incremental (skips when sources are older than the .so)
+    python diffsinger_b200/build.py --force
 """
 import os
 import subprocess

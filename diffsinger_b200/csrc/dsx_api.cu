@@ -98,10 +98,23 @@ static int run_eval(dsx_handle* h, const float* x, dsx_strides xs, const Geom& g
   DSX_TRY(launch_inproj(h, x, xs, g, row0, row_per_b, s));
   const int nl = (h->layer_limit >= 0) ? std::min(h->layer_limit, h->m.L) : h->m.L;
   for (int l = 0; l < nl; ++l) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profile) {
+      while (h->prof_events.size() < h->prof_used + 2) {
+        cudaEvent_t e;
+        DSX_CUDA(cudaEventCreate(&e));
+        h->prof_events.push_back(e);
+      }
+      e0 = h->prof_events[h->prof_used];
+      e1 = h->prof_events[h->prof_used + 1];
+      h->prof_used += 2;
+      DSX_CUDA(cudaEventRecord(e0, s));
+    }
     if (tc)
       DSX_TRY(launch_tc_layer(h, l, g, row0, row_per_b, s));
     else
       DSX_TRY(launch_simt_layer(h, l, g, row0, row_per_b, s));
+    if (h->profile) DSX_CUDA(cudaEventRecord(e1, s));
   }
   if (nl == h->m.L) DSX_TRY(launch_head(h, g, eps, s));
   return DSX_OK;
@@ -266,6 +279,8 @@ void dsx_destroy(dsx_handle* h) {
   cudaDeviceSynchronize();
   free_model(h);
   free_ws(h->ws);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  if (h->trace_dev) cudaFree(h->trace_dev);
   if (h->status_dev) cudaFree(h->status_dev);
   if (h->status_host) cudaFreeHost(h->status_host);
   delete h;
@@ -432,6 +447,18 @@ int dsx_get_info(dsx_handle* h, int what, int64_t* out) {
     case DSX_INFO_WORKSPACE_BYTES: *out = static_cast<int64_t>(h->ws.bytes); break;
     case DSX_INFO_SM_COUNT: *out = h->sm_count; break;
     case DSX_INFO_TC_CTA_GROUP: *out = h->tc_group; break;
+    case DSX_INFO_LAYER_KERNEL_LAUNCHES: *out = static_cast<int64_t>(h->prof_used / 2); break;
+    case DSX_INFO_LAYER_KERNEL_NS: {
+      double total_ms = 0;
+      for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+        float ms = 0.f;
+        DSX_CUDA(cudaEventSynchronize(h->prof_events[i + 1]));
+        DSX_CUDA(cudaEventElapsedTime(&ms, h->prof_events[i], h->prof_events[i + 1]));
+        total_ms += ms;
+      }
+      *out = static_cast<int64_t>(total_ms * 1e6);
+      break;
+    }
     default: set_error("unknown info %d", what); return DSX_E_INVALID;
   }
   return DSX_OK;
@@ -446,6 +473,10 @@ int dsx_set_option(dsx_handle* h, int what, int64_t value) {
       h->tc_group = static_cast<int>(value);
       break;
     case DSX_OPT_USE_GRAPH: h->use_graph = value ? 1 : 0; break;
+    case DSX_OPT_PROFILE:
+      h->profile = value ? 1 : 0;
+      h->prof_used = 0;
+      break;
     default: set_error("unknown option %d", what); return DSX_E_INVALID;
   }
   return DSX_OK;
@@ -459,6 +490,25 @@ int dsx_debug_read(dsx_handle* h, int which, float* out, int B, int T, void* str
   const int C = h->m.C;
   DSX_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(T) * C * 4, src, static_cast<size_t>(h->ws.g.Tp) * C * 4,
                              static_cast<size_t>(T) * C * 4, B, cudaMemcpyDeviceToDevice, s));
+  return DSX_OK;
+}
+
+int dsx_debug_trace(dsx_handle* h, int enable, int64_t* out_host) {
+  DSX_CHECK(h, DSX_E_INVALID, "null handle");
+  DSX_CUDA(cudaSetDevice(h->device));
+  const size_t bytes = 6 * 256 * sizeof(long long);
+  if (out_host && h->trace_dev) {
+    DSX_CUDA(cudaDeviceSynchronize());
+    DSX_CUDA(cudaMemcpy(out_host, h->trace_dev, bytes, cudaMemcpyDeviceToHost));
+  }
+  if (enable && !h->trace_dev) {
+    DSX_CUDA(cudaMalloc(&h->trace_dev, bytes));
+    DSX_CUDA(cudaMemset(h->trace_dev, 0, bytes));
+  } else if (!enable && h->trace_dev) {
+    DSX_CUDA(cudaDeviceSynchronize());
+    cudaFree(h->trace_dev);
+    h->trace_dev = nullptr;
+  }
   return DSX_OK;
 }
 

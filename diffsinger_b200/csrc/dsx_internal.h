@@ -114,6 +114,10 @@ struct dsx_handle {
   CUtensorMap tm_w{}, tm_y[2][2]{}, tm_cond[2]{};
   dsx::Geom tm_geom;           // geometry the activation maps were built for
   int tm_group = 0;
+  int profile = 0;
+  long long* trace_dev = nullptr;   // debug timeline buffer (dsx_debug_trace)
+  std::vector<cudaEvent_t> prof_events;   // pairs (start, stop), prof_used of them recorded
+  size_t prof_used = 0;
   void* tm_base_y = nullptr;
   void* tm_base_cond = nullptr;
 };

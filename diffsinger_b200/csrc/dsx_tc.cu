@@ -69,6 +69,7 @@ struct TcLayerParams {
   int skip_init;           // 1: skip = value, 0: skip += value
   int* status;
   unsigned long long budget_ns;
+  long long* trace;        // debug: [2 CTAs][3 roles][256] clock64 stamps, or nullptr
 };
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
@@ -77,6 +78,12 @@ __device__ __forceinline__ float tanh_acc(float x) {
   // 2*sigmoid(2x) - 1, absolute error ~2e-7
   return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * x)), -1.f);
 }
+
+#define DSX_TRACE(role, slot)                                                              \
+  do {                                                                                     \
+    if (p.trace && blockIdx.x < 2 && (slot) < 256)                                          \
+      p.trace[(blockIdx.x * 3 + (role)) * 256 + (slot)] = clock64();                       \
+  } while (0)
 
 template <int G, int P>
 __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcLayerParams p) {
@@ -133,6 +140,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   Watchdog wd{p.status, globaltimer_ns() + p.budget_ns};
+  if (threadIdx.x == 0) DSX_TRACE(0, 254);
 
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
@@ -144,6 +152,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
           const int s = it % S;
           ok = mbar_wait(&empty[s], ((it / S) & 1) ^ 1, wd, 101);
           if (!ok) break;
+          DSX_TRACE(0, it);
           if (rank == 0) mbar_arrive_expect_tx(&full[s], G * Cfg::STAGE_BYTES);
           const int aplane = (pp == 2) ? 1 : 0, wplane = (pp == 1) ? 1 : 0;
           if (kb < 12)
@@ -159,6 +168,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
           const int s = it % S;
           ok = mbar_wait(&empty[s], ((it / S) & 1) ^ 1, wd, 102);
           if (!ok) break;
+          DSX_TRACE(0, it);
           if (rank == 0) mbar_arrive_expect_tx(&full[s], G * Cfg::W_BYTES);
           const int wplane = (pp == 1) ? 1 : 0;
           const int wrow = p.w_row0 + (64 + (wplane * 2 + q) * 4 + kb) * 256 + rank * Cfg::W_ROWS;
@@ -182,6 +192,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
           const int s = it % S;
           ok = mbar_wait(&full[s], (it / S) & 1, wd, 202);
           if (!ok) break;
+          DSX_TRACE(1, it);
           tc_fence_after();
           const uint64_t ad = umma_desc_sw128(smem_u32(stageA(s)));
           const uint64_t bd = umma_desc_sw128(smem_u32(stageW(s)));
@@ -194,12 +205,15 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
         }
       if (ok) umma_commit<G>(&tfull[buf]);
     }
+    DSX_TRACE(1, 200);
     if (ok) ok = mbar_wait(zfull, 0, wd, 203);
+    DSX_TRACE(1, 201);
     tc_fence_after();
     for (int q = 0; q < 2 && ok; ++q) {
       const int buf = q;
       ok = mbar_wait(&tempty[buf], (tuse[buf] & 1) ^ 1, wd, 204);
       if (!ok) break;
+      DSX_TRACE(1, 202 + q);
       tuse[buf]++;
       tc_fence_after();
       const uint32_t d = tmem_base + buf * 256;
@@ -209,6 +223,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
           const int s = it % S;
           ok = mbar_wait(&full[s], (it / S) & 1, wd, 205);
           if (!ok) break;
+          DSX_TRACE(1, it);
           tc_fence_after();
           const int zplane = (pp == 2) ? 1 : 0;
           const uint64_t ad = umma_desc_sw128(smem_u32(zbuf + (zplane * 4 + kb) * Cfg::A_BYTES));
@@ -234,8 +249,10 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
     bool ok = true;
     // ---- epi1: gate ----
     for (int h = 0; h < 2 && ok; ++h) {
+      if (warp == 4 && lane == 0) DSX_TRACE(2, h * 4 + 0);
       ok = mbar_wait(&tfull[h], tf[h] & 1, wd, 301);
       if (!ok) break;
+      if (warp == 4 && lane == 0) DSX_TRACE(2, h * 4 + 1);
       tf[h]++;
       tc_fence_after();
       const float* bg = p.b1p + h * 256;
@@ -276,6 +293,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
+      if (warp == 4 && lane == 0) DSX_TRACE(2, h * 4 + 2);
       if (lane == 0) {
         if (G == 2) {
           mbar_arrive_cluster(&tempty[h], 0);
@@ -287,7 +305,9 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
       }
     }
     // ---- epi2, residual half: x <- (x + o + b)/sqrt2 ; y_next ----
+    if (warp == 4 && lane == 0) DSX_TRACE(2, 8);
     if (ok) ok = mbar_wait(&tfull[0], tf[0] & 1, wd, 302);
+    if (warp == 4 && lane == 0) DSX_TRACE(2, 9);
     if (ok) {
       tf[0]++;
       tc_fence_after();
@@ -338,7 +358,9 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
       }
     }
     // ---- epi2, skip half ----
+    if (warp == 4 && lane == 0) DSX_TRACE(2, 10);
     if (ok) ok = mbar_wait(&tfull[1], tf[1] & 1, wd, 303);
+    if (warp == 4 && lane == 0) DSX_TRACE(2, 11);
     if (ok) {
       tf[1]++;
       tc_fence_after();
@@ -369,6 +391,8 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
     }
   }
 
+  if (warp == 4 && lane == 0) DSX_TRACE(2, 12);
+  if (threadIdx.x == 0) DSX_TRACE(0, 255);
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
@@ -548,6 +572,7 @@ int launch_tc_layer(dsx_handle* h, int layer, const Geom& g, int row0, int row_p
   prm.skip_init = (layer == 0);
   prm.status = h->status_dev;
   prm.budget_ns = 2000000000ull;
+  prm.trace = h->trace_dev;
   const int P = (h->precision == DSX_PREC_FP16) ? 1 : 3;
   if (h->tc_group == 2) {
     return P == 1 ? launch_tc_layer_t<2, 1>(h, prm, g.tiles, s) : launch_tc_layer_t<2, 3>(h, prm, g.tiles, s);

@@ -159,19 +159,27 @@ enum {
   DSX_INFO_KERNEL_LAUNCHES = 1, /* kernels launched by this handle so far               */
   DSX_INFO_WORKSPACE_BYTES = 2,
   DSX_INFO_SM_COUNT = 3,
-  DSX_INFO_TC_CTA_GROUP = 4     /* 1 or 2: cta_group of the tcgen05 path in use          */
+  DSX_INFO_TC_CTA_GROUP = 4,    /* 1 or 2: cta_group of the tcgen05 path in use          */
+  DSX_INFO_LAYER_KERNEL_NS = 5, /* DSX_OPT_PROFILE: summed device time of the residual-layer kernels since the
+                                   option was set (CUDA events on the launching stream; synchronises)     */
+  DSX_INFO_LAYER_KERNEL_LAUNCHES = 6
 };
 /* Tuning knobs (tests exercise every variant): */
 int dsx_set_option(dsx_handle* h, int what, int64_t value);
 enum {
   DSX_OPT_TC_CTA_GROUP = 0, /* 1 | 2                                                  */
-  DSX_OPT_USE_GRAPH = 1     /* capture each sampling loop into a CUDA graph (0 | 1)   */
+  DSX_OPT_USE_GRAPH = 1,    /* capture each sampling loop into a CUDA graph (0 | 1)   */
+  DSX_OPT_PROFILE = 2       /* 1: bracket every residual-layer kernel with CUDA events; setting it resets the sums */
 };
 
 /* Debug taps for layer-by-layer parity (tests only): copies internal fp32 frames-major
  * buffers after a dsx_diffnet_forward.  which: 0 = residual stream after the last layer
  * executed, 1 = skip sum.  out: [B, T, C] contiguous. */
 int dsx_debug_read(dsx_handle* h, int which, float* out, int B, int T, void* stream);
+/* Debug timeline of the residual-layer kernel: enable != 0 makes CTAs 0 and 1 of every following layer
+ * launch record clock64 stamps ([2][3 roles: producer, MMA issuer, epilogue][256] int64); out_host (may be
+ * NULL) receives the current buffer contents (6*256 int64) after synchronising the device. */
+int dsx_debug_trace(dsx_handle* h, int enable, int64_t* out_host);
 /* Run only layers [0, n_layers) in the next dsx_diffnet_forward calls (<0: all). */
 int dsx_debug_set_layer_limit(dsx_handle* h, int n_layers);
 
