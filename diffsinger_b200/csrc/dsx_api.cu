@@ -35,7 +35,7 @@ int dev_alloc(dsx_handle* h, void** p, size_t bytes, bool model_owned) {
 }
 
 static void free_ws(Workspace& w) {
-  void* ptrs[] = {w.X, w.SKIP, w.CONDF, w.G1, w.Zf, w.Y, w.CONDH, w.DTAB, w.EMB, w.TVALS, w.EPS, w.XTMP};
+  void* ptrs[] = {w.X, w.SKIP, w.CONDF, w.G1, w.Zf, w.Y, w.CONDH, w.S16, w.DTAB, w.EMB, w.TVALS, w.EPS, w.XTMP};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   w = Workspace();
@@ -64,6 +64,7 @@ int ensure_workspace(dsx_handle* h, const Geom& g, int rows) {
   if (tc) {
     DSX_TRY(A(reinterpret_cast<void**>(&w.Y), nf * m.C * 2 * 4));
     DSX_TRY(A(reinterpret_cast<void**>(&w.CONDH), nf * m.H * 2 * 2));
+    DSX_TRY(A(reinterpret_cast<void**>(&w.S16), nf * m.C * 2 * 2));
   } else {
     DSX_TRY(A(reinterpret_cast<void**>(&w.CONDF), nf * m.H * 4));
   }
@@ -91,12 +92,8 @@ int check_status(dsx_handle* h, cudaStream_t s, const char* what) {
   return DSX_OK;
 }
 
-// One DiffNet evaluation on the internal state: x (any strides) -> eps (contiguous [B,1,M,T]).
-static int run_eval(dsx_handle* h, const float* x, dsx_strides xs, const Geom& g, int row0, int row_per_b, float* eps,
-                    cudaStream_t s) {
+static int run_layers(dsx_handle* h, const Geom& g, int row0, int row_per_b, int nl, cudaStream_t s) {
   const bool tc = h->precision != DSX_PREC_FP32_SIMT;
-  DSX_TRY(launch_inproj(h, x, xs, g, row0, row_per_b, s));
-  const int nl = (h->layer_limit >= 0) ? std::min(h->layer_limit, h->m.L) : h->m.L;
   for (int l = 0; l < nl; ++l) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
@@ -116,7 +113,26 @@ static int run_eval(dsx_handle* h, const float* x, dsx_strides xs, const Geom& g
       DSX_TRY(launch_simt_layer(h, l, g, row0, row_per_b, s));
     if (h->profile) DSX_CUDA(cudaEventRecord(e1, s));
   }
-  if (nl == h->m.L) DSX_TRY(launch_head(h, g, eps, s));
+  return DSX_OK;
+}
+
+// One DiffNet evaluation: x (any strides) -> eps (contiguous [B,1,M,T]).
+static int run_eval(dsx_handle* h, const float* x, dsx_strides xs, const Geom& g, int row0, int row_per_b, float* eps,
+                    cudaStream_t s) {
+  const bool tc = h->precision != DSX_PREC_FP32_SIMT;
+  const int nl = (h->layer_limit >= 0) ? std::min(h->layer_limit, h->m.L) : h->m.L;
+  const DdpmCoef none{};
+  if (tc)
+    DSX_TRY(launch_tc_head(h, g, TC_INPROJ, const_cast<float*>(x), xs, nullptr, nullptr, 0, 0, none, row0, row_per_b, s));
+  else
+    DSX_TRY(launch_inproj(h, x, xs, g, row0, row_per_b, s));
+  DSX_TRY(run_layers(h, g, row0, row_per_b, nl, s));
+  if (nl == h->m.L) {
+    if (tc)
+      DSX_TRY(launch_tc_head(h, g, TC_HEAD | TC_WRITE_EPS, nullptr, xs, eps, nullptr, 0, 0, none, row0, row_per_b, s));
+    else
+      DSX_TRY(launch_head(h, g, eps, s));
+  }
   return DSX_OK;
 }
 
@@ -148,17 +164,26 @@ static int sample_ddpm_impl(dsx_handle* h, float* x, const Geom& g, int t_start,
   DSX_CUDA(cudaStreamSynchronize(s));   // tv is a stack-owned staging buffer
   DSX_TRY(launch_embed_table(h, h->ws.TVALS, n_steps, s));
   const dsx_strides xs = contiguous_mel(h->m.M, g.T);
+  const bool tc = h->precision != DSX_PREC_FP32_SIMT;
+  if (tc) DSX_TRY(launch_tc_head(h, g, TC_INPROJ, x, xs, nullptr, nullptr, 0, 0, DdpmCoef{}, 0, 0, s));
   for (int j = 0; j < n_steps; ++j) {
     const int t = t_start - 1 - j;
-    DSX_TRY(run_eval(h, x, xs, g, j, 0, h->ws.EPS, s));
+    if (!tc) DSX_TRY(run_eval(h, x, xs, g, j, 0, h->ws.EPS, s));
     DdpmCoef c;
     c.A = h->sched[DSX_SCH_SQRT_RECIP_ALPHAS_CUMPROD][t];
     c.Bc = h->sched[DSX_SCH_SQRT_RECIPM1_ALPHAS_CUMPROD][t];
     c.c1 = h->sched[DSX_SCH_POSTERIOR_MEAN_COEF1][t];
     c.c2 = h->sched[DSX_SCH_POSTERIOR_MEAN_COEF2][t];
     c.sigma = (t == 0) ? 0.f : expf(0.5f * h->sched[DSX_SCH_POSTERIOR_LOG_VARIANCE_CLIPPED][t]);
-    DSX_TRY(launch_ddpm_update(h, x, h->ws.EPS, noise ? noise + static_cast<size_t>(j) * mel : nullptr, seed,
-                               static_cast<uint64_t>(j), c, mel, s));
+    const float* nz = noise ? noise + static_cast<size_t>(j) * mel : nullptr;
+    if (tc) {
+      // 20 fused residual-layer kernels, then ONE kernel: head GEMMs + p_sample update + next step's input projection
+      DSX_TRY(run_layers(h, g, j, 0, h->m.L, s));
+      const int flags = TC_HEAD | TC_UPDATE | (j + 1 < n_steps ? TC_INPROJ : 0);
+      DSX_TRY(launch_tc_head(h, g, flags, x, xs, nullptr, nz, seed, static_cast<uint64_t>(j), c, j + 1, 0, s));
+    } else {
+      DSX_TRY(launch_ddpm_update(h, x, h->ws.EPS, nz, seed, static_cast<uint64_t>(j), c, mel, s));
+    }
   }
   return DSX_OK;
 }
@@ -468,7 +493,7 @@ int dsx_set_option(dsx_handle* h, int what, int64_t value) {
   DSX_CHECK(h, DSX_E_INVALID, "null handle");
   switch (what) {
     case DSX_OPT_TC_CTA_GROUP:
-      DSX_CHECK(value == 1 || value == 2, DSX_E_INVALID, "cta_group must be 1 or 2");
+      DSX_CHECK(value == 2, DSX_E_INVALID, "the residual-layer kernel is cta_group::2 only (cta_group::1 is exercised by dsx_selftest)");
       DSX_CHECK(h->tc_group != 0, DSX_E_INVALID, "no tcgen05 on this device");
       h->tc_group = static_cast<int>(value);
       break;

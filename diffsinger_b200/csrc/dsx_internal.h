@@ -73,6 +73,7 @@ struct ModelDev {
   // tcgen05 packs (fp16, 128-byte rows of 64 k-values; see dsx_tc.cu for the tile order)
   const __half* wpack; // [L][20480 rows][64]
   const float* b1p;    // [L][2 chunks][256]  gate(128) | filter(128) per chunk
+  const __half* whead; // [32 tiles][128 rows][64]: skip_projection, output_projection, input_projection packs
 };
 
 struct Workspace {
@@ -85,6 +86,7 @@ struct Workspace {
   float* Zf = nullptr;      // [B][Tp][C]  SIMT gate output
   __half* Y = nullptr;      // [2 buffers][2 planes][B][Tp][C]
   __half* CONDH = nullptr;  // [2 planes][B][Tp][H]
+  __half* S16 = nullptr;    // [2 planes][B][Tp][C] skip_sum / sqrt(L), operand of the head GEMM
   float* DTAB = nullptr;    // [rows][L][C]
   float* EMB = nullptr;     // [rows][C] scratch (mlp output)
   int64_t* TVALS = nullptr; // [rows]
@@ -111,7 +113,7 @@ struct dsx_handle {
   dsx::Workspace ws;
   int* status_dev = nullptr;   // kernel watchdog / self-check word
   int* status_host = nullptr;  // pinned mirror
-  CUtensorMap tm_w{}, tm_y[2][2]{}, tm_cond[2]{};
+  CUtensorMap tm_w{}, tm_y[2][2]{}, tm_cond[2]{}, tm_s16[2]{}, tm_whead{};
   dsx::Geom tm_geom;           // geometry the activation maps were built for
   int tm_group = 0;
   int profile = 0;
@@ -148,6 +150,12 @@ int launch_epilogue(dsx_handle* h, const float* x, const int64_t* mel2ph, const 
 int tc_pack_model(dsx_handle* h, cudaStream_t s);
 int tc_prepare_maps(dsx_handle* h, const Geom& g);
 int launch_tc_layer(dsx_handle* h, int layer, const Geom& g, int row0, int row_per_b, cudaStream_t s);
+// Head / tail of DiffNet on tensor cores.  flags: 1 = head (skip -> eps), 2 = write eps, 4 = DDPM update of x,
+// 8 = input projection of x (after the update if any) for the evaluation that uses table row (next_row0, row_per_b).
+enum { TC_HEAD = 1, TC_WRITE_EPS = 2, TC_UPDATE = 4, TC_INPROJ = 8 };
+int launch_tc_head(dsx_handle* h, const Geom& g, int flags, float* x_state, dsx_strides xs, float* eps_out,
+                   const float* noise, uint64_t seed, uint64_t offset, DdpmCoef c, int next_row0, int row_per_b,
+                   cudaStream_t s);
 bool tc_supported(const dsx_handle* h);
 
 int dev_alloc(dsx_handle* h, void** p, size_t bytes, bool model_owned);

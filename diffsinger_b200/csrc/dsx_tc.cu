@@ -31,28 +31,41 @@
 
 #include "dsx_internal.h"
 #include "dsx_ptx.cuh"
+#include "dsx_rng.cuh"
 
 namespace dsx {
 
 constexpr int kC = 256;            // residual / conditioner channels supported by this path
 constexpr int kRowsPerLayer = 80 * 256;   // wpack rows (of 64 fp16) per layer: 64 W1 tiles + 16 W2 tiles
 
-template <int G, int P>
+constexpr int kG = 2;                      // cta_group of the layer kernel (cluster of two CTAs)
+constexpr int kUnitBytes = kTile * 128;    // ring unit: 128 rows x 64 fp16 (one A k-block tile, or one CTA's half of a W tile)
+constexpr int kEpiWarps = 8;               // epilogue warps (two per TMEM lane quadrant, split by columns)
+constexpr int kThreads = 128 + kEpiWarps * 32;
+constexpr int kStageRowBytes = 48;         // epilogue-2 transpose staging: 8 fp32 + 16 B pad per row
+constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowBytes;
+
+template <int P>
 struct TcCfg {
-  static constexpr int A_BYTES = kTile * 128;                 // 128 frames x 64 fp16
-  static constexpr int W_ROWS = 256 / G;                      // rows of a weight tile held by one CTA
-  static constexpr int W_BYTES = W_ROWS * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int Z_PLANES = (P == 1) ? 1 : 2;
-  static constexpr int Z_BYTES = Z_PLANES * 4 * A_BYTES;      // z [planes][4 k-blocks][128 x 64]
-  static constexpr int STAGES = (G == 2) ? (P == 1 ? 4 : 3) : (P == 1 ? 3 : 2);
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + Z_BYTES + BAR_BYTES;
+  // GEMM1 streams through a ring of UNITS 16 KB units.  z (the A operand of GEMM2) is [planes][4 k-blocks]
+  // of 16 KB: k-blocks 0,1 (written while GEMM1 still runs) have their own buffer; k-blocks 2,3 are written
+  // after GEMM1 has finished and alias the last Z23_UNITS ring units, so GEMM2's weight ring is the first
+  // UNITS2 units only.
+  static constexpr int UNITS = (P == 1) ? 11 : 9;
+  static constexpr int Z23_UNITS = 2 * Z_PLANES;
+  static constexpr int UNITS2 = UNITS - Z23_UNITS;
+  static constexpr int Z01_BYTES = Z_PLANES * 2 * kUnitBytes;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = 1024 + UNITS * kUnitBytes + Z01_BYTES + kStagingBytes + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  // ring units consumed per k-block: GEMM1 {A_hi, W_hi [, W_lo, A_lo]}, GEMM2 {W_hi [, W_lo]}
+  static constexpr int U1 = (P == 1) ? 2 : 4;
+  static constexpr int U2 = (P == 1) ? 1 : 2;
 };
 
 struct TcLayerParams {
-  CUtensorMap tm_w;        // packed weights, 2D [rows][64]
+  CUtensorMap tm_w;        // packed weights, 2D [rows][64], box 64 x 128 rows
   CUtensorMap tm_y[2];     // this layer's conv input, planes hi/lo, 3D [B][T][256]
   CUtensorMap tm_cond[2];  // conditioner, planes hi/lo
   float* X;                // [B][Tp][256] residual stream (in/out)
@@ -67,6 +80,8 @@ struct TcLayerParams {
   int dil;
   int w_row0;              // first wpack row of this layer
   int skip_init;           // 1: skip = value, 0: skip += value
+  __half* s16;             // last layer only: fp16 split of skip_total * inv_sqrt_L, plane 1 at + plane_elems
+  float inv_sqrt_l;
   int* status;
   unsigned long long budget_ns;
   long long* trace;        // debug: [2 CTAs][3 roles][256] clock64 stamps, or nullptr
@@ -78,6 +93,7 @@ __device__ __forceinline__ float tanh_acc(float x) {
   // 2*sigmoid(2x) - 1, absolute error ~2e-7
   return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * x)), -1.f);
 }
+__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
 #define DSX_TRACE(role, slot)                                                              \
   do {                                                                                     \
@@ -85,26 +101,40 @@ __device__ __forceinline__ float tanh_acc(float x) {
       p.trace[(blockIdx.x * 3 + (role)) * 256 + (slot)] = clock64();                       \
   } while (0)
 
-template <int G, int P>
-__global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcLayerParams p) {
-  using Cfg = TcCfg<G, P>;
-  constexpr int S = Cfg::STAGES;
+// Ring bookkeeping shared by the producer and the MMA issuer: unit u lives in slot u % UNITS with
+// phase (u / UNITS) & 1.
+template <int P>
+__global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant__ TcLayerParams p) {
+  using Cfg = TcCfg<P>;
+  constexpr int G = kG;
+  constexpr int NU = Cfg::UNITS;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* zbuf = base + S * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(zbuf + Cfg::Z_BYTES);
-  uint64_t* full = bars;            // [S]
-  uint64_t* empty = bars + S;       // [S]
-  uint64_t* tfull = bars + 2 * S;   // [2]
-  uint64_t* tempty = tfull + 2;     // [2]
-  uint64_t* zfull = tempty + 2;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zfull + 1);
-  auto stageA = [&](int s) { return base + s * Cfg::STAGE_BYTES; };
-  auto stageW = [&](int s) { return base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NU2 = Cfg::UNITS2;
+  uint8_t* z01 = ring + NU * kUnitBytes;
+  uint8_t* staging = z01 + Cfg::Z01_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint64_t* full = bars;             // [NU]   GEMM1 ring
+  uint64_t* empty = full + NU;       // [NU]
+  uint64_t* full2 = empty + NU;      // [NU2]  GEMM2 weight ring (aliases ring units 0..NU2-1)
+  uint64_t* empty2 = full2 + NU2;    // [NU2]
+  uint64_t* tfull = empty2 + NU2;    // [2]
+  uint64_t* tempty = tfull + 2;      // [2]
+  uint64_t* zfull = tempty + 2;      // [1]
+  uint64_t* g1done = zfull + 1;      // [1]  all GEMM1 MMAs complete (ring units reusable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g1done + 1);
+  // z k-block address: plane 0 = hi, 1 = lo
+  auto zaddr = [&](int plane, int kb) -> uint8_t* {
+    return kb < 2 ? z01 + (plane * 2 + kb) * kUnitBytes : ring + (NU2 + plane * 2 + (kb - 2)) * kUnitBytes;
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = (G == 2) ? cluster_ctarank() : 0;
-  const int tile = blockIdx.x;      // grid is padded to a multiple of G; tiles >= p.tiles are dummies
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    DSX_TRACE(0, 250);                                           // kernel entry (clock64)
+    if (p.trace && blockIdx.x < 2) p.trace[(blockIdx.x * 3 + 1) * 256 + 250] = static_cast<long long>(globaltimer_ns());
+  }
+  const int tile = blockIdx.x;      // grid is padded to a multiple of 2; tiles >= p.tiles are dummies
   const bool tile_valid = tile < p.tiles;
   const int b = tile_valid ? tile / p.tiles_per_utt : p.B;          // b == B -> every TMA row is out of bounds
   const int t0 = tile_valid ? (tile % p.tiles_per_utt) * kTile : 0;
@@ -119,24 +149,27 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < NU; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
+    for (int s = 0; s < NU2; ++s) {
+      mbar_init(&full2[s], 1);
+      mbar_init(&empty2[s], 1);
+    }
+    mbar_init(g1done, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4 * G);
+      mbar_init(&tempty[i], kEpiWarps * G);
     }
-    mbar_init(zfull, 4 * G);
+    mbar_init(zfull, kEpiWarps * G);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<G>(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
-  if (G == 2) {
-    cluster_arrive();
-    cluster_wait();
-  }
+  cluster_arrive();
+  cluster_wait();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   Watchdog wd{p.status, globaltimer_ns() + p.budget_ns};
@@ -144,41 +177,83 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
 
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
-    uint32_t it = 0;
+    uint32_t u = 0;
     bool ok = true;
+    auto acquire = [&](int code) -> uint8_t* {
+      const int s = u % NU;
+      ok = mbar_wait(&empty[s], ((u / NU) & 1) ^ 1, wd, code);
+      if (!ok) return nullptr;
+      DSX_TRACE(0, u);
+      if (rank == 0) mbar_arrive_expect_tx(&full[s], G * kUnitBytes);
+      return ring + s * kUnitBytes;
+    };
+    auto load_a = [&](int plane, int kb) {
+      const int s = u % NU;
+      uint8_t* dst = acquire(101);
+      if (!dst) return;
+      if (kb < 12)
+        tma_load_3d<G>(&p.tm_y[plane], &full[s], dst, (kb & 3) * 64, t0 + ((kb >> 2) - 1) * p.dil, b);
+      else
+        tma_load_3d<G>(&p.tm_cond[plane], &full[s], dst, (kb - 12) * 64, t0, b);
+      ++u;
+    };
+    auto load_w = [&](int tileidx) {
+      const int s = u % NU;
+      uint8_t* dst = acquire(102);
+      if (!dst) return;
+      tma_load_2d<G>(&p.tm_w, &full[s], dst, 0, p.w_row0 + tileidx * 256 + static_cast<int>(rank) * 128);
+      ++u;
+    };
     for (int h = 0; h < 2 && ok; ++h)
-      for (int pp = 0; pp < P && ok; ++pp)
-        for (int kb = 0; kb < 16 && ok; ++kb, ++it) {
-          const int s = it % S;
-          ok = mbar_wait(&empty[s], ((it / S) & 1) ^ 1, wd, 101);
-          if (!ok) break;
-          DSX_TRACE(0, it);
-          if (rank == 0) mbar_arrive_expect_tx(&full[s], G * Cfg::STAGE_BYTES);
-          const int aplane = (pp == 2) ? 1 : 0, wplane = (pp == 1) ? 1 : 0;
-          if (kb < 12)
-            tma_load_3d<G>(&p.tm_y[aplane], &full[s], stageA(s), (kb & 3) * 64, t0 + ((kb >> 2) - 1) * p.dil, b);
-          else
-            tma_load_3d<G>(&p.tm_cond[aplane], &full[s], stageA(s), (kb - 12) * 64, t0, b);
-          const int wrow = p.w_row0 + ((wplane * 2 + h) * 16 + kb) * 256 + rank * Cfg::W_ROWS;
-          tma_load_2d<G>(&p.tm_w, &full[s], stageW(s), 0, wrow);
+      for (int kb = 0; kb < 16 && ok; ++kb) {
+        load_a(0, kb);
+        if (ok) load_w((0 * 2 + h) * 16 + kb);
+        if (P == 3) {
+          if (ok) load_w((1 * 2 + h) * 16 + kb);
+          if (ok) load_a(1, kb);
         }
+      }
+    // GEMM2 weights: second ring over units 0..NU2-1, usable once every GEMM1 MMA has completed
+    if (ok) ok = mbar_wait(g1done, 0, wd, 103);
+    uint32_t u2 = 0;
+    auto load_w2 = [&](int tileidx) {
+      const int s = u2 % NU2;
+      ok = mbar_wait(&empty2[s], ((u2 / NU2) & 1) ^ 1, wd, 104);
+      if (!ok) return;
+      DSX_TRACE(0, 128 + u2);
+      if (rank == 0) mbar_arrive_expect_tx(&full2[s], G * kUnitBytes);
+      tma_load_2d<G>(&p.tm_w, &full2[s], ring + s * kUnitBytes, 0,
+                     p.w_row0 + tileidx * 256 + static_cast<int>(rank) * 128);
+      ++u2;
+    };
     for (int q = 0; q < 2 && ok; ++q)
-      for (int pp = 0; pp < P && ok; ++pp)
-        for (int kb = 0; kb < 4 && ok; ++kb, ++it) {
-          const int s = it % S;
-          ok = mbar_wait(&empty[s], ((it / S) & 1) ^ 1, wd, 102);
-          if (!ok) break;
-          DSX_TRACE(0, it);
-          if (rank == 0) mbar_arrive_expect_tx(&full[s], G * Cfg::W_BYTES);
-          const int wplane = (pp == 1) ? 1 : 0;
-          const int wrow = p.w_row0 + (64 + (wplane * 2 + q) * 4 + kb) * 256 + rank * Cfg::W_ROWS;
-          tma_load_2d<G>(&p.tm_w, &full[s], stageW(s), 0, wrow);
-        }
+      for (int kb = 0; kb < 4 && ok; ++kb) {
+        load_w2(64 + (0 * 2 + q) * 4 + kb);
+        if (P == 3 && ok) load_w2(64 + (1 * 2 + q) * 4 + kb);
+      }
   } else if (warp == 1 && lane == 0 && rank == 0) {
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc = umma_idesc_f16(128 * G, 256);
-    uint32_t it = 0, tuse[2] = {0, 0};
+    uint32_t u = 0, tuse[2] = {0, 0};
     bool ok = true;
+    auto wait_unit = [&](uint32_t uu, int code) -> uint64_t {
+      const int s = uu % NU;
+      ok = ok && mbar_wait(&full[s], (uu / NU) & 1, wd, code);
+      return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
+    };
+    uint32_t u2 = 0;
+    auto wait_unit2 = [&](uint32_t uu, int code) -> uint64_t {
+      const int s = uu % NU2;
+      ok = ok && mbar_wait(&full2[s], (uu / NU2) & 1, wd, code);
+      return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
+    };
+    auto mma4 = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t& acc) {
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        umma_f16<G>(d, ad + 2 * k4, bd + 2 * k4, idesc, acc);
+        acc = 1;
+      }
+    };
     for (int h = 0; h < 2 && ok; ++h) {
       const int buf = h;
       ok = mbar_wait(&tempty[buf], (tuse[buf] & 1) ^ 1, wd, 201);
@@ -187,24 +262,29 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
       tc_fence_after();
       const uint32_t d = tmem_base + buf * 256;
       uint32_t acc = 0;
-      for (int pp = 0; pp < P && ok; ++pp)
-        for (int kb = 0; kb < 16 && ok; ++kb, ++it) {
-          const int s = it % S;
-          ok = mbar_wait(&full[s], (it / S) & 1, wd, 202);
+      for (int kb = 0; kb < 16 && ok; ++kb) {
+        const uint64_t a_hi = wait_unit(u, 202);
+        const uint64_t w_hi = wait_unit(u + 1, 202);
+        if (!ok) break;
+        DSX_TRACE(1, u);
+        tc_fence_after();
+        mma4(d, a_hi, w_hi, acc);
+        if (P == 3) {
+          const uint64_t w_lo = wait_unit(u + 2, 202);
           if (!ok) break;
-          DSX_TRACE(1, it);
           tc_fence_after();
-          const uint64_t ad = umma_desc_sw128(smem_u32(stageA(s)));
-          const uint64_t bd = umma_desc_sw128(smem_u32(stageW(s)));
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            umma_f16<G>(d, ad + 2 * k4, bd + 2 * k4, idesc, acc);
-            acc = 1;
-          }
-          umma_commit<G>(&empty[s]);
+          mma4(d, a_hi, w_lo, acc);
+          const uint64_t a_lo = wait_unit(u + 3, 202);
+          if (!ok) break;
+          tc_fence_after();
+          mma4(d, a_lo, w_hi, acc);
         }
+        for (int i = 0; i < Cfg::U1; ++i) umma_commit<G>(&empty[(u + i) % NU]);
+        u += Cfg::U1;
+      }
       if (ok) umma_commit<G>(&tfull[buf]);
     }
+    if (ok) umma_commit<G>(g1done);
     DSX_TRACE(1, 200);
     if (ok) ok = mbar_wait(zfull, 0, wd, 203);
     DSX_TRACE(1, 201);
@@ -218,191 +298,658 @@ __global__ void __launch_bounds__(256, 1) k_tc_layer(const __grid_constant__ TcL
       tc_fence_after();
       const uint32_t d = tmem_base + buf * 256;
       uint32_t acc = 0;
-      for (int pp = 0; pp < P && ok; ++pp)
-        for (int kb = 0; kb < 4 && ok; ++kb, ++it) {
-          const int s = it % S;
-          ok = mbar_wait(&full[s], (it / S) & 1, wd, 205);
+      for (int kb = 0; kb < 4 && ok; ++kb) {
+        const uint64_t z_hi = umma_desc_sw128(smem_u32(zaddr(0, kb)));
+        const uint64_t w_hi = wait_unit2(u2, 205);
+        if (!ok) break;
+        DSX_TRACE(1, 128 + u2);
+        tc_fence_after();
+        mma4(d, z_hi, w_hi, acc);
+        if (P == 3) {
+          const uint64_t w_lo = wait_unit2(u2 + 1, 205);
           if (!ok) break;
-          DSX_TRACE(1, it);
           tc_fence_after();
-          const int zplane = (pp == 2) ? 1 : 0;
-          const uint64_t ad = umma_desc_sw128(smem_u32(zbuf + (zplane * 4 + kb) * Cfg::A_BYTES));
-          const uint64_t bd = umma_desc_sw128(smem_u32(stageW(s)));
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            umma_f16<G>(d, ad + 2 * k4, bd + 2 * k4, idesc, acc);
-            acc = 1;
-          }
-          umma_commit<G>(&empty[s]);
+          mma4(d, z_hi, w_lo, acc);
+          const uint64_t z_lo = umma_desc_sw128(smem_u32(zaddr(1, kb)));
+          mma4(d, z_lo, w_hi, acc);
         }
+        for (int i = 0; i < Cfg::U2; ++i) umma_commit<G>(&empty2[(u2 + i) % NU2]);
+        u2 += Cfg::U2;
+      }
       if (ok) umma_commit<G>(&tfull[buf]);
     }
   } else if (warp >= 4) {
-    // ================================ epilogue ================================
-    const int quad = warp & 3;
+    // ================================ epilogue (8 warps) ================================
+    const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;               // which half of the columns
     const int r = quad * 32 + lane;                 // frame row in the tile == TMEM lane
     const uint32_t tlane = static_cast<uint32_t>(quad * 32) << 16;
-    const int t = t0 + r;
-    const bool row_valid = tile_valid && t < p.T;
-    const size_t rowoff = (static_cast<size_t>(b) * p.Tp + t) * kC;
+    const bool tracer = (warp == 4 && lane == 0);
     uint32_t tf[2] = {0, 0};
     bool ok = true;
-    // ---- epi1: gate ----
+    auto release = [&](uint64_t* bar) {
+      if (lane == 0) mbar_arrive_cluster(bar, 0);
+    };
+    // one lane polls the barrier; the warp reconverges on the shuffle
+    auto wait_warp = [&](uint64_t* bar, uint32_t parity, int code) -> bool {
+      int okv = 1;
+      if (lane == 0) okv = mbar_wait(bar, parity, wd, code) ? 1 : 0;
+      return __shfl_sync(0xffffffffu, okv, 0) != 0;
+    };
+    // ---- epi1: z = sigmoid(gate) * tanh(filter); this warp produces 64 z channels = one k-block of z ----
     for (int h = 0; h < 2 && ok; ++h) {
-      if (warp == 4 && lane == 0) DSX_TRACE(2, h * 4 + 0);
-      ok = mbar_wait(&tfull[h], tf[h] & 1, wd, 301);
+      if (tracer) DSX_TRACE(2, h * 4 + 0);
+      ok = wait_warp(&tfull[h], tf[h] & 1, 301);
       if (!ok) break;
-      if (warp == 4 && lane == 0) DSX_TRACE(2, h * 4 + 1);
+      if (tracer) DSX_TRACE(2, h * 4 + 1);
       tf[h]++;
       tc_fence_after();
-      const float* bg = p.b1p + h * 256;
+      const float* bg = p.b1p + h * 256 + half * 64;          // gate biases; filter biases at +128
+      uint8_t* zrow = zaddr(0, 2 * h + half) + r * 128;
+      uint8_t* zrow_lo = zaddr(1, 2 * h + half) + r * 128;
 #pragma unroll 1
-      for (int j = 0; j < 128; j += 32) {
+      for (int j = 0; j < 64; j += 32) {
         uint32_t g[32], f[32];
-        tmem_ld_32x32(tmem_base + tlane + h * 256 + j, g);
-        tmem_ld_32x32(tmem_base + tlane + h * 256 + 128 + j, f);
+        tmem_ld_32x32(tmem_base + tlane + h * 256 + half * 64 + j, g);
+        tmem_ld_32x32(tmem_base + tlane + h * 256 + 128 + half * 64 + j, f);
         tmem_ld_wait();
-        const int ch0 = h * 128 + j;                 // first z channel of this group
-        const int kb = ch0 >> 6;
-        uint8_t* zrow = zbuf + kb * Cfg::A_BYTES + r * 128;
-        const int chunk0 = (ch0 & 63) >> 3;
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
           uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float z2[2];
+          for (int e = 0; e < 4; e += 2) {
+            const int i = c8 * 8 + e * 2;
+            const float4 bgv = __ldg(reinterpret_cast<const float4*>(bg + j + i));
+            const float4 bfv = __ldg(reinterpret_cast<const float4*>(bg + 128 + j + i));
+            float z4[4];
+            const float vg[4] = {__uint_as_float(g[i]) + bgv.x, __uint_as_float(g[i + 1]) + bgv.y,
+                                 __uint_as_float(g[i + 2]) + bgv.z, __uint_as_float(g[i + 3]) + bgv.w};
+            const float vf[4] = {__uint_as_float(f[i]) + bfv.x, __uint_as_float(f[i + 1]) + bfv.y,
+                                 __uint_as_float(f[i + 2]) + bfv.z, __uint_as_float(f[i + 3]) + bfv.w};
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int i = c8 * 8 + e * 2 + u;
-              const float vg = __uint_as_float(g[i]) + __ldg(bg + j + i);
-              const float vf = __uint_as_float(f[i]) + __ldg(bg + 128 + j + i);
-              z2[u] = (P == 1) ? sigmoid_fast(vg) * tanh_approx(vf) : sigmoid_acc(vg) * tanh_acc(vf);
+            for (int q4 = 0; q4 < 4; ++q4)
+              z4[q4] = (P == 1) ? sigmoid_fast(vg[q4]) * tanh_approx(vf[q4]) : sigmoid_acc(vg[q4]) * tanh_acc(vf[q4]);
+            const __half2 h01 = __floats2half2_rn(z4[0], z4[1]), h23 = __floats2half2_rn(z4[2], z4[3]);
+            hi[e] = h2_bits(h01);
+            hi[e + 1] = h2_bits(h23);
+            if (P == 3) {
+              const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+              lo[e] = h2_bits(__floats2half2_rn(z4[0] - f01.x, z4[1] - f01.y));
+              lo[e + 1] = h2_bits(__floats2half2_rn(z4[2] - f23.x, z4[3] - f23.y));
             }
-            __half h0 = __float2half_rn(z2[0]), h1 = __float2half_rn(z2[1]);
-            hi[e] = pack_h2(h0, h1);
-            if (P == 3)
-              lo[e] = pack_h2(__float2half_rn(z2[0] - __half2float(h0)), __float2half_rn(z2[1] - __half2float(h1)));
           }
-          const int off = ((chunk0 + c8) ^ (r & 7)) << 4;
+          const int off = (((j >> 3) + c8) ^ (r & 7)) << 4;
           *reinterpret_cast<uint4*>(zrow + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (P == 3)
-            *reinterpret_cast<uint4*>(zrow + 4 * Cfg::A_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          if (P == 3) *reinterpret_cast<uint4*>(zrow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (warp == 4 && lane == 0) DSX_TRACE(2, h * 4 + 2);
-      if (lane == 0) {
-        if (G == 2) {
-          mbar_arrive_cluster(&tempty[h], 0);
-          if (h == 1) mbar_arrive_cluster(zfull, 0);
-        } else {
-          mbar_arrive(&tempty[h]);
-          if (h == 1) mbar_arrive(zfull);
-        }
-      }
+      if (tracer) DSX_TRACE(2, h * 4 + 2);
+      release(&tempty[h]);
+      if (h == 1) release(zfull);
     }
-    // ---- epi2, residual half: x <- (x + o + b)/sqrt2 ; y_next ----
-    if (warp == 4 && lane == 0) DSX_TRACE(2, 8);
-    if (ok) ok = mbar_wait(&tfull[0], tf[0] & 1, wd, 302);
-    if (warp == 4 && lane == 0) DSX_TRACE(2, 9);
-    if (ok) {
-      tf[0]++;
-      tc_fence_after();
-      const float* dn = p.dnext ? p.dnext + static_cast<size_t>(tile_valid ? b : 0) * p.d_row_stride : nullptr;
-#pragma unroll 1
-      for (int j = 0; j < 256; j += 32) {
-        uint32_t o[32];
-        tmem_ld_32x32(tmem_base + tlane + j, o);
-        tmem_ld_wait();
-        if (row_valid) {
-          float4* xp = reinterpret_cast<float4*>(p.X + rowoff + j);
-          float xn[32];
+    // ---- epi2: transpose 8-column slices through shared memory so global accesses are row-contiguous ----
+    uint8_t* stg = staging + (warp - 4) * 32 * kStageRowBytes;
+    const int lrow = lane >> 2, lcol = (lane & 3) * 2;        // reader mapping: 8 rows x 4 float2 per pass
+    const int urow0 = tile_valid ? t0 + quad * 32 : p.T;      // first frame of this warp's 32 rows
+    for (int q = 0; q < 2 && ok; ++q) {
+      float* const gbuf = (q == 0) ? p.X : p.SKIP;
+      // skip half: plain store on layer 0, red.add on the middle layers (no read), load+add on the last layer
+      // (which also emits the head's fp16 operand)
+      const bool do_load = (q == 0) || (p.s16 != nullptr && !p.skip_init);
+      const float* dn = (q == 0 && p.dnext) ? p.dnext + static_cast<size_t>(tile_valid ? b : 0) * p.d_row_stride : nullptr;
+      // the previous x / skip values of this warp's 32 rows x 32 columns: 16 independent 8-byte loads per lane,
+      // issued before the accumulator is waited for so their L2 latency overlaps the MMA tail
+      float2 pre[4][4];
+      auto prefetch = [&](int j) {
 #pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            float4 xv = xp[v];
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + j) + v);
-            xv.x = (xv.x + (__uint_as_float(o[4 * v + 0]) + bb.x)) * 0.70710678118654752440f;
-            xv.y = (xv.y + (__uint_as_float(o[4 * v + 1]) + bb.y)) * 0.70710678118654752440f;
-            xv.z = (xv.z + (__uint_as_float(o[4 * v + 2]) + bb.z)) * 0.70710678118654752440f;
-            xv.w = (xv.w + (__uint_as_float(o[4 * v + 3]) + bb.w)) * 0.70710678118654752440f;
-            xp[v] = xv;
-            xn[4 * v + 0] = xv.x; xn[4 * v + 1] = xv.y; xn[4 * v + 2] = xv.z; xn[4 * v + 3] = xv.w;
+        for (int sl = 0; sl < 4; ++sl)
+#pragma unroll
+          for (int itr = 0; itr < 4; ++itr) {
+            const int t = urow0 + itr * 8 + lrow;
+            pre[sl][itr] = make_float2(0.f, 0.f);
+            if (do_load && t < p.T)
+              pre[sl][itr] = *reinterpret_cast<const float2*>(
+                  gbuf + (static_cast<size_t>(b) * p.Tp + t) * kC + half * 128 + j + sl * 8 + lcol);
           }
-          if (dn) {
-            __half* y0 = p.Yout + rowoff + j;
-            __half* y1 = y0 + p.plane_elems;
+      };
+      prefetch(0);
+      if (tracer) DSX_TRACE(2, 8 + 2 * q);
+      ok = wait_warp(&tfull[q], tf[q] & 1, 302 + q);
+      if (!ok) break;
+      if (tracer) DSX_TRACE(2, 9 + 2 * q);
+      tf[q]++;
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 128; j += 32) {
+        uint32_t o[32];
+        tmem_ld_32x32(tmem_base + tlane + q * 256 + half * 128 + j, o);
+        tmem_ld_wait();
+        float2 res[4][4];
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              uint32_t hi[4], lo[4];
+        for (int sl = 0; sl < 4; ++sl) {
+          const int col = half * 128 + j + sl * 8 + lcol;     // column within this 256-wide half
+          __syncwarp();
+          *reinterpret_cast<uint4*>(stg + lane * kStageRowBytes) = make_uint4(o[sl * 8], o[sl * 8 + 1], o[sl * 8 + 2], o[sl * 8 + 3]);
+          *reinterpret_cast<uint4*>(stg + lane * kStageRowBytes + 16) =
+              make_uint4(o[sl * 8 + 4], o[sl * 8 + 5], o[sl * 8 + 6], o[sl * 8 + 7]);
+          __syncwarp();
+          const float2 bias = __ldg(reinterpret_cast<const float2*>(p.b2 + q * 256 + col));
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int i = c8 * 8 + e * 2;
-                const float ya = xn[i] + __ldg(dn + j + i), yb = xn[i + 1] + __ldg(dn + j + i + 1);
-                __half ha = __float2half_rn(ya), hb = __float2half_rn(yb);
-                hi[e] = pack_h2(ha, hb);
-                lo[e] = pack_h2(__float2half_rn(ya - __half2float(ha)), __float2half_rn(yb - __half2float(hb)));
+          for (int itr = 0; itr < 4; ++itr) {
+            const float2 d = *reinterpret_cast<const float2*>(stg + (itr * 8 + lrow) * kStageRowBytes + lcol * 4);
+            float2 v = pre[sl][itr];
+            if (q == 0) {
+              v.x = (v.x + (d.x + bias.x)) * 0.70710678118654752440f;
+              v.y = (v.y + (d.y + bias.y)) * 0.70710678118654752440f;
+            } else {
+              v.x += d.x + bias.x;
+              v.y += d.y + bias.y;
+            }
+            res[sl][itr] = v;
+          }
+        }
+        if (j + 32 < 128) prefetch(j + 32);                   // next group's loads fly while this one is stored
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          const int col = half * 128 + j + sl * 8 + lcol;
+          float2 dnv = make_float2(0.f, 0.f);
+          if (dn) dnv = __ldg(reinterpret_cast<const float2*>(dn + col));
+#pragma unroll
+          for (int itr = 0; itr < 4; ++itr) {
+            const int t = urow0 + itr * 8 + lrow;
+            if (t < p.T) {
+              const size_t off = (static_cast<size_t>(b) * p.Tp + t) * kC + col;
+              const float2 v = res[sl][itr];
+              if (q == 0 || p.skip_init || p.s16) {
+                *reinterpret_cast<float2*>(gbuf + off) = v;
+              } else {
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gbuf + off), "f"(v.x), "f"(v.y) : "memory");
               }
-              reinterpret_cast<uint4*>(y0)[c8] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              if (P == 3) reinterpret_cast<uint4*>(y1)[c8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              if (q == 1 && p.s16) {
+                const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l;
+                const __half2 hh = __floats2half2_rn(sa, sb);
+                *reinterpret_cast<__half2*>(p.s16 + off) = hh;
+                if (P == 3) {
+                  const float2 hf = __half22float2(hh);
+                  *reinterpret_cast<__half2*>(p.s16 + p.plane_elems + off) = __floats2half2_rn(sa - hf.x, sb - hf.y);
+                }
+              }
+              if (dn) {
+                const float ya = v.x + dnv.x, yb = v.y + dnv.y;
+                const __half2 hh = __floats2half2_rn(ya, yb);
+                *reinterpret_cast<__half2*>(p.Yout + off) = hh;
+                if (P == 3) {
+                  const float2 hf = __half22float2(hh);
+                  *reinterpret_cast<__half2*>(p.Yout + p.plane_elems + off) = __floats2half2_rn(ya - hf.x, yb - hf.y);
+                }
+              }
             }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if (G == 2) mbar_arrive_cluster(&tempty[0], 0); else mbar_arrive(&tempty[0]);
-      }
+      release(&tempty[q]);
     }
-    // ---- epi2, skip half ----
-    if (warp == 4 && lane == 0) DSX_TRACE(2, 10);
-    if (ok) ok = mbar_wait(&tfull[1], tf[1] & 1, wd, 303);
-    if (warp == 4 && lane == 0) DSX_TRACE(2, 11);
-    if (ok) {
-      tf[1]++;
-      tc_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < 256; j += 32) {
-        uint32_t o[32];
-        tmem_ld_32x32(tmem_base + tlane + 256 + j, o);
-        tmem_ld_wait();
-        if (row_valid) {
-          float4* sp = reinterpret_cast<float4*>(p.SKIP + rowoff + j);
-#pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + 256 + j) + v);
-            float4 sv = p.skip_init ? make_float4(0.f, 0.f, 0.f, 0.f) : sp[v];
-            sv.x += __uint_as_float(o[4 * v + 0]) + bb.x;
-            sv.y += __uint_as_float(o[4 * v + 1]) + bb.y;
-            sv.z += __uint_as_float(o[4 * v + 2]) + bb.z;
-            sv.w += __uint_as_float(o[4 * v + 3]) + bb.w;
-            sp[v] = sv;
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (G == 2) mbar_arrive_cluster(&tempty[1], 0); else mbar_arrive(&tempty[1]);
-      }
-    }
+    if (tracer) DSX_TRACE(2, 12);
   }
-
-  if (warp == 4 && lane == 0) DSX_TRACE(2, 12);
   if (threadIdx.x == 0) DSX_TRACE(0, 255);
+
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (G == 2) {
-    cluster_arrive();
-    cluster_wait();
-  }
+  cluster_arrive();
+  cluster_wait();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<G>(tmem_base, 512);
+  }
+  if (threadIdx.x == 64) {
+    DSX_TRACE(0, 251);                                           // after TMEM free (clock64)
+    if (p.trace && blockIdx.x < 2) p.trace[(blockIdx.x * 3 + 1) * 256 + 251] = static_cast<long long>(globaltimer_ns());
+  }
+}
+
+// ==========================================================================================
+// Head / tail of DiffNet on tensor cores (usr/diff/net.py:115-118 and 126-130), one CTA per 128-frame tile:
+//   H1   h   = relu(W_s . (skip_sum / sqrt L) + b_s)            A = S16 planes written by the last layer
+//   H2   eps = W_out . h + b_out                                 N = 80 padded to 128
+//   mel  DDPM update of the mel state x with eps (shallow_diffusion_tts.py:134-166), thread = frame
+//   I    x0  = relu(W_in . x + b_in), y0 = fp16 split of (x0 + d_0)  -> residual stream of the NEXT evaluation
+// Any subset runs (flags); the in-projection alone starts a sampling loop or a forward call.
+// cta_group::1, UMMA M = 128, N = 128 per instruction (two column halves for the 256-wide outputs).
+// ==========================================================================================
+struct TcHeadParams {
+  CUtensorMap tm_s16[2];   // 3D [B][T][256] hi/lo
+  CUtensorMap tm_wh;       // 2D [32 tiles x 128 rows][64], box 64 x 128
+  float* x;                // mel state (in/out), addressed through xs
+  dsx_strides xs;
+  float* eps;              // [B][M][T] contiguous (TC_WRITE_EPS)
+  const float* noise;      // [B][M][T] for this step, or nullptr -> Philox
+  unsigned long long seed, offset;
+  DdpmCoef c;
+  float* X;                // [B][Tp][256]
+  __half* Y;               // conv input of layer 0, plane 0; plane 1 at + plane_elems
+  size_t plane_elems;
+  const float* bs;         // skip_projection.bias   [256]
+  const float* bf;         // output_projection.bias [M]
+  const float* bin;        // input_projection.bias  [256]
+  const float* d0;         // FiLM vector of layer 0 (row base of the evaluation being prepared)
+  int d_row_stride;
+  int T, Tp, tiles_per_utt, tiles, B, M;
+  int flags;
+  int* status;
+  unsigned long long budget_ns;
+};
+
+template <int P>
+struct HeadCfg {
+  static constexpr int UNITS = 5;
+  static constexpr int Z_PLANES = (P == 1) ? 1 : 2;
+  static constexpr int H_BYTES = Z_PLANES * 4 * kUnitBytes;
+  static constexpr int SMEM_BYTES = 1024 + UNITS * kUnitBytes + H_BYTES + kStagingBytes + 256;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+template <int P>
+__global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__ TcHeadParams p) {
+  using Cfg = HeadCfg<P>;
+  constexpr int NU = Cfg::UNITS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* hbuf = ring + NU * kUnitBytes;                       // h [planes][4 k-blocks]; x_in aliases k-blocks 0,1
+  uint8_t* staging = hbuf + Cfg::H_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint64_t* full = bars;           // [NU]
+  uint64_t* empty = full + NU;     // [NU]
+  uint64_t* tf = empty + NU;       // [3]  accumulator ready: H1, H2, I
+  uint64_t* hfull = tf + 3;        // h written
+  uint64_t* xfull = hfull + 1;     // x_in written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull + 1);
+  auto hk = [&](int plane, int kb) -> uint8_t* { return hbuf + (plane * 4 + kb) * kUnitBytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int b = tile / p.tiles_per_utt;
+  const int t0 = (tile % p.tiles_per_utt) * kTile;
+  const bool do_head = p.flags & TC_HEAD, do_in = p.flags & TC_INPROJ;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_wh);
+    tma_prefetch_desc(&p.tm_s16[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NU; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 3; ++i) mbar_init(&tf[i], 1);
+    mbar_init(hfull, kEpiWarps);
+    mbar_init(xfull, kEpiWarps);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  Watchdog wd{p.status, globaltimer_ns() + p.budget_ns};
+
+  if (warp == 0 && lane == 0) {
+    // ================================ TMA producer ================================
+    uint32_t u = 0;
+    bool ok = true;
+    auto acquire = [&](int code) -> uint8_t* {
+      const int s = u % NU;
+      ok = mbar_wait(&empty[s], ((u / NU) & 1) ^ 1, wd, code);
+      if (!ok) return nullptr;
+      mbar_arrive_expect_tx(&full[s], kUnitBytes);
+      return ring + s * kUnitBytes;
+    };
+    auto load_a = [&](int plane, int kb) {
+      const int s = u % NU;
+      uint8_t* dst = acquire(111);
+      if (!dst) return;
+      tma_load_3d<1>(&p.tm_s16[plane], &full[s], dst, kb * 64, t0, b);
+      ++u;
+    };
+    auto load_w = [&](int tileidx) {
+      const int s = u % NU;
+      uint8_t* dst = acquire(112);
+      if (!dst) return;
+      tma_load_2d<1>(&p.tm_wh, &full[s], dst, 0, tileidx * 128);
+      ++u;
+    };
+    if (do_head) {
+      for (int kb = 0; kb < 4 && ok; ++kb) {
+        load_a(0, kb);
+        if (ok) load_w((0 * 2 + 0) * 4 + kb);
+        if (ok) load_w((0 * 2 + 1) * 4 + kb);
+        if (P == 3) {
+          if (ok) load_w((1 * 2 + 0) * 4 + kb);
+          if (ok) load_w((1 * 2 + 1) * 4 + kb);
+          if (ok) load_a(1, kb);
+        }
+      }
+      for (int kb = 0; kb < 4 && ok; ++kb) {
+        load_w(16 + 0 * 4 + kb);
+        if (P == 3 && ok) load_w(16 + 1 * 4 + kb);
+      }
+    }
+    if (do_in) {
+      for (int kb = 0; kb < 2 && ok; ++kb) {
+        load_w(24 + (0 * 2 + 0) * 2 + kb);
+        if (ok) load_w(24 + (0 * 2 + 1) * 2 + kb);
+        if (P == 3) {
+          if (ok) load_w(24 + (1 * 2 + 0) * 2 + kb);
+          if (ok) load_w(24 + (1 * 2 + 1) * 2 + kb);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc = umma_idesc_f16(128, 128);
+    uint32_t u = 0;
+    bool ok = true;
+    auto wait_unit = [&](uint32_t uu, int code) -> uint64_t {
+      const int s = uu % NU;
+      ok = ok && mbar_wait(&full[s], (uu / NU) & 1, wd, code);
+      return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
+    };
+    auto mma4 = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t& acc) {
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        umma_f16<1>(d, ad + 2 * k4, bd + 2 * k4, idesc, acc);
+        acc = 1;
+      }
+    };
+    auto release = [&](int n) {
+      for (int i = 0; i < n; ++i) umma_commit<1>(&empty[(u + i) % NU]);
+      u += n;
+    };
+    if (do_head) {
+      uint32_t acc0 = 0, acc1 = 0;
+      for (int kb = 0; kb < 4 && ok; ++kb) {
+        const uint64_t a_hi = wait_unit(u, 211), w0 = wait_unit(u + 1, 211), w1 = wait_unit(u + 2, 211);
+        if (!ok) break;
+        tc_fence_after();
+        mma4(tmem_base, a_hi, w0, acc0);
+        mma4(tmem_base + 128, a_hi, w1, acc1);
+        if (P == 3) {
+          // 6 units per k-block but only 5 ring slots: free A_hi and the two W_lo units before A_lo is needed
+          const uint64_t l0 = wait_unit(u + 3, 211), l1 = wait_unit(u + 4, 211);
+          if (!ok) break;
+          tc_fence_after();
+          mma4(tmem_base, a_hi, l0, acc0);
+          mma4(tmem_base + 128, a_hi, l1, acc1);
+          umma_commit<1>(&empty[u % NU]);
+          umma_commit<1>(&empty[(u + 3) % NU]);
+          umma_commit<1>(&empty[(u + 4) % NU]);
+          const uint64_t a_lo = wait_unit(u + 5, 211);
+          if (!ok) break;
+          tc_fence_after();
+          mma4(tmem_base, a_lo, w0, acc0);
+          mma4(tmem_base + 128, a_lo, w1, acc1);
+          umma_commit<1>(&empty[(u + 1) % NU]);
+          umma_commit<1>(&empty[(u + 2) % NU]);
+          umma_commit<1>(&empty[(u + 5) % NU]);
+          u += 6;
+        } else {
+          release(3);
+        }
+      }
+      if (ok) umma_commit<1>(&tf[0]);
+      if (ok) ok = mbar_wait(hfull, 0, wd, 212);
+      tc_fence_after();
+      uint32_t acc = 0;
+      for (int kb = 0; kb < 4 && ok; ++kb) {
+        const uint64_t h_hi = umma_desc_sw128(smem_u32(hk(0, kb)));
+        const uint64_t w = wait_unit(u, 213);
+        if (!ok) break;
+        tc_fence_after();
+        mma4(tmem_base + 256, h_hi, w, acc);
+        if (P == 3) {
+          const uint64_t wl = wait_unit(u + 1, 213);
+          if (!ok) break;
+          tc_fence_after();
+          mma4(tmem_base + 256, h_hi, wl, acc);
+          mma4(tmem_base + 256, umma_desc_sw128(smem_u32(hk(1, kb))), w, acc);
+        }
+        release(P == 1 ? 1 : 2);
+      }
+      if (ok) umma_commit<1>(&tf[1]);
+    }
+    if (do_in) {
+      if (ok) ok = mbar_wait(xfull, 0, wd, 214);
+      tc_fence_after();
+      uint32_t acc0 = 0, acc1 = 0;
+      for (int kb = 0; kb < 2 && ok; ++kb) {
+        const uint64_t x_hi = umma_desc_sw128(smem_u32(hk(0, kb)));
+        const uint64_t w0 = wait_unit(u, 215), w1 = wait_unit(u + 1, 215);
+        if (!ok) break;
+        tc_fence_after();
+        mma4(tmem_base, x_hi, w0, acc0);
+        mma4(tmem_base + 128, x_hi, w1, acc1);
+        if (P == 3) {
+          const uint64_t l0 = wait_unit(u + 2, 215), l1 = wait_unit(u + 3, 215);
+          if (!ok) break;
+          tc_fence_after();
+          const uint64_t x_lo = umma_desc_sw128(smem_u32(hk(1, kb)));
+          mma4(tmem_base, x_hi, l0, acc0);
+          mma4(tmem_base + 128, x_hi, l1, acc1);
+          mma4(tmem_base, x_lo, w0, acc0);
+          mma4(tmem_base + 128, x_lo, w1, acc1);
+        }
+        release(P == 1 ? 2 : 4);
+      }
+      if (ok) umma_commit<1>(&tf[2]);
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue (8 warps) ================================
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t tlane = static_cast<uint32_t>(quad * 32) << 16;
+    const int t = t0 + r;
+    const bool row_valid = t < p.T;
+    bool ok = true;
+    auto wait_warp = [&](uint64_t* bar, uint32_t parity, int code) -> bool {
+      int okv = 1;
+      if (lane == 0) okv = mbar_wait(bar, parity, wd, code) ? 1 : 0;
+      return __shfl_sync(0xffffffffu, okv, 0) != 0;
+    };
+    if (do_head) {
+      // ---- epi-H1: h = relu(D1 + b_s) -> fp16 planes, K-major swizzled rows ----
+      ok = wait_warp(&tf[0], 0, 311);
+      if (ok) {
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < 128; j += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + tlane + half * 128 + j, v);
+          tmem_ld_wait();
+          const int ch0 = half * 128 + j, kb = ch0 >> 6, chunk0 = (ch0 & 63) >> 3;
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = c8 * 8 + e * 2;
+              const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bs + ch0 + i));
+              const float a0 = fmaxf(__uint_as_float(v[i]) + bb.x, 0.f), a1 = fmaxf(__uint_as_float(v[i + 1]) + bb.y, 0.f);
+              const __half2 hh = __floats2half2_rn(a0, a1);
+              hi[e] = h2_bits(hh);
+              if (P == 3) {
+                const float2 hf = __half22float2(hh);
+                lo[e] = h2_bits(__floats2half2_rn(a0 - hf.x, a1 - hf.y));
+              }
+            }
+            const int off = r * 128 + (((chunk0 + c8) ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(hk(0, kb) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (P == 3) *reinterpret_cast<uint4*>(hk(1, kb) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hfull);
+      }
+    }
+    // ---- mel phase: eps, DDPM update, x_in operand.  half 0: bins [0,48), half 1: bins [48,80) ----
+    if (ok && do_head) ok = wait_warp(&tf[1], 0, 312);
+    if (ok) {
+      tc_fence_after();
+      const int m_lo = half ? 48 : 0, m_hi = half ? p.M : 48;
+#pragma unroll 1
+      for (int m0 = m_lo; m0 < m_hi; m0 += 16) {
+        uint32_t e16[16];
+        if (do_head) {
+          tmem_ld_32x16(tmem_base + tlane + 256 + m0, e16);
+        }
+        float xv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          xv[i] = 0.f;
+          if (row_valid && (p.flags & (TC_UPDATE | TC_INPROJ)))
+            xv[i] = p.x[static_cast<size_t>(b) * p.xs.b + static_cast<size_t>(m0 + i) * p.xs.c + static_cast<size_t>(t) * p.xs.t];
+        }
+        if (do_head) tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int m = m0 + i;
+          const size_t idx = (static_cast<size_t>(b) * p.M + m) * p.T + t;      // contiguous [B][M][T]
+          float ev = 0.f;
+          if (do_head) ev = __uint_as_float(e16[i]) + __ldg(p.bf + m);
+          if ((p.flags & TC_WRITE_EPS) && row_valid) p.eps[idx] = ev;
+          if (p.flags & TC_UPDATE) {
+            float xr = __fsub_rn(__fmul_rn(p.c.A, xv[i]), __fmul_rn(p.c.Bc, ev));
+            xr = fminf(fmaxf(xr, -1.f), 1.f);
+            const float mean = __fadd_rn(__fmul_rn(p.c.c1, xr), __fmul_rn(p.c.c2, xv[i]));
+            float z = 0.f;
+            if (p.c.sigma != 0.f && row_valid) z = p.noise ? p.noise[idx] : philox_normal(p.seed, p.offset, idx);
+            xv[i] = __fadd_rn(mean, __fmul_rn(p.c.sigma, z));
+            if (row_valid) p.x[static_cast<size_t>(b) * p.xs.b + static_cast<size_t>(m) * p.xs.c + static_cast<size_t>(t) * p.xs.t] = xv[i];
+          }
+        }
+        if (do_in) {
+          // 16 bins = two 16-byte chunks of row r in k-block m0 >> 6
+          const int kb = m0 >> 6, chunk0 = (m0 & 63) >> 3;
+#pragma unroll
+          for (int c8 = 0; c8 < 2; ++c8) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = c8 * 8 + e * 2;
+              const float a0 = row_valid ? xv[i] : 0.f, a1 = row_valid ? xv[i + 1] : 0.f;
+              const __half2 hh = __floats2half2_rn(a0, a1);
+              hi[e] = h2_bits(hh);
+              const float2 hf = __half22float2(hh);
+              lo[e] = h2_bits(__floats2half2_rn(a0 - hf.x, a1 - hf.y));
+            }
+            const int off = r * 128 + (((chunk0 + c8) ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(hk(0, kb) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (P == 3) *reinterpret_cast<uint4*>(hk(1, kb) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+      }
+      if (do_in) {
+        if (half == 1) {
+          // zero the K padding (bins 80..127 = chunks 2..7 of k-block 1)
+#pragma unroll
+          for (int c = 2; c < 8; ++c) {
+            const int off = r * 128 + ((c ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(hk(0, 1) + off) = make_uint4(0, 0, 0, 0);
+            if (P == 3) *reinterpret_cast<uint4*>(hk(1, 1) + off) = make_uint4(0, 0, 0, 0);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xfull);
+      }
+    }
+    // ---- epi-I: x0 = relu(D3 + b_in) -> X ; y0 = split(x0 + d_0) -> Y (row-contiguous stores via the transpose staging) ----
+    if (ok && do_in) ok = wait_warp(&tf[2], 0, 313);
+    if (ok && do_in) {
+      tc_fence_after();
+      uint8_t* stg = staging + (warp - 4) * 32 * kStageRowBytes;
+      const int lrow = lane >> 2, lcol = (lane & 3) * 2;
+      const int urow0 = t0 + quad * 32;
+      const float* d0 = p.d0 + static_cast<size_t>(b) * p.d_row_stride;
+#pragma unroll 1
+      for (int j = 0; j < 128; j += 32) {
+        uint32_t o[32];
+        tmem_ld_32x32(tmem_base + tlane + half * 128 + j, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          const int col = half * 128 + j + sl * 8 + lcol;
+          __syncwarp();
+          *reinterpret_cast<uint4*>(stg + lane * kStageRowBytes) = make_uint4(o[sl * 8], o[sl * 8 + 1], o[sl * 8 + 2], o[sl * 8 + 3]);
+          *reinterpret_cast<uint4*>(stg + lane * kStageRowBytes + 16) =
+              make_uint4(o[sl * 8 + 4], o[sl * 8 + 5], o[sl * 8 + 6], o[sl * 8 + 7]);
+          __syncwarp();
+          const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bin + col));
+          const float2 dv = __ldg(reinterpret_cast<const float2*>(d0 + col));
+#pragma unroll
+          for (int itr = 0; itr < 4; ++itr) {
+            const float2 d = *reinterpret_cast<const float2*>(stg + (itr * 8 + lrow) * kStageRowBytes + lcol * 4);
+            const int tt = urow0 + itr * 8 + lrow;
+            if (tt < p.T) {
+              const size_t off = (static_cast<size_t>(b) * p.Tp + tt) * kC + col;
+              const float x0 = fmaxf(d.x + bias.x, 0.f), x1 = fmaxf(d.y + bias.y, 0.f);
+              *reinterpret_cast<float2*>(p.X + off) = make_float2(x0, x1);
+              const float ya = x0 + dv.x, yb = x1 + dv.y;
+              const __half2 hh = __floats2half2_rn(ya, yb);
+              *reinterpret_cast<__half2*>(p.Y + off) = hh;
+              if (P == 3) {
+                const float2 hf = __half22float2(hh);
+                *reinterpret_cast<__half2*>(p.Y + p.plane_elems + off) = __floats2half2_rn(ya - hf.x, yb - hf.y);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// whead tile order (128 rows x 64 k each): skip_projection [plane][row half][kb 0..3] (16 tiles),
+// output_projection [plane][kb 0..3] with rows >= M zero (8 tiles), input_projection [plane][row half][kb 0..1]
+// with k >= M zero (8 tiles).
+__global__ void k_pack_whead(const float* __restrict__ skip_w, const float* __restrict__ fin_w,
+                             const float* __restrict__ in_w, __half* __restrict__ whead, int M) {
+  const int tileidx = blockIdx.x, n = threadIdx.x;   // 128 threads = rows
+  int plane;
+  __half* dst = whead + (static_cast<size_t>(tileidx) * 128 + n) * 64;
+  for (int kk = 0; kk < 64; ++kk) {
+    float v = 0.f;
+    if (tileidx < 16) {
+      plane = tileidx / 8;
+      const int nh = (tileidx / 4) & 1, kb = tileidx & 3;
+      v = skip_w[static_cast<size_t>(nh * 128 + n) * kC + kb * 64 + kk];
+    } else if (tileidx < 24) {
+      const int u = tileidx - 16;
+      plane = u / 4;
+      const int kb = u & 3;
+      v = (n < M) ? fin_w[static_cast<size_t>(n) * kC + kb * 64 + kk] : 0.f;
+    } else {
+      const int u = tileidx - 24;
+      plane = u / 4;
+      const int nh = (u / 2) & 1, kb = u & 1;
+      const int k = kb * 64 + kk;
+      v = (k < M) ? in_w[static_cast<size_t>(nh * 128 + n) * M + k] : 0.f;
+    }
+    const __half hi = __float2half_rn(v);
+    dst[kk] = plane == 0 ? hi : __float2half_rn(v - __half2float(hi));
   }
 }
 
@@ -439,7 +986,7 @@ __global__ void k_pack_wtc(const float* __restrict__ w1f, const float* __restric
   }
 }
 
-bool tc_supported(const dsx_handle* h) { return h->m.C == kC && h->m.H == kC; }
+bool tc_supported(const dsx_handle* h) { return h->m.C == kC && h->m.H == kC && h->m.M == 80; }
 
 int tc_pack_model(dsx_handle* h, cudaStream_t s) {
   DSX_CHECK(tc_supported(h), DSX_E_INVALID, "tcgen05 path needs residual_channels == hidden_size == 256 (got %d, %d)",
@@ -455,6 +1002,12 @@ int tc_pack_model(dsx_handle* h, cudaStream_t s) {
   DSX_CUDA(cudaGetLastError());
   h->m.wpack = wpack;
   h->m.b1p = b1p;
+  __half* whead;
+  DSX_TRY(dev_alloc(h, reinterpret_cast<void**>(&whead), static_cast<size_t>(32) * 128 * 64 * sizeof(__half), true));
+  k_pack_whead<<<32, 128, 0, s>>>(h->m.skip_w, h->m.fin_w, h->m.in_w, whead, h->m.M);
+  h->launches++;
+  DSX_CUDA(cudaGetLastError());
+  h->m.whead = whead;
   return DSX_OK;
 }
 
@@ -510,12 +1063,15 @@ int tc_prepare_maps(dsx_handle* h, const Geom& g) {
   if (h->tm_geom.B == g.B && h->tm_geom.T == g.T && h->tm_base_y == h->ws.Y && h->tm_base_cond == h->ws.CONDH &&
       h->tm_group == h->tc_group)
     return DSX_OK;
-  DSX_TRY(make_map_2d(&h->tm_w, h->m.wpack, static_cast<uint64_t>(h->m.L) * kRowsPerLayer, 256 / h->tc_group));
+  DSX_TRY(make_map_2d(&h->tm_w, h->m.wpack, static_cast<uint64_t>(h->m.L) * kRowsPerLayer, 128));
   for (int buf = 0; buf < 2; ++buf)
     for (int pl = 0; pl < 2; ++pl)
       DSX_TRY(make_map_act(&h->tm_y[buf][pl], h->ws.Y + (static_cast<size_t>(buf) * 2 + pl) * plane, kC, g.T, g.Tp, g.B));
-  for (int pl = 0; pl < 2; ++pl)
+  for (int pl = 0; pl < 2; ++pl) {
     DSX_TRY(make_map_act(&h->tm_cond[pl], h->ws.CONDH + static_cast<size_t>(pl) * plane, kC, g.T, g.Tp, g.B));
+    DSX_TRY(make_map_act(&h->tm_s16[pl], h->ws.S16 + static_cast<size_t>(pl) * plane, kC, g.T, g.Tp, g.B));
+  }
+  DSX_TRY(make_map_2d(&h->tm_whead, h->m.whead, 32 * 128, 128));
   h->tm_geom = g;
   h->tm_base_y = h->ws.Y;
   h->tm_base_cond = h->ws.CONDH;
@@ -523,27 +1079,27 @@ int tc_prepare_maps(dsx_handle* h, const Geom& g) {
   return DSX_OK;
 }
 
-template <int G, int P>
+template <int P>
 static int launch_tc_layer_t(dsx_handle* h, const TcLayerParams& prm, int tiles, cudaStream_t s) {
-  using Cfg = TcCfg<G, P>;
+  using Cfg = TcCfg<P>;
   static bool attr_done = false;
   if (!attr_done) {
-    DSX_CUDA(cudaFuncSetAttribute(k_tc_layer<G, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DSX_CUDA(cudaFuncSetAttribute(k_tc_layer<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>((tiles + G - 1) / G * G));
-  cfg.blockDim = dim3(256);
+  cfg.gridDim = dim3(static_cast<unsigned>((tiles + kG - 1) / kG * kG));
+  cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = G;
+  attr[0].val.clusterDim.x = kG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DSX_CUDA(cudaLaunchKernelEx(&cfg, k_tc_layer<G, P>, prm));
+  DSX_CUDA(cudaLaunchKernelEx(&cfg, k_tc_layer<P>, prm));
   h->launches++;
   return DSX_OK;
 }
@@ -570,14 +1126,57 @@ int launch_tc_layer(dsx_handle* h, int layer, const Geom& g, int row0, int row_p
   prm.dil = 1 << (layer % m.cycle);
   prm.w_row0 = layer * kRowsPerLayer;
   prm.skip_init = (layer == 0);
+  prm.s16 = (layer == m.L - 1) ? h->ws.S16 : nullptr;
+  prm.inv_sqrt_l = 1.0f / sqrtf(static_cast<float>(m.L));
   prm.status = h->status_dev;
   prm.budget_ns = 2000000000ull;
   prm.trace = h->trace_dev;
-  const int P = (h->precision == DSX_PREC_FP16) ? 1 : 3;
-  if (h->tc_group == 2) {
-    return P == 1 ? launch_tc_layer_t<2, 1>(h, prm, g.tiles, s) : launch_tc_layer_t<2, 3>(h, prm, g.tiles, s);
+  return (h->precision == DSX_PREC_FP16) ? launch_tc_layer_t<1>(h, prm, g.tiles, s) : launch_tc_layer_t<3>(h, prm, g.tiles, s);
+}
+
+template <int P>
+static int launch_tc_head_t(dsx_handle* h, const TcHeadParams& prm, int tiles, cudaStream_t s) {
+  using Cfg = HeadCfg<P>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DSX_CUDA(cudaFuncSetAttribute(k_tc_head<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
   }
-  return P == 1 ? launch_tc_layer_t<1, 1>(h, prm, g.tiles, s) : launch_tc_layer_t<1, 3>(h, prm, g.tiles, s);
+  k_tc_head<P><<<tiles, kThreads, Cfg::SMEM_BYTES, s>>>(prm);
+  h->launches++;
+  DSX_CUDA(cudaGetLastError());
+  return DSX_OK;
+}
+
+int launch_tc_head(dsx_handle* h, const Geom& g, int flags, float* x_state, dsx_strides xs, float* eps_out,
+                   const float* noise, uint64_t seed, uint64_t offset, DdpmCoef c, int next_row0, int row_per_b,
+                   cudaStream_t s) {
+  const ModelDev& m = h->m;
+  TcHeadParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.tm_s16[0] = h->tm_s16[0];
+  prm.tm_s16[1] = h->tm_s16[1];
+  prm.tm_wh = h->tm_whead;
+  prm.x = x_state;
+  prm.xs = xs;
+  prm.eps = eps_out;
+  prm.noise = noise;
+  prm.seed = seed;
+  prm.offset = offset;
+  prm.c = c;
+  prm.X = h->ws.X;
+  prm.Y = h->ws.Y;                       // layer 0 reads buffer 0
+  prm.plane_elems = g.frames_padded() * kC;
+  prm.bs = m.skip_b;
+  prm.bf = m.fin_b;
+  prm.bin = m.in_b;
+  prm.d0 = h->ws.DTAB + static_cast<size_t>(next_row0) * m.L * kC;
+  prm.d_row_stride = row_per_b * m.L * kC;
+  prm.T = g.T; prm.Tp = g.Tp; prm.tiles_per_utt = g.tiles_per_utt; prm.tiles = g.tiles; prm.B = g.B; prm.M = m.M;
+  prm.flags = flags;
+  prm.status = h->status_dev;
+  prm.budget_ns = 2000000000ull;
+  return (h->precision == DSX_PREC_FP16) ? launch_tc_head_t<1>(h, prm, g.tiles, s) : launch_tc_head_t<3>(h, prm, g.tiles, s);
 }
 
 }  // namespace dsx

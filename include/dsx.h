@@ -167,7 +167,7 @@ enum {
 /* Tuning knobs (tests exercise every variant): */
 int dsx_set_option(dsx_handle* h, int what, int64_t value);
 enum {
-  DSX_OPT_TC_CTA_GROUP = 0, /* 1 | 2                                                  */
+  DSX_OPT_TC_CTA_GROUP = 0, /* 2 (the layer kernel pairs CTAs; kept for forward compatibility) */
   DSX_OPT_USE_GRAPH = 1,    /* capture each sampling loop into a CUDA graph (0 | 1)   */
   DSX_OPT_PROFILE = 2       /* 1: bracket every residual-layer kernel with CUDA events; setting it resets the sums */
 };

@@ -52,7 +52,7 @@ def test_tcgen05_selftests(dsx):
 
 
 @pytest.mark.parametrize("cycle", [1, 4])
-@pytest.mark.parametrize("prec,group", [("fp32", None), ("fp16x3", 1), ("fp16x3", 2), ("fp16", 1), ("fp16", 2)])
+@pytest.mark.parametrize("prec,group", [("fp32", None), ("fp16x3", 2), ("fp16", 2)])
 def test_diffnet_forward_golden(dsx, cycle, prec, group):
     g = golden(f"diffnet_fwd_cycle{cycle}.npz")
     s, dev = make_sampler(dsx, cycle, prec, group=group)
@@ -164,16 +164,16 @@ def test_infer_forward_golden(dsx, prec):
     assert np.all(mel[1, 60:] == 0)
 
 
-def test_strided_inputs_and_group_equivalence(dsx):
+def test_strided_inputs(dsx):
     """x arrives either contiguous or as the transposed view of [B,T,M]; cond as the transposed view of
-    [B,T,H] (SURVEY.md section 4 'layout robustness').  cta_group 1 and 2 run the same MMA sequence."""
+    [B,T,H] (SURVEY.md section 4 'layout robustness')."""
     S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
     B, T = 3, 333
     cond_bt = rs_normal(1, (B, T, 256))
     x_bt = rs_normal(2, (B, T, 80))
     t = torch.tensor([9, 0, 99])
     outs = {}
-    for group in (1, 2):
+    for group in (2,):
         s, dev = make_sampler(dsx, 1, "fp16x3", S, group=group)
         cond_view = cond_bt.to(dev).transpose(1, 2)                     # strides (256T, 1, 256)
         x_view = x_bt.to(dev).transpose(1, 2)[:, None]                  # strides (80T, 80T, 1, 80)
@@ -182,11 +182,10 @@ def test_strided_inputs_and_group_equivalence(dsx):
         assert torch.equal(a, b)
         outs[group] = a.cpu()
         s.close()
-    assert torch.equal(outs[1], outs[2])
     sd = O.build_state_dict(0)
     with torch.no_grad():
         ref = O.diffnet_forward(sd, x_bt.transpose(1, 2)[:, None], t, cond_bt.transpose(1, 2), 1)
-    assert (outs[1] - ref).abs().max() < 2e-4
+    assert (outs[2] - ref).abs().max() < 2e-4
 
 
 def test_shard_equivalence_and_determinism(dsx):

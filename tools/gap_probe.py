@@ -1,0 +1,28 @@
+"""How long does one eval take on the GPU vs the sum of its kernels?  Events around the whole eval and per layer."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, bench
+import diffsinger_b200 as dsx
+from diffsinger_b200 import _capi
+from oracle import diffnet_oracle as O
+dev = torch.device("cuda", 0)
+net = bench.make_net(dsx, dev)
+for prec in ("fp16", "fp16x3"):
+    s = dsx.DsxSampler(net, prec, 1)
+    s.ensure_weights(dev)
+    s.set_schedule(O.make_schedule(O.linear_beta_schedule(100, 0.06)))
+    cond, xT = bench.make_inputs(16, 1024, 0)
+    cond, xT = cond.to(dev).transpose(1, 2), xT.to(dev)
+    K = 20
+    for rep in range(2):
+        s.sample_ddpm(xT, cond, 100, K, seed=1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); s.sample_ddpm(xT, cond, 100, K, seed=1); e1.record(); torch.cuda.synchronize()
+    total = e0.elapsed_time(e1)
+    s.set_option(_capi.OPT_PROFILE, 1)
+    s.sample_ddpm(xT, cond, 100, K, seed=1)
+    ns, n = s.info(_capi.INFO_LAYER_KERNEL_NS), s.info(_capi.INFO_LAYER_KERNEL_LAUNCHES)
+    s.set_option(_capi.OPT_PROFILE, 0)
+    print(f"{prec}: {K} DDPM steps {total:.2f} ms -> {total/K*1e3:.0f} us/eval; layer kernels (events) {ns/1e3/n:.1f} us avg x {n//K}/eval = {ns/1e3/K:.0f} us/eval")
+    s.close()

@@ -16,7 +16,7 @@ cond = torch.randn(B, T, 256, generator=g).transpose(1, 2).to(dev)
 x = torch.randn(B, 1, 80, T, generator=g).to(dev)
 t = torch.full((B,), 50, dtype=torch.long, device=dev)
 FLOP = 21184512 * B * T
-for prec, group in (("fp32", None), ("fp16", 1), ("fp16", 2), ("fp16x3", 1), ("fp16x3", 2)):
+for prec, group in (("fp16", 2), ("fp16x3", 2)):
     s = dsx.DsxSampler(net, prec, 1)
     s.ensure_weights(dev)
     if group:

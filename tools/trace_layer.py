@@ -1,0 +1,41 @@
+"""Timeline of one residual-layer kernel launch (CTA 0/1): clock64 stamps of the producer, MMA issuer and epilogue."""
+import os, sys, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+import diffsinger_b200 as dsx
+from diffsinger_b200._capi import lib, check
+
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp16"
+group = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+dev = torch.device("cuda", 0)
+net = bench.make_net(dsx, dev)
+s = dsx.DsxSampler(net, prec, 1)
+s.ensure_weights(dev)
+s.set_option(0, group)
+cond, xT = bench.make_inputs(16, 1024, 0)
+cond, xT = cond.to(dev).transpose(1, 2), xT.to(dev)
+t = torch.full((16,), 50, dtype=torch.long, device=dev)
+for _ in range(2):
+    s.diffnet_forward(xT, t, cond)
+check(lib.dsx_debug_trace(s._h, 1, None))
+s.set_layer_limit(6)
+s.diffnet_forward(xT, t, cond)
+buf = np.zeros(6 * 256, dtype=np.int64)
+check(lib.dsx_debug_trace(s._h, 0, buf.ctypes.data_as(ctypes.c_void_p)))
+tr = buf.reshape(2, 3, 256)
+P = 1 if prec == "fp16" else 3
+U1, U2 = (2, 1) if P == 1 else (4, 2)
+for cta in (0, 1):
+    t0 = tr[cta, 0, 254]
+    rel = lambda v: int(v - t0) if v else -1
+    print(f"--- CTA {cta} ({prec}); cycles since setup done; all roles done at {rel(tr[cta,0,255])}; "
+          f"kernel entry at {rel(tr[cta,0,250])}, exit at {rel(tr[cta,0,251])}; entry->exit {(tr[cta,1,251]-tr[cta,1,250])/1e3:.1f} us (globaltimer)")
+    print("producer ring1 issue (first unit of each k-block):", [rel(v) for v in tr[cta, 0, 0:32 * U1:U1]])
+    print("producer ring2 issue:", [rel(v) for v in tr[cta, 0, 128:128 + 8 * U2]])
+    print("mma k-block start (GEMM1):", [rel(v) for v in tr[cta, 1, 0:32 * U1:U1]])
+    print("mma k-block start (GEMM2):", [rel(v) for v in tr[cta, 1, 128:128 + 8 * U2:U2]])
+    print("mma: before zfull wait, after zfull, tempty q0, q1:", [rel(v) for v in tr[cta, 1, 200:204]])
+    e = [rel(v) for v in tr[cta, 2, :13]]
+    print("epilogue: [c0 wait-start, wait-done, done] [c1 ...] res wait-start, wait-done, skip wait-start, wait-done, end:")
+    print("  ", e[0:3], e[4:7], e[8:13])
