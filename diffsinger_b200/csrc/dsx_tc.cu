@@ -27,6 +27,7 @@
 #include <string.h>
 
 #include <cmath>
+#include <type_traits>
 #include <vector>
 
 #include "dsx_internal.h"
@@ -52,12 +53,14 @@ struct TcCfg {
   // of 16 KB: k-blocks 0,1 (written while GEMM1 still runs) have their own buffer; k-blocks 2,3 are written
   // after GEMM1 has finished and alias the last Z23_UNITS ring units, so GEMM2's weight ring is the first
   // UNITS2 units only.
+  // Epilogue 2 transposes the accumulator through STG_UNITS more ring units (free once GEMM1 is done).
   static constexpr int UNITS = (P == 1) ? 11 : 9;
   static constexpr int Z23_UNITS = 2 * Z_PLANES;
-  static constexpr int UNITS2 = UNITS - Z23_UNITS;
+  static constexpr int STG_UNITS = 2;                           // 8 warps x 32 rows x 128 B
+  static constexpr int UNITS2 = UNITS - Z23_UNITS - STG_UNITS;
   static constexpr int Z01_BYTES = Z_PLANES * 2 * kUnitBytes;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = 1024 + UNITS * kUnitBytes + Z01_BYTES + kStagingBytes + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + UNITS * kUnitBytes + Z01_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   // ring units consumed per k-block: GEMM1 {A_hi, W_hi [, W_lo, A_lo]}, GEMM2 {W_hi [, W_lo]}
   static constexpr int U1 = (P == 1) ? 2 : 4;
@@ -112,8 +115,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NU2 = Cfg::UNITS2;
   uint8_t* z01 = ring + NU * kUnitBytes;
-  uint8_t* staging = z01 + Cfg::Z01_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint8_t* staging = ring + NU2 * kUnitBytes;                   // units [NU2, NU2 + 2): epilogue-2 transpose
+  uint64_t* bars = reinterpret_cast<uint64_t*>(z01 + Cfg::Z01_BYTES);
   uint64_t* full = bars;             // [NU]   GEMM1 ring
   uint64_t* empty = full + NU;       // [NU]
   uint64_t* full2 = empty + NU;      // [NU2]  GEMM2 weight ring (aliases ring units 0..NU2-1)
@@ -125,7 +128,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g1done + 1);
   // z k-block address: plane 0 = hi, 1 = lo
   auto zaddr = [&](int plane, int kb) -> uint8_t* {
-    return kb < 2 ? z01 + (plane * 2 + kb) * kUnitBytes : ring + (NU2 + plane * 2 + (kb - 2)) * kUnitBytes;
+    return kb < 2 ? z01 + (plane * 2 + kb) * kUnitBytes
+                  : ring + (NU2 + Cfg::STG_UNITS + plane * 2 + (kb - 2)) * kUnitBytes;
   };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -390,35 +394,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       release(&tempty[h]);
       if (h == 1) release(zfull);
     }
-    // ---- epi2: transpose 8-column slices through shared memory so global accesses are row-contiguous ----
-    uint8_t* stg = staging + (warp - 4) * 32 * kStageRowBytes;
-    const int lrow = lane >> 2, lcol = (lane & 3) * 2;        // reader mapping: 8 rows x 4 float2 per pass
+    // ---- epi2: each warp moves its 32 rows x 32 columns through a swizzled shared-memory tile so that every
+    //      global access instruction covers whole 128-byte row segments (2 rows x 32 columns of fp32).
+    //      All addresses are one base pointer per thread plus compile-time offsets; the row-validity test is
+    //      hoisted (only the last tile of an utterance takes the predicated path). ----
+    uint8_t* stg = staging + (warp - 4) * 4096;
+    const int lrow = lane >> 4;                               // reader: half-warp = one row
+    const int lc2 = lane & 15;                                // column pair within the 32-column group
     const int urow0 = tile_valid ? t0 + quad * 32 : p.T;      // first frame of this warp's 32 rows
-    for (int q = 0; q < 2 && ok; ++q) {
-      float* const gbuf = (q == 0) ? p.X : p.SKIP;
-      // skip half: plain store on layer 0, red.add on the middle layers (no read), load+add on the last layer
-      // (which also emits the head's fp16 operand)
-      const bool do_load = (q == 0) || (p.s16 != nullptr && !p.skip_init);
-      const float* dn = (q == 0 && p.dnext) ? p.dnext + static_cast<size_t>(tile_valid ? b : 0) * p.d_row_stride : nullptr;
-      // the previous x / skip values of this warp's 32 rows x 32 columns: 16 independent 8-byte loads per lane,
-      // issued before the accumulator is waited for so their L2 latency overlaps the MMA tail
-      float2 pre[4][4];
+    const int nrows = min(max(p.T - urow0, 0), 32);           // valid rows of this warp (warp-uniform)
+    const size_t rbase = (static_cast<size_t>(tile_valid ? b : 0) * p.Tp + (tile_valid ? t0 + quad * 32 : 0) + lrow) * kC +
+                         half * 128 + lc2 * 2;
+    const uint8_t* stg_rd = stg + lrow * 128 + (lc2 & 1) * 8;
+    auto epi2_half = [&](auto full_tag, int q) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      float* const gp = ((q == 0) ? p.X : p.SKIP) + rbase;
+      __half* const yp = p.Yout + rbase;
+      __half* const sp = p.s16 ? p.s16 + rbase : nullptr;
+      const int mode = (q == 0) ? 0 : (p.skip_init ? 1 : (p.s16 ? 2 : 3));   // 0 residual, 1 store, 2 load+add (+s16), 3 red.add
+      const bool do_load = (mode == 0 || mode == 2);
+      const float* dn = (q == 0 && p.dnext) ? p.dnext + static_cast<size_t>(tile_valid ? b : 0) * p.d_row_stride + half * 128 + lc2 * 2 : nullptr;
+      const float* bp = p.b2 + q * 256 + half * 128 + lc2 * 2;
+      float2 pre[16];
       auto prefetch = [&](int j) {
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl)
-#pragma unroll
-          for (int itr = 0; itr < 4; ++itr) {
-            const int t = urow0 + itr * 8 + lrow;
-            pre[sl][itr] = make_float2(0.f, 0.f);
-            if (do_load && t < p.T)
-              pre[sl][itr] = *reinterpret_cast<const float2*>(
-                  gbuf + (static_cast<size_t>(b) * p.Tp + t) * kC + half * 128 + j + sl * 8 + lcol);
-          }
+        for (int it = 0; it < 16; ++it) {
+          pre[it] = make_float2(0.f, 0.f);
+          if (do_load && (FULL || it * 2 + lrow < nrows)) pre[it] = *reinterpret_cast<const float2*>(gp + it * 2 * kC + j);
+        }
       };
       prefetch(0);
       if (tracer) DSX_TRACE(2, 8 + 2 * q);
-      ok = wait_warp(&tfull[q], tf[q] & 1, 302 + q);
-      if (!ok) break;
+      if (!wait_warp(&tfull[q], tf[q] & 1, 302 + q)) return false;
       if (tracer) DSX_TRACE(2, 9 + 2 * q);
       tf[q]++;
       tc_fence_after();
@@ -427,64 +434,57 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         uint32_t o[32];
         tmem_ld_32x32(tmem_base + tlane + q * 256 + half * 128 + j, o);
         tmem_ld_wait();
-        float2 res[4][4];
+        __syncwarp();
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
-          const int col = half * 128 + j + sl * 8 + lcol;     // column within this 256-wide half
-          __syncwarp();
-          *reinterpret_cast<uint4*>(stg + lane * kStageRowBytes) = make_uint4(o[sl * 8], o[sl * 8 + 1], o[sl * 8 + 2], o[sl * 8 + 3]);
-          *reinterpret_cast<uint4*>(stg + lane * kStageRowBytes + 16) =
-              make_uint4(o[sl * 8 + 4], o[sl * 8 + 5], o[sl * 8 + 6], o[sl * 8 + 7]);
-          __syncwarp();
-          const float2 bias = __ldg(reinterpret_cast<const float2*>(p.b2 + q * 256 + col));
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+              make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
+        __syncwarp();
+        const float2 bias = __ldg(reinterpret_cast<const float2*>(bp + j));
+        float2 dnv = make_float2(0.f, 0.f);
+        if (dn) dnv = __ldg(reinterpret_cast<const float2*>(dn + j));
+        float2 res[16];
 #pragma unroll
-          for (int itr = 0; itr < 4; ++itr) {
-            const float2 d = *reinterpret_cast<const float2*>(stg + (itr * 8 + lrow) * kStageRowBytes + lcol * 4);
-            float2 v = pre[sl][itr];
-            if (q == 0) {
-              v.x = (v.x + (d.x + bias.x)) * 0.70710678118654752440f;
-              v.y = (v.y + (d.y + bias.y)) * 0.70710678118654752440f;
-            } else {
-              v.x += d.x + bias.x;
-              v.y += d.y + bias.y;
-            }
-            res[sl][itr] = v;
+        for (int it = 0; it < 16; ++it) {
+          // row rr = 2*it + lrow; its 16-byte chunk (lc2 >> 1) sits at position chunk ^ (rr & 7)
+          const float2 d = *reinterpret_cast<const float2*>(stg_rd + it * 256 + ((((lc2 >> 1) ^ ((it * 2) & 7)) ^ lrow) << 4));
+          float2 v = pre[it];
+          if (mode == 0) {
+            v.x = (v.x + (d.x + bias.x)) * 0.70710678118654752440f;
+            v.y = (v.y + (d.y + bias.y)) * 0.70710678118654752440f;
+          } else {
+            v.x += d.x + bias.x;
+            v.y += d.y + bias.y;
           }
+          res[it] = v;
         }
         if (j + 32 < 128) prefetch(j + 32);                   // next group's loads fly while this one is stored
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
-          const int col = half * 128 + j + sl * 8 + lcol;
-          float2 dnv = make_float2(0.f, 0.f);
-          if (dn) dnv = __ldg(reinterpret_cast<const float2*>(dn + col));
-#pragma unroll
-          for (int itr = 0; itr < 4; ++itr) {
-            const int t = urow0 + itr * 8 + lrow;
-            if (t < p.T) {
-              const size_t off = (static_cast<size_t>(b) * p.Tp + t) * kC + col;
-              const float2 v = res[sl][itr];
-              if (q == 0 || p.skip_init || p.s16) {
-                *reinterpret_cast<float2*>(gbuf + off) = v;
-              } else {
-                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gbuf + off), "f"(v.x), "f"(v.y) : "memory");
+        for (int it = 0; it < 16; ++it) {
+          if (FULL || it * 2 + lrow < nrows) {
+            const float2 v = res[it];
+            float* g = gp + it * 2 * kC + j;
+            if (mode != 3) {
+              *reinterpret_cast<float2*>(g) = v;
+            } else {
+              asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(g), "f"(v.x), "f"(v.y) : "memory");
+            }
+            if (mode == 2) {
+              const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l;
+              const __half2 hh = __floats2half2_rn(sa, sb);
+              *reinterpret_cast<__half2*>(sp + it * 2 * kC + j) = hh;
+              if (P == 3) {
+                const float2 hf = __half22float2(hh);
+                *reinterpret_cast<__half2*>(sp + p.plane_elems + it * 2 * kC + j) = __floats2half2_rn(sa - hf.x, sb - hf.y);
               }
-              if (q == 1 && p.s16) {
-                const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l;
-                const __half2 hh = __floats2half2_rn(sa, sb);
-                *reinterpret_cast<__half2*>(p.s16 + off) = hh;
-                if (P == 3) {
-                  const float2 hf = __half22float2(hh);
-                  *reinterpret_cast<__half2*>(p.s16 + p.plane_elems + off) = __floats2half2_rn(sa - hf.x, sb - hf.y);
-                }
-              }
-              if (dn) {
-                const float ya = v.x + dnv.x, yb = v.y + dnv.y;
-                const __half2 hh = __floats2half2_rn(ya, yb);
-                *reinterpret_cast<__half2*>(p.Yout + off) = hh;
-                if (P == 3) {
-                  const float2 hf = __half22float2(hh);
-                  *reinterpret_cast<__half2*>(p.Yout + p.plane_elems + off) = __floats2half2_rn(ya - hf.x, yb - hf.y);
-                }
+            }
+            if (dn) {
+              const float ya = v.x + dnv.x, yb = v.y + dnv.y;
+              const __half2 hh = __floats2half2_rn(ya, yb);
+              *reinterpret_cast<__half2*>(yp + it * 2 * kC + j) = hh;
+              if (P == 3) {
+                const float2 hf = __half22float2(hh);
+                *reinterpret_cast<__half2*>(yp + p.plane_elems + it * 2 * kC + j) = __floats2half2_rn(ya - hf.x, yb - hf.y);
               }
             }
           }
@@ -493,7 +493,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       tc_fence_before();
       __syncwarp();
       release(&tempty[q]);
-    }
+      return true;
+    };
+    for (int q = 0; q < 2 && ok; ++q)
+      ok = (nrows == 32) ? epi2_half(std::true_type{}, q) : epi2_half(std::false_type{}, q);
     if (tracer) DSX_TRACE(2, 12);
   }
   if (threadIdx.x == 0) DSX_TRACE(0, 255);
