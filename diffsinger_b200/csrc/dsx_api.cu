@@ -35,7 +35,7 @@ int dev_alloc(dsx_handle* h, void** p, size_t bytes, bool model_owned) {
 }
 
 static void free_ws(Workspace& w) {
-  void* ptrs[] = {w.X, w.SKIP, w.CONDF, w.G1, w.Zf, w.Y, w.CONDH, w.S16, w.DTAB, w.EMB, w.TVALS, w.EPS, w.XTMP};
+  void* ptrs[] = {w.X, w.SKIP, w.CONDF, w.G1, w.Zf, w.Y, w.CONDH, w.S16, w.DTAB, w.EMB, w.TVALS, w.EPS, w.XTMP, w.XSTATE};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   w = Workspace();
@@ -74,6 +74,7 @@ int ensure_workspace(dsx_handle* h, const Geom& g, int rows) {
   const size_t mel = static_cast<size_t>(g.B) * m.M * g.T;
   DSX_TRY(A(reinterpret_cast<void**>(&w.EPS), 5 * mel * 4));
   DSX_TRY(A(reinterpret_cast<void**>(&w.XTMP), mel * 4));
+  DSX_TRY(A(reinterpret_cast<void**>(&w.XSTATE), mel * 4));
   w.g = g;
   w.rows_cap = keep_rows;
   w.bytes = total;
@@ -94,25 +95,24 @@ int check_status(dsx_handle* h, cudaStream_t s, const char* what) {
 
 static int run_layers(dsx_handle* h, const Geom& g, int row0, int row_per_b, int nl, cudaStream_t s) {
   const bool tc = h->precision != DSX_PREC_FP32_SIMT;
-  for (int l = 0; l < nl; ++l) {
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (h->profile) {
-      while (h->prof_events.size() < h->prof_used + 2) {
-        cudaEvent_t e;
-        DSX_CUDA(cudaEventCreate(&e));
-        h->prof_events.push_back(e);
-      }
-      e0 = h->prof_events[h->prof_used];
-      e1 = h->prof_events[h->prof_used + 1];
-      h->prof_used += 2;
-      DSX_CUDA(cudaEventRecord(e0, s));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profile) {
+    while (h->prof_events.size() < h->prof_used + 2) {
+      cudaEvent_t e;
+      DSX_CUDA(cudaEventCreate(&e));
+      h->prof_events.push_back(e);
     }
-    if (tc)
-      DSX_TRY(launch_tc_layer(h, l, g, row0, row_per_b, s));
-    else
-      DSX_TRY(launch_simt_layer(h, l, g, row0, row_per_b, s));
-    if (h->profile) DSX_CUDA(cudaEventRecord(e1, s));
+    e0 = h->prof_events[h->prof_used];
+    e1 = h->prof_events[h->prof_used + 1];
+    h->prof_used += 2;
+    DSX_CUDA(cudaEventRecord(e0, s));
   }
+  if (tc) {
+    DSX_TRY(launch_tc_layers(h, 0, nl, g, row0, row_per_b, s));
+  } else {
+    for (int l = 0; l < nl; ++l) DSX_TRY(launch_simt_layer(h, l, g, row0, row_per_b, s));
+  }
+  if (h->profile) DSX_CUDA(cudaEventRecord(e1, s));
   return DSX_OK;
 }
 
@@ -306,6 +306,7 @@ void dsx_destroy(dsx_handle* h) {
   free_ws(h->ws);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->trace_dev) cudaFree(h->trace_dev);
+  if (h->flags_dev) cudaFree(h->flags_dev);
   if (h->status_dev) cudaFree(h->status_dev);
   if (h->status_host) cudaFreeHost(h->status_host);
   delete h;
@@ -398,9 +399,7 @@ int dsx_infer(dsx_handle* h, const float* cond, dsx_strides cs, const float* fs2
   DSX_TRY(prepare(h, cond, cs, B, T, rows, g, s));
   const int M = h->m.M;
   const size_t mel = static_cast<size_t>(B) * M * T;
-  float* state = nullptr;   // x_t, [B,1,M,T]
-  DSX_TRY(dev_alloc(h, reinterpret_cast<void**>(&state), mel * 4, false));
-  float* x = state;
+  float* x = h->ws.XSTATE;   // x_t, [B,1,M,T]
   int rc = DSX_OK;
   if (x_start) {
     cudaError_t e = cudaMemcpyAsync(x, x_start, mel * 4, cudaMemcpyDeviceToDevice, s);
@@ -415,8 +414,6 @@ int dsx_infer(dsx_handle* h, const float* cond, dsx_strides cs, const float* fs2
                            : sample_ddpm_impl(h, x, g, K_step, K_step, step_noise, seed, s);
   if (rc == DSX_OK) rc = launch_epilogue(h, x, mel2ph, spec_min, spec_max, mel_out, B, T, M, s);
   if (rc == DSX_OK) rc = check_status(h, s, "dsx_infer");
-  cudaStreamSynchronize(s);
-  cudaFree(state);
   return rc;
 }
 
@@ -473,6 +470,8 @@ int dsx_get_info(dsx_handle* h, int what, int64_t* out) {
     case DSX_INFO_SM_COUNT: *out = h->sm_count; break;
     case DSX_INFO_TC_CTA_GROUP: *out = h->tc_group; break;
     case DSX_INFO_LAYER_KERNEL_LAUNCHES: *out = static_cast<int64_t>(h->prof_used / 2); break;
+    case DSX_INFO_STACK_MODE: *out = h->stack_mode; break;
+    case DSX_INFO_CLUSTER_OCCUPANCY: *out = h->cluster_occ; break;
     case DSX_INFO_LAYER_KERNEL_NS: {
       double total_ms = 0;
       for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
@@ -498,6 +497,7 @@ int dsx_set_option(dsx_handle* h, int what, int64_t value) {
       h->tc_group = static_cast<int>(value);
       break;
     case DSX_OPT_USE_GRAPH: h->use_graph = value ? 1 : 0; break;
+    case DSX_OPT_STACK_MODE: h->stack_mode = static_cast<int>(value); break;
     case DSX_OPT_PROFILE:
       h->profile = value ? 1 : 0;
       h->prof_used = 0;

@@ -92,6 +92,7 @@ struct Workspace {
   int64_t* TVALS = nullptr; // [rows]
   float* EPS = nullptr;     // [5][B][M][T] current + PLMS history ring
   float* XTMP = nullptr;    // [B][M][T] PLMS warm-up state
+  float* XSTATE = nullptr;  // [B][M][T] mel state of dsx_infer
   size_t bytes = 0;
 };
 
@@ -117,6 +118,12 @@ struct dsx_handle {
   dsx::Geom tm_geom;           // geometry the activation maps were built for
   int tm_group = 0;
   int profile = 0;
+  unsigned int* flags_dev = nullptr;   // per-tile publish counters of the stack kernel
+  int flags_cap = 0;
+  int flags_grid = 0;                  // grid size of the last stack launch
+  unsigned int flag_count = 0;         // value of every counter before the next stack launch
+  int cluster_occ = 0;              // max co-resident utterance clusters reported by the driver (last launch)
+  int stack_mode = 1;               // 1: all residual layers of an evaluation in one cluster-per-utterance launch
   long long* trace_dev = nullptr;   // debug timeline buffer (dsx_debug_trace)
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop), prof_used of them recorded
   size_t prof_used = 0;
@@ -149,7 +156,7 @@ int launch_epilogue(dsx_handle* h, const float* x, const int64_t* mel2ph, const 
 // ---- dsx_tc.cu ---------------------------------------------------------------------------
 int tc_pack_model(dsx_handle* h, cudaStream_t s);
 int tc_prepare_maps(dsx_handle* h, const Geom& g);
-int launch_tc_layer(dsx_handle* h, int layer, const Geom& g, int row0, int row_per_b, cudaStream_t s);
+int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int row_per_b, cudaStream_t s);
 // Head / tail of DiffNet on tensor cores.  flags: 1 = head (skip -> eps), 2 = write eps, 4 = DDPM update of x,
 // 8 = input projection of x (after the update if any) for the evaluation that uses table row (next_row0, row_per_b).
 enum { TC_HEAD = 1, TC_WRITE_EPS = 2, TC_UPDATE = 4, TC_INPROJ = 8 };

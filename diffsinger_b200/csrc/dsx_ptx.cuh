@@ -94,12 +94,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// default-semantics (release.cta) arrive on a barrier of another CTA of the cluster: enough for TMEM / shared
+// memory hand-offs inside a CTA pair (what CUTLASS's ClusterBarrier::arrive(cta_id) emits)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t a = mapa(smem_u32(bar), rank);
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(a) : "memory");
+}
 // Bounded wait.  Returns false if the watchdog expired (caller should bail out).
+template <bool CLUSTER = false>
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, const Watchdog& wd, int code) {
-  if (mbar_try_wait(bar, parity)) return true;
+  auto probe = [&]() { return CLUSTER ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity); };
+  if (probe()) return true;
   uint32_t spins = 0;
   while (true) {
-    if (mbar_try_wait(bar, parity)) return true;
+    if (probe()) return true;
     if (((++spins) & 0x3ff) == 0) {
       if (*(volatile int*)wd.status != 0) return false;
       if (globaltimer_ns() > wd.deadline_ns) {
@@ -128,16 +147,18 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
-// G = cta_group.  For G == 2 the mbarrier is the one at the same offset in cluster rank 0.
+// G = cta_group.  For G == 2 the mbarrier is the one at the same offset in the pair's leader CTA
+// (cluster rank `lead`, the even rank of the pair).
 template <int G>
-__device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, void* dst, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, void* dst, int c0, int c1,
+                                            uint32_t lead = 0) {
   if constexpr (G == 1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
   } else {
-    uint32_t lead_bar = mapa(smem_u32(bar), 0);
+    uint32_t lead_bar = mapa(smem_u32(bar), lead);
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
         "%4}], [%2];"
@@ -146,7 +167,8 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, voi
   }
 }
 template <int G>
-__device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            uint32_t lead = 0) {
   if constexpr (G == 1) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
@@ -154,7 +176,7 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, voi
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
   } else {
-    uint32_t lead_bar = mapa(smem_u32(bar), 0);
+    uint32_t lead_bar = mapa(smem_u32(bar), lead);
     asm volatile(
         "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
         "%4, %5}], [%2];"
@@ -231,14 +253,14 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // completed (implies tcgen05.fence::before_thread_sync).  G == 2: delivered to the barrier at the
 // same offset in both CTAs of the pair.
 template <int G>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint16_t pair_mask = 3) {
   if constexpr (G == 1) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
   } else {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+        ::"r"(smem_u32(bar)), "h"(pair_mask)
         : "memory");
   }
 }

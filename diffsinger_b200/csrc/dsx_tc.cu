@@ -57,7 +57,7 @@ struct TcCfg {
   static constexpr int UNITS = (P == 1) ? 11 : 9;
   static constexpr int Z23_UNITS = 2 * Z_PLANES;
   static constexpr int STG_UNITS = 2;                           // 8 warps x 32 rows x 128 B
-  static constexpr int UNITS2 = UNITS - Z23_UNITS - STG_UNITS;
+  static constexpr int UNITS2 = UNITS - Z23_UNITS - STG_UNITS;   // ring layout: [ring2 | z23 | staging]
   static constexpr int Z01_BYTES = Z_PLANES * 2 * kUnitBytes;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = 1024 + UNITS * kUnitBytes + Z01_BYTES + BAR_BYTES;
@@ -68,26 +68,26 @@ struct TcCfg {
 };
 
 struct TcLayerParams {
-  CUtensorMap tm_w;        // packed weights, 2D [rows][64], box 64 x 128 rows
-  CUtensorMap tm_y[2];     // this layer's conv input, planes hi/lo, 3D [B][T][256]
-  CUtensorMap tm_cond[2];  // conditioner, planes hi/lo
-  float* X;                // [B][Tp][256] residual stream (in/out)
-  float* SKIP;             // [B][Tp][256]
-  __half* Yout;            // next layer's conv input, plane 0; plane 1 at + plane_elems
+  CUtensorMap tm_w;          // packed weights, 2D [rows][64], box 64 x 128 rows
+  CUtensorMap tm_y[2][2];    // conv input, [buffer = layer parity][plane hi/lo], 3D [B][T][256]
+  CUtensorMap tm_cond[2];    // conditioner, planes hi/lo
+  float* X;                  // [B][Tp][256] residual stream (in/out)
+  float* SKIP;               // [B][Tp][256]
+  __half* Y;                 // [2 buffers][2 planes][plane_elems]: layer l reads buffer l&1, writes buffer (l+1)&1
   size_t plane_elems;
-  const float* b1p;        // [2][256] this layer (packed order)
-  const float* b2;         // [512]    this layer
-  const float* dnext;      // FiLM vector of the next layer (row base), or nullptr on the last layer
-  int d_row_stride;        // floats between utterances' rows in dnext
+  const float* b1p;          // [L][2][256] (packed order)
+  const float* b2;           // [L][512]
+  const float* dtab;         // FiLM table row of this evaluation: [L][256], utterance b at + b * d_row_stride
+  int d_row_stride;
   int T, Tp, tiles_per_utt, tiles, B;
-  int dil;
-  int w_row0;              // first wpack row of this layer
-  int skip_init;           // 1: skip = value, 0: skip += value
-  __half* s16;             // last layer only: fp16 split of skip_total * inv_sqrt_L, plane 1 at + plane_elems
+  int l0, l1, L, cycle;      // layers [l0, l1); dilation of layer l = 1 << (l % cycle)
+  unsigned int* flags;       // [tiles] monotonic publish counters (multi-layer launches), else nullptr
+  unsigned int flag_base;    // counter value every valid tile had when this launch started
+  __half* s16;               // fp16 split of skip_total * inv_sqrt_l (written by layer L-1), plane 1 at + plane_elems
   float inv_sqrt_l;
   int* status;
   unsigned long long budget_ns;
-  long long* trace;        // debug: [2 CTAs][3 roles][256] clock64 stamps, or nullptr
+  long long* trace;          // debug: [2 CTAs][3 roles][256] clock64 stamps, or nullptr
 };
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
@@ -98,24 +98,49 @@ __device__ __forceinline__ float tanh_acc(float x) {
 }
 __device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
+// publish / wait on a tile's counter in global memory (gpu scope)
+__device__ __forceinline__ void flag_publish(unsigned int* f) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
+}
+__device__ __forceinline__ bool flag_wait(const unsigned int* f, unsigned int target, const Watchdog& wd, int code) {
+  uint32_t spins = 0;
+  while (true) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (static_cast<int>(v - target) >= 0) return true;
+    if (((++spins) & 0xff) == 0) {
+      if (*(volatile int*)wd.status != 0) return false;
+      if (globaltimer_ns() > wd.deadline_ns) {
+        atomicCAS(wd.status, 0, code);
+        return false;
+      }
+    }
+  }
+}
+
 #define DSX_TRACE(role, slot)                                                              \
   do {                                                                                     \
     if (p.trace && blockIdx.x < 2 && (slot) < 256)                                          \
       p.trace[(blockIdx.x * 3 + (role)) * 256 + (slot)] = clock64();                       \
   } while (0)
 
-// Ring bookkeeping shared by the producer and the MMA issuer: unit u lives in slot u % UNITS with
-// phase (u / UNITS) & 1.
+// Residual layers [l0, l1) of one DiffNet evaluation.
+//
+// Multi-layer launches (l1 - l0 > 1, every CTA co-resident): the only cross-CTA dependency of the stack is that
+// layer l+1 of tile i reads the conv input y_{l+1} of tiles i-1, i, i+1 of the same utterance.  After its residual
+// epilogue every epilogue warp of a tile does a release-increment of that tile's publish counter in global memory;
+// the TMA producer of a tile acquire-polls the counters of its (up to) three source tiles before the first
+// activation load of the next layer.  No grid-wide barrier exists; weight loads run ahead of the dependency.
 template <int P>
 __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant__ TcLayerParams p) {
   using Cfg = TcCfg<P>;
   constexpr int G = kG;
   constexpr int NU = Cfg::UNITS;
+  constexpr int NU2 = Cfg::UNITS2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int NU2 = Cfg::UNITS2;
   uint8_t* z01 = ring + NU * kUnitBytes;
-  uint8_t* staging = ring + NU2 * kUnitBytes;                   // units [NU2, NU2 + 2): epilogue-2 transpose
+  uint8_t* staging = ring + (NU - Cfg::STG_UNITS) * kUnitBytes;   // last ring units: epilogue-2 transpose
   uint64_t* bars = reinterpret_cast<uint64_t*>(z01 + Cfg::Z01_BYTES);
   uint64_t* full = bars;             // [NU]   GEMM1 ring
   uint64_t* empty = full + NU;       // [NU]
@@ -123,32 +148,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   uint64_t* empty2 = full2 + NU2;    // [NU2]
   uint64_t* tfull = empty2 + NU2;    // [2]
   uint64_t* tempty = tfull + 2;      // [2]
-  uint64_t* zfull = tempty + 2;      // [1]
-  uint64_t* g1done = zfull + 1;      // [1]  all GEMM1 MMAs complete (ring units reusable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g1done + 1);
-  // z k-block address: plane 0 = hi, 1 = lo
+  uint64_t* zfull = tempty + 2;      // z complete (both CTAs of the pair)
+  uint64_t* g1done = zfull + 1;      // all GEMM1 MMAs of the layer complete
+  uint64_t* g2done = g1done + 1;     // all GEMM2 MMAs of the layer complete (ring2 / z units reusable)
+  uint64_t* edone = g2done + 1;      // this CTA's epilogue has left the staging units
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(edone + 1);
+  // z k-block address: plane 0 = hi, 1 = lo.  k-blocks 2,3 alias ring units [NU2, NU2 + Z23_UNITS)
   auto zaddr = [&](int plane, int kb) -> uint8_t* {
-    return kb < 2 ? z01 + (plane * 2 + kb) * kUnitBytes
-                  : ring + (NU2 + Cfg::STG_UNITS + plane * 2 + (kb - 2)) * kUnitBytes;
+    return kb < 2 ? z01 + (plane * 2 + kb) * kUnitBytes : ring + (NU2 + plane * 2 + (kb - 2)) * kUnitBytes;
   };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t prank = crank & 1;               // rank inside the cta_group::2 pair
+  const uint32_t lead = crank & ~1u;              // cluster rank of the pair's leader
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << lead);
   if (threadIdx.x == 0) {
     DSX_TRACE(0, 250);                                           // kernel entry (clock64)
     if (p.trace && blockIdx.x < 2) p.trace[(blockIdx.x * 3 + 1) * 256 + 250] = static_cast<long long>(globaltimer_ns());
   }
-  const int tile = blockIdx.x;      // grid is padded to a multiple of 2; tiles >= p.tiles are dummies
+  // tile -> (utterance, 128-frame tile in the utterance); the grid is padded to an even number of CTAs
+  const int tile = blockIdx.x;
   const bool tile_valid = tile < p.tiles;
-  const int b = tile_valid ? tile / p.tiles_per_utt : p.B;          // b == B -> every TMA row is out of bounds
-  const int t0 = tile_valid ? (tile % p.tiles_per_utt) * kTile : 0;
+  const int b = tile / p.tiles_per_utt, tr = tile % p.tiles_per_utt;
+  const int bq = tile_valid ? b : p.B;            // b == B -> every TMA row is out of bounds (zeros)
+  const int t0 = tile_valid ? tr * kTile : 0;
+  const bool multi = (p.l1 - p.l0 > 1);
+  const bool nb_lo = multi && tile_valid && tr > 0, nb_hi = multi && tile_valid && tr + 1 < p.tiles_per_utt;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_w);
-    tma_prefetch_desc(&p.tm_y[0]);
+    tma_prefetch_desc(&p.tm_y[0][0]);
+    tma_prefetch_desc(&p.tm_y[1][0]);
     tma_prefetch_desc(&p.tm_cond[0]);
     if (P == 3) {
-      tma_prefetch_desc(&p.tm_y[1]);
+      tma_prefetch_desc(&p.tm_y[0][1]);
+      tma_prefetch_desc(&p.tm_y[1][1]);
       tma_prefetch_desc(&p.tm_cond[1]);
     }
   }
@@ -162,6 +197,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       mbar_init(&empty2[s], 1);
     }
     mbar_init(g1done, 1);
+    mbar_init(g2done, 1);
+    mbar_init(edone, kEpiWarps);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kEpiWarps * G);
@@ -181,76 +218,91 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
-    uint32_t u = 0;
+    uint32_t pbits = 0, pbits2 = 0;                 // per-slot use parity of ring 1 / ring 2
     bool ok = true;
-    auto acquire = [&](int code) -> uint8_t* {
-      const int s = u % NU;
-      ok = mbar_wait(&empty[s], ((u / NU) & 1) ^ 1, wd, code);
-      if (!ok) return nullptr;
-      DSX_TRACE(0, u);
-      if (rank == 0) mbar_arrive_expect_tx(&full[s], G * kUnitBytes);
-      return ring + s * kUnitBytes;
-    };
-    auto load_a = [&](int plane, int kb) {
-      const int s = u % NU;
-      uint8_t* dst = acquire(101);
-      if (!dst) return;
-      if (kb < 12)
-        tma_load_3d<G>(&p.tm_y[plane], &full[s], dst, (kb & 3) * 64, t0 + ((kb >> 2) - 1) * p.dil, b);
-      else
-        tma_load_3d<G>(&p.tm_cond[plane], &full[s], dst, (kb - 12) * 64, t0, b);
-      ++u;
-    };
-    auto load_w = [&](int tileidx) {
-      const int s = u % NU;
-      uint8_t* dst = acquire(102);
-      if (!dst) return;
-      tma_load_2d<G>(&p.tm_w, &full[s], dst, 0, p.w_row0 + tileidx * 256 + static_cast<int>(rank) * 128);
-      ++u;
-    };
-    for (int h = 0; h < 2 && ok; ++h)
-      for (int kb = 0; kb < 16 && ok; ++kb) {
-        load_a(0, kb);
-        if (ok) load_w((0 * 2 + h) * 16 + kb);
-        if (P == 3) {
-          if (ok) load_w((1 * 2 + h) * 16 + kb);
-          if (ok) load_a(1, kb);
+    for (int l = p.l0; l < p.l1 && ok; ++l) {
+      const int li = l - p.l0;
+      const uint32_t prev = (li - 1) & 1;
+      const int dil = 1 << (l % p.cycle);
+      const int w_row0 = l * kRowsPerLayer;
+      const CUtensorMap* ymap = p.tm_y[l & 1];
+      bool y_ok = (li == 0) || !multi || !tile_valid, e_ok = (li == 0);
+      if (li > 0) ok = mbar_wait(g2done, prev, wd, 105);            // ring-2 / z units of the previous layer are free
+      int ul = 0;                                                   // unit index within the layer
+      auto acquire = [&](int code) -> uint8_t* {
+        const int s = ul % NU;
+        if (!e_ok && s >= NU - Cfg::STG_UNITS) {                    // staging units: previous epilogue must be done
+          ok = mbar_wait(edone, prev, wd, 106);
+          e_ok = true;
+          if (!ok) return nullptr;
         }
-      }
-    // GEMM2 weights: second ring over units 0..NU2-1, usable once every GEMM1 MMA has completed
-    if (ok) ok = mbar_wait(g1done, 0, wd, 103);
-    uint32_t u2 = 0;
-    auto load_w2 = [&](int tileidx) {
-      const int s = u2 % NU2;
-      ok = mbar_wait(&empty2[s], ((u2 / NU2) & 1) ^ 1, wd, 104);
-      if (!ok) return;
-      DSX_TRACE(0, 128 + u2);
-      if (rank == 0) mbar_arrive_expect_tx(&full2[s], G * kUnitBytes);
-      tma_load_2d<G>(&p.tm_w, &full2[s], ring + s * kUnitBytes, 0,
-                     p.w_row0 + tileidx * 256 + static_cast<int>(rank) * 128);
-      ++u2;
-    };
-    for (int q = 0; q < 2 && ok; ++q)
-      for (int kb = 0; kb < 4 && ok; ++kb) {
-        load_w2(64 + (0 * 2 + q) * 4 + kb);
-        if (P == 3 && ok) load_w2(64 + (1 * 2 + q) * 4 + kb);
-      }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
-    // ================================ MMA issuer ================================
+        ok = mbar_wait(&empty[s], ((pbits >> s) & 1) ^ 1, wd, code);
+        if (!ok) return nullptr;
+        pbits ^= 1u << s;
+        DSX_TRACE(0, ul);
+        if (prank == 0) mbar_arrive_expect_tx(&full[s], G * kUnitBytes);
+        return ring + s * kUnitBytes;
+      };
+      auto load_a = [&](int plane, int kb) {
+        if (!y_ok) {                                                // y_l of this tile and its neighbours
+          const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
+          ok = flag_wait(p.flags + tile, target, wd, 107);
+          if (ok && nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
+          if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
+          fence_proxy_async_all();
+          y_ok = true;
+          if (!ok) return;
+        }
+        const int s = ul % NU;
+        uint8_t* dst = acquire(101);
+        if (!dst) return;
+        if (kb < 12)
+          tma_load_3d<G>(&ymap[plane], &full[s], dst, (kb & 3) * 64, t0 + ((kb >> 2) - 1) * dil, bq, lead);
+        else
+          tma_load_3d<G>(&p.tm_cond[plane], &full[s], dst, (kb - 12) * 64, t0, bq, lead);
+        ++ul;
+      };
+      auto load_w = [&](int tileidx) {
+        const int s = ul % NU;
+        uint8_t* dst = acquire(102);
+        if (!dst) return;
+        tma_load_2d<G>(&p.tm_w, &full[s], dst, 0, w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
+        ++ul;
+      };
+      for (int h = 0; h < 2 && ok; ++h)
+        for (int kb = 0; kb < 16 && ok; ++kb) {
+          load_a(0, kb);
+          if (ok) load_w((0 * 2 + h) * 16 + kb);
+          if (P == 3) {
+            if (ok) load_w((1 * 2 + h) * 16 + kb);
+            if (ok) load_a(1, kb);
+          }
+        }
+      // GEMM2 weights: second ring over units 0..NU2-1, usable once every GEMM1 MMA has completed
+      if (ok) ok = mbar_wait(g1done, li & 1, wd, 103);
+      int u2 = 0;
+      auto load_w2 = [&](int tileidx) {
+        const int s = u2 % NU2;
+        ok = mbar_wait(&empty2[s], ((pbits2 >> s) & 1) ^ 1, wd, 104);
+        if (!ok) return;
+        pbits2 ^= 1u << s;
+        DSX_TRACE(0, 128 + u2);
+        if (prank == 0) mbar_arrive_expect_tx(&full2[s], G * kUnitBytes);
+        tma_load_2d<G>(&p.tm_w, &full2[s], ring + s * kUnitBytes, 0,
+                       w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
+        ++u2;
+      };
+      for (int q = 0; q < 2 && ok; ++q)
+        for (int kb = 0; kb < 4 && ok; ++kb) {
+          load_w2(64 + (0 * 2 + q) * 4 + kb);
+          if (P == 3 && ok) load_w2(64 + (1 * 2 + q) * 4 + kb);
+        }
+    }
+  } else if (warp == 1 && lane == 0 && prank == 0) {
+    // ================================ MMA issuer (pair leader) ================================
     constexpr uint32_t idesc = umma_idesc_f16(128 * G, 256);
-    uint32_t u = 0, tuse[2] = {0, 0};
+    uint32_t mbits = 0, mbits2 = 0, tuse[2] = {0, 0};
     bool ok = true;
-    auto wait_unit = [&](uint32_t uu, int code) -> uint64_t {
-      const int s = uu % NU;
-      ok = ok && mbar_wait(&full[s], (uu / NU) & 1, wd, code);
-      return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
-    };
-    uint32_t u2 = 0;
-    auto wait_unit2 = [&](uint32_t uu, int code) -> uint64_t {
-      const int s = uu % NU2;
-      ok = ok && mbar_wait(&full2[s], (uu / NU2) & 1, wd, code);
-      return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
-    };
     auto mma4 = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t& acc) {
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4) {
@@ -258,69 +310,86 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         acc = 1;
       }
     };
-    for (int h = 0; h < 2 && ok; ++h) {
-      const int buf = h;
-      ok = mbar_wait(&tempty[buf], (tuse[buf] & 1) ^ 1, wd, 201);
-      if (!ok) break;
-      tuse[buf]++;
-      tc_fence_after();
-      const uint32_t d = tmem_base + buf * 256;
-      uint32_t acc = 0;
-      for (int kb = 0; kb < 16 && ok; ++kb) {
-        const uint64_t a_hi = wait_unit(u, 202);
-        const uint64_t w_hi = wait_unit(u + 1, 202);
+    for (int l = p.l0; l < p.l1 && ok; ++l) {
+      const int li = l - p.l0;
+      int ul = 0, u2 = 0;
+      auto wait_unit = [&](int uu, int code) -> uint64_t {
+        const int s = uu % NU;
+        ok = ok && mbar_wait(&full[s], (mbits >> s) & 1, wd, code);
+        mbits ^= 1u << s;
+        return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
+      };
+      auto wait_unit2 = [&](int uu, int code) -> uint64_t {
+        const int s = uu % NU2;
+        ok = ok && mbar_wait(&full2[s], (mbits2 >> s) & 1, wd, code);
+        mbits2 ^= 1u << s;
+        return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
+      };
+      for (int h = 0; h < 2 && ok; ++h) {
+        const int buf = h;
+        ok = mbar_wait(&tempty[buf], (tuse[buf] & 1) ^ 1, wd, 201);
         if (!ok) break;
-        DSX_TRACE(1, u);
+        tuse[buf]++;
         tc_fence_after();
-        mma4(d, a_hi, w_hi, acc);
-        if (P == 3) {
-          const uint64_t w_lo = wait_unit(u + 2, 202);
+        const uint32_t d = tmem_base + buf * 256;
+        uint32_t acc = 0;
+        for (int kb = 0; kb < 16 && ok; ++kb) {
+          const uint64_t a_hi = wait_unit(ul, 202);
+          const uint64_t w_hi = wait_unit(ul + 1, 202);
           if (!ok) break;
+          DSX_TRACE(1, ul);
           tc_fence_after();
-          mma4(d, a_hi, w_lo, acc);
-          const uint64_t a_lo = wait_unit(u + 3, 202);
-          if (!ok) break;
-          tc_fence_after();
-          mma4(d, a_lo, w_hi, acc);
+          mma4(d, a_hi, w_hi, acc);
+          if (P == 3) {
+            const uint64_t w_lo = wait_unit(ul + 2, 202);
+            if (!ok) break;
+            tc_fence_after();
+            mma4(d, a_hi, w_lo, acc);
+            const uint64_t a_lo = wait_unit(ul + 3, 202);
+            if (!ok) break;
+            tc_fence_after();
+            mma4(d, a_lo, w_hi, acc);
+          }
+          for (int i = 0; i < Cfg::U1; ++i) umma_commit<G>(&empty[(ul + i) % NU], pair_mask);
+          ul += Cfg::U1;
         }
-        for (int i = 0; i < Cfg::U1; ++i) umma_commit<G>(&empty[(u + i) % NU]);
-        u += Cfg::U1;
+        if (ok) umma_commit<G>(&tfull[buf], pair_mask);
       }
-      if (ok) umma_commit<G>(&tfull[buf]);
-    }
-    if (ok) umma_commit<G>(g1done);
-    DSX_TRACE(1, 200);
-    if (ok) ok = mbar_wait(zfull, 0, wd, 203);
-    DSX_TRACE(1, 201);
-    tc_fence_after();
-    for (int q = 0; q < 2 && ok; ++q) {
-      const int buf = q;
-      ok = mbar_wait(&tempty[buf], (tuse[buf] & 1) ^ 1, wd, 204);
-      if (!ok) break;
-      DSX_TRACE(1, 202 + q);
-      tuse[buf]++;
+      if (ok) umma_commit<G>(g1done, pair_mask);
+      DSX_TRACE(1, 200);
+      if (ok) ok = mbar_wait(zfull, li & 1, wd, 203);
+      DSX_TRACE(1, 201);
       tc_fence_after();
-      const uint32_t d = tmem_base + buf * 256;
-      uint32_t acc = 0;
-      for (int kb = 0; kb < 4 && ok; ++kb) {
-        const uint64_t z_hi = umma_desc_sw128(smem_u32(zaddr(0, kb)));
-        const uint64_t w_hi = wait_unit2(u2, 205);
+      for (int q = 0; q < 2 && ok; ++q) {
+        const int buf = q;
+        ok = mbar_wait(&tempty[buf], (tuse[buf] & 1) ^ 1, wd, 204);
         if (!ok) break;
-        DSX_TRACE(1, 128 + u2);
+        DSX_TRACE(1, 202 + q);
+        tuse[buf]++;
         tc_fence_after();
-        mma4(d, z_hi, w_hi, acc);
-        if (P == 3) {
-          const uint64_t w_lo = wait_unit2(u2 + 1, 205);
+        const uint32_t d = tmem_base + buf * 256;
+        uint32_t acc = 0;
+        for (int kb = 0; kb < 4 && ok; ++kb) {
+          const uint64_t z_hi = umma_desc_sw128(smem_u32(zaddr(0, kb)));
+          const uint64_t w_hi = wait_unit2(u2, 205);
           if (!ok) break;
+          DSX_TRACE(1, 128 + u2);
           tc_fence_after();
-          mma4(d, z_hi, w_lo, acc);
-          const uint64_t z_lo = umma_desc_sw128(smem_u32(zaddr(1, kb)));
-          mma4(d, z_lo, w_hi, acc);
+          mma4(d, z_hi, w_hi, acc);
+          if (P == 3) {
+            const uint64_t w_lo = wait_unit2(u2 + 1, 205);
+            if (!ok) break;
+            tc_fence_after();
+            mma4(d, z_hi, w_lo, acc);
+            const uint64_t z_lo = umma_desc_sw128(smem_u32(zaddr(1, kb)));
+            mma4(d, z_lo, w_hi, acc);
+          }
+          for (int i = 0; i < Cfg::U2; ++i) umma_commit<G>(&empty2[(u2 + i) % NU2], pair_mask);
+          u2 += Cfg::U2;
         }
-        for (int i = 0; i < Cfg::U2; ++i) umma_commit<G>(&empty2[(u2 + i) % NU2]);
-        u2 += Cfg::U2;
+        if (ok) umma_commit<G>(&tfull[buf], pair_mask);
       }
-      if (ok) umma_commit<G>(&tfull[buf]);
+      if (ok) umma_commit<G>(g2done, pair_mask);
     }
   } else if (warp >= 4) {
     // ================================ epilogue (8 warps) ================================
@@ -331,8 +400,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
     const bool tracer = (warp == 4 && lane == 0);
     uint32_t tf[2] = {0, 0};
     bool ok = true;
-    auto release = [&](uint64_t* bar) {
-      if (lane == 0) mbar_arrive_cluster(bar, 0);
+    auto release = [&](uint64_t* bar) {             // hand a TMEM buffer / z back to the pair leader's MMA thread
+      if (lane == 0) mbar_arrive_remote(bar, lead);
     };
     // one lane polls the barrier; the warp reconverges on the shuffle
     auto wait_warp = [&](uint64_t* bar, uint32_t parity, int code) -> bool {
@@ -340,163 +409,185 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       if (lane == 0) okv = mbar_wait(bar, parity, wd, code) ? 1 : 0;
       return __shfl_sync(0xffffffffu, okv, 0) != 0;
     };
-    // ---- epi1: z = sigmoid(gate) * tanh(filter); this warp produces 64 z channels = one k-block of z ----
-    for (int h = 0; h < 2 && ok; ++h) {
-      if (tracer) DSX_TRACE(2, h * 4 + 0);
-      ok = wait_warp(&tfull[h], tf[h] & 1, 301);
-      if (!ok) break;
-      if (tracer) DSX_TRACE(2, h * 4 + 1);
-      tf[h]++;
-      tc_fence_after();
-      const float* bg = p.b1p + h * 256 + half * 64;          // gate biases; filter biases at +128
-      uint8_t* zrow = zaddr(0, 2 * h + half) + r * 128;
-      uint8_t* zrow_lo = zaddr(1, 2 * h + half) + r * 128;
-#pragma unroll 1
-      for (int j = 0; j < 64; j += 32) {
-        uint32_t g[32], f[32];
-        tmem_ld_32x32(tmem_base + tlane + h * 256 + half * 64 + j, g);
-        tmem_ld_32x32(tmem_base + tlane + h * 256 + 128 + half * 64 + j, f);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; e += 2) {
-            const int i = c8 * 8 + e * 2;
-            const float4 bgv = __ldg(reinterpret_cast<const float4*>(bg + j + i));
-            const float4 bfv = __ldg(reinterpret_cast<const float4*>(bg + 128 + j + i));
-            float z4[4];
-            const float vg[4] = {__uint_as_float(g[i]) + bgv.x, __uint_as_float(g[i + 1]) + bgv.y,
-                                 __uint_as_float(g[i + 2]) + bgv.z, __uint_as_float(g[i + 3]) + bgv.w};
-            const float vf[4] = {__uint_as_float(f[i]) + bfv.x, __uint_as_float(f[i + 1]) + bfv.y,
-                                 __uint_as_float(f[i + 2]) + bfv.z, __uint_as_float(f[i + 3]) + bfv.w};
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              z4[q4] = (P == 1) ? sigmoid_fast(vg[q4]) * tanh_approx(vf[q4]) : sigmoid_acc(vg[q4]) * tanh_acc(vf[q4]);
-            const __half2 h01 = __floats2half2_rn(z4[0], z4[1]), h23 = __floats2half2_rn(z4[2], z4[3]);
-            hi[e] = h2_bits(h01);
-            hi[e + 1] = h2_bits(h23);
-            if (P == 3) {
-              const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-              lo[e] = h2_bits(__floats2half2_rn(z4[0] - f01.x, z4[1] - f01.y));
-              lo[e + 1] = h2_bits(__floats2half2_rn(z4[2] - f23.x, z4[3] - f23.y));
-            }
-          }
-          const int off = (((j >> 3) + c8) ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(zrow + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (P == 3) *reinterpret_cast<uint4*>(zrow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-      }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (tracer) DSX_TRACE(2, h * 4 + 2);
-      release(&tempty[h]);
-      if (h == 1) release(zfull);
-    }
-    // ---- epi2: each warp moves its 32 rows x 32 columns through a swizzled shared-memory tile so that every
-    //      global access instruction covers whole 128-byte row segments (2 rows x 32 columns of fp32).
-    //      All addresses are one base pointer per thread plus compile-time offsets; the row-validity test is
-    //      hoisted (only the last tile of an utterance takes the predicated path). ----
     uint8_t* stg = staging + (warp - 4) * 4096;
-    const int lrow = lane >> 4;                               // reader: half-warp = one row
+    const int lrow = lane >> 4;                               // epi2 reader: half-warp = one row
     const int lc2 = lane & 15;                                // column pair within the 32-column group
     const int urow0 = tile_valid ? t0 + quad * 32 : p.T;      // first frame of this warp's 32 rows
     const int nrows = min(max(p.T - urow0, 0), 32);           // valid rows of this warp (warp-uniform)
     const size_t rbase = (static_cast<size_t>(tile_valid ? b : 0) * p.Tp + (tile_valid ? t0 + quad * 32 : 0) + lrow) * kC +
                          half * 128 + lc2 * 2;
     const uint8_t* stg_rd = stg + lrow * 128 + (lc2 & 1) * 8;
-    auto epi2_half = [&](auto full_tag, int q) {
-      constexpr bool FULL = decltype(full_tag)::value;
-      float* const gp = ((q == 0) ? p.X : p.SKIP) + rbase;
-      __half* const yp = p.Yout + rbase;
-      __half* const sp = p.s16 ? p.s16 + rbase : nullptr;
-      const int mode = (q == 0) ? 0 : (p.skip_init ? 1 : (p.s16 ? 2 : 3));   // 0 residual, 1 store, 2 load+add (+s16), 3 red.add
-      const bool do_load = (mode == 0 || mode == 2);
-      const float* dn = (q == 0 && p.dnext) ? p.dnext + static_cast<size_t>(tile_valid ? b : 0) * p.d_row_stride + half * 128 + lc2 * 2 : nullptr;
-      const float* bp = p.b2 + q * 256 + half * 128 + lc2 * 2;
-      float2 pre[16];
-      auto prefetch = [&](int j) {
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          pre[it] = make_float2(0.f, 0.f);
-          if (do_load && (FULL || it * 2 + lrow < nrows)) pre[it] = *reinterpret_cast<const float2*>(gp + it * 2 * kC + j);
-        }
-      };
-      prefetch(0);
-      if (tracer) DSX_TRACE(2, 8 + 2 * q);
-      if (!wait_warp(&tfull[q], tf[q] & 1, 302 + q)) return false;
-      if (tracer) DSX_TRACE(2, 9 + 2 * q);
-      tf[q]++;
-      tc_fence_after();
+
+    for (int l = p.l0; l < p.l1 && ok; ++l) {
+      const float* b1p = p.b1p + static_cast<size_t>(l) * 512;
+      const float* b2 = p.b2 + static_cast<size_t>(l) * 512;
+      const bool skip_init = (l == 0);
+      __half* const s16 = (l == p.L - 1) ? p.s16 : nullptr;
+      __half* const yout = p.Y + static_cast<size_t>(((l + 1) & 1) * 2) * p.plane_elems;
+      const float* dnext = (l + 1 < p.L) ? p.dtab + static_cast<size_t>(l + 1) * kC : nullptr;
+      // ---- epi1: z = sigmoid(gate) * tanh(filter); this warp produces 64 z channels = one k-block of z ----
+      for (int h = 0; h < 2 && ok; ++h) {
+        if (tracer) DSX_TRACE(2, h * 4 + 0);
+        ok = wait_warp(&tfull[h], tf[h] & 1, 301);
+        if (!ok) break;
+        if (tracer) DSX_TRACE(2, h * 4 + 1);
+        tf[h]++;
+        tc_fence_after();
+        const float* bg = b1p + h * 256 + half * 64;          // gate biases; filter biases at +128
+        uint8_t* zrow = zaddr(0, 2 * h + half) + r * 128;
+        uint8_t* zrow_lo = zaddr(1, 2 * h + half) + r * 128;
 #pragma unroll 1
-      for (int j = 0; j < 128; j += 32) {
-        uint32_t o[32];
-        tmem_ld_32x32(tmem_base + tlane + q * 256 + half * 128 + j, o);
-        tmem_ld_wait();
-        __syncwarp();
+        for (int j = 0; j < 64; j += 32) {
+          uint32_t g[32], f[32];
+          tmem_ld_32x32(tmem_base + tlane + h * 256 + half * 64 + j, g);
+          tmem_ld_32x32(tmem_base + tlane + h * 256 + 128 + half * 64 + j, f);
+          tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-              make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
-        __syncwarp();
-        const float2 bias = __ldg(reinterpret_cast<const float2*>(bp + j));
-        float2 dnv = make_float2(0.f, 0.f);
-        if (dn) dnv = __ldg(reinterpret_cast<const float2*>(dn + j));
-        float2 res[16];
+          for (int c8 = 0; c8 < 4; ++c8) {
+            uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          // row rr = 2*it + lrow; its 16-byte chunk (lc2 >> 1) sits at position chunk ^ (rr & 7)
-          const float2 d = *reinterpret_cast<const float2*>(stg_rd + it * 256 + ((((lc2 >> 1) ^ ((it * 2) & 7)) ^ lrow) << 4));
-          float2 v = pre[it];
-          if (mode == 0) {
-            v.x = (v.x + (d.x + bias.x)) * 0.70710678118654752440f;
-            v.y = (v.y + (d.y + bias.y)) * 0.70710678118654752440f;
-          } else {
-            v.x += d.x + bias.x;
-            v.y += d.y + bias.y;
+            for (int e = 0; e < 4; e += 2) {
+              const int i = c8 * 8 + e * 2;
+              const float4 bgv = __ldg(reinterpret_cast<const float4*>(bg + j + i));
+              const float4 bfv = __ldg(reinterpret_cast<const float4*>(bg + 128 + j + i));
+              float z4[4];
+              const float vg[4] = {__uint_as_float(g[i]) + bgv.x, __uint_as_float(g[i + 1]) + bgv.y,
+                                   __uint_as_float(g[i + 2]) + bgv.z, __uint_as_float(g[i + 3]) + bgv.w};
+              const float vf[4] = {__uint_as_float(f[i]) + bfv.x, __uint_as_float(f[i + 1]) + bfv.y,
+                                   __uint_as_float(f[i + 2]) + bfv.z, __uint_as_float(f[i + 3]) + bfv.w};
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4)
+                z4[q4] = (P == 1) ? sigmoid_fast(vg[q4]) * tanh_approx(vf[q4]) : sigmoid_acc(vg[q4]) * tanh_acc(vf[q4]);
+              const __half2 h01 = __floats2half2_rn(z4[0], z4[1]), h23 = __floats2half2_rn(z4[2], z4[3]);
+              hi[e] = h2_bits(h01);
+              hi[e + 1] = h2_bits(h23);
+              if (P == 3) {
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                lo[e] = h2_bits(__floats2half2_rn(z4[0] - f01.x, z4[1] - f01.y));
+                lo[e + 1] = h2_bits(__floats2half2_rn(z4[2] - f23.x, z4[3] - f23.y));
+              }
+            }
+            const int off = (((j >> 3) + c8) ^ (r & 7)) << 4;
+            *reinterpret_cast<uint4*>(zrow + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (P == 3) *reinterpret_cast<uint4*>(zrow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-          res[it] = v;
         }
-        if (j + 32 < 128) prefetch(j + 32);                   // next group's loads fly while this one is stored
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (tracer) DSX_TRACE(2, h * 4 + 2);
+        release(&tempty[h]);
+        if (h == 1) release(zfull);
+      }
+      // ---- epi2: each warp moves its 32 rows x 32 columns through a swizzled shared-memory tile so that every
+      //      global access instruction covers whole 128-byte row segments (2 rows x 32 columns of fp32).  All
+      //      addresses are one base pointer per thread plus compile-time offsets; the row-validity test is hoisted
+      //      (only the last tile of an utterance takes the predicated path). ----
+      auto epi2_half = [&](auto full_tag, int q) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        float* const gp = ((q == 0) ? p.X : p.SKIP) + rbase;
+        __half* const yp = yout + rbase;
+        __half* const sp = s16 ? s16 + rbase : nullptr;
+        const int mode = (q == 0) ? 0 : (skip_init ? 1 : (s16 ? 2 : 3));   // 0 residual, 1 store, 2 load+add (+s16), 3 red.add
+        const bool do_load = (mode == 0 || mode == 2);
+        const float* dn = (q == 0 && dnext) ? dnext + static_cast<size_t>(tile_valid ? b : 0) * p.d_row_stride + half * 128 + lc2 * 2 : nullptr;
+        const float* bp = b2 + q * 256 + half * 128 + lc2 * 2;
+        float2 pre[16];
+        auto prefetch = [&](int j) {
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          if (FULL || it * 2 + lrow < nrows) {
-            const float2 v = res[it];
-            float* g = gp + it * 2 * kC + j;
-            if (mode != 3) {
-              *reinterpret_cast<float2*>(g) = v;
+          for (int it = 0; it < 16; ++it) {
+            pre[it] = make_float2(0.f, 0.f);
+            if (do_load && (FULL || it * 2 + lrow < nrows)) pre[it] = *reinterpret_cast<const float2*>(gp + it * 2 * kC + j);
+          }
+        };
+        prefetch(0);
+        if (tracer) DSX_TRACE(2, 8 + 2 * q);
+        if (!wait_warp(&tfull[q], tf[q] & 1, 302 + q)) return false;
+        if (tracer) DSX_TRACE(2, 9 + 2 * q);
+        tf[q]++;
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < 128; j += 32) {
+          uint32_t o[32];
+          tmem_ld_32x32(tmem_base + tlane + q * 256 + half * 128 + j, o);
+          tmem_ld_wait();
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
+          __syncwarp();
+          const float2 bias = __ldg(reinterpret_cast<const float2*>(bp + j));
+          float2 dnv = make_float2(0.f, 0.f);
+          if (dn) dnv = __ldg(reinterpret_cast<const float2*>(dn + j));
+          float2 res[16];
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            // row rr = 2*it + lrow; its 16-byte chunk (lc2 >> 1) sits at position chunk ^ (rr & 7)
+            const float2 d = *reinterpret_cast<const float2*>(stg_rd + it * 256 + ((((lc2 >> 1) ^ ((it * 2) & 7)) ^ lrow) << 4));
+            float2 v = pre[it];
+            if (mode == 0) {
+              v.x = (v.x + (d.x + bias.x)) * 0.70710678118654752440f;
+              v.y = (v.y + (d.y + bias.y)) * 0.70710678118654752440f;
             } else {
-              asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(g), "f"(v.x), "f"(v.y) : "memory");
+              v.x += d.x + bias.x;
+              v.y += d.y + bias.y;
             }
-            if (mode == 2) {
-              const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l;
-              const __half2 hh = __floats2half2_rn(sa, sb);
-              *reinterpret_cast<__half2*>(sp + it * 2 * kC + j) = hh;
-              if (P == 3) {
-                const float2 hf = __half22float2(hh);
-                *reinterpret_cast<__half2*>(sp + p.plane_elems + it * 2 * kC + j) = __floats2half2_rn(sa - hf.x, sb - hf.y);
+            res[it] = v;
+          }
+          if (j + 32 < 128) prefetch(j + 32);                   // next group's loads fly while this one is stored
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            if (FULL || it * 2 + lrow < nrows) {
+              const float2 v = res[it];
+              float* g = gp + it * 2 * kC + j;
+              if (mode != 3) {
+                *reinterpret_cast<float2*>(g) = v;
+              } else {
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(g), "f"(v.x), "f"(v.y) : "memory");
               }
-            }
-            if (dn) {
-              const float ya = v.x + dnv.x, yb = v.y + dnv.y;
-              const __half2 hh = __floats2half2_rn(ya, yb);
-              *reinterpret_cast<__half2*>(yp + it * 2 * kC + j) = hh;
-              if (P == 3) {
-                const float2 hf = __half22float2(hh);
-                *reinterpret_cast<__half2*>(yp + p.plane_elems + it * 2 * kC + j) = __floats2half2_rn(ya - hf.x, yb - hf.y);
+              if (mode == 2) {
+                const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l;
+                const __half2 hh = __floats2half2_rn(sa, sb);
+                *reinterpret_cast<__half2*>(sp + it * 2 * kC + j) = hh;
+                if (P == 3) {
+                  const float2 hf = __half22float2(hh);
+                  *reinterpret_cast<__half2*>(sp + p.plane_elems + it * 2 * kC + j) = __floats2half2_rn(sa - hf.x, sb - hf.y);
+                }
+              }
+              if (dn) {
+                const float ya = v.x + dnv.x, yb = v.y + dnv.y;
+                const __half2 hh = __floats2half2_rn(ya, yb);
+                *reinterpret_cast<__half2*>(yp + it * 2 * kC + j) = hh;
+                if (P == 3) {
+                  const float2 hf = __half22float2(hh);
+                  *reinterpret_cast<__half2*>(yp + p.plane_elems + it * 2 * kC + j) = __floats2half2_rn(ya - hf.x, yb - hf.y);
+                }
               }
             }
           }
+        }
+        tc_fence_before();
+        __syncwarp();
+        release(&tempty[q]);
+        return true;
+      };
+      for (int q = 0; q < 2 && ok; ++q) {
+        ok = (nrows == 32) ? epi2_half(std::true_type{}, q) : epi2_half(std::false_type{}, q);
+        if (q == 0 && ok && multi && l + 1 < p.l1) {      // padding tiles publish too: all counters stay in lockstep
+          // publish y_{l+1}: generic-proxy global stores of every lane -> async-proxy (TMA) readers in this CTA and
+          // its neighbours.  Proxy fence + gpu fence per lane, warp sync, then one release-increment per warp.
+          fence_proxy_async_all();
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) flag_publish(p.flags + tile);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      release(&tempty[q]);
-      return true;
-    };
-    for (int q = 0; q < 2 && ok; ++q)
-      ok = (nrows == 32) ? epi2_half(std::true_type{}, q) : epi2_half(std::false_type{}, q);
+      if (ok && multi && l + 1 < p.l1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(edone);
+      }
+    }
     if (tracer) DSX_TRACE(2, 12);
   }
   if (threadIdx.x == 0) DSX_TRACE(0, 255);
@@ -1083,21 +1174,22 @@ int tc_prepare_maps(dsx_handle* h, const Geom& g) {
 }
 
 template <int P>
-static int launch_tc_layer_t(dsx_handle* h, const TcLayerParams& prm, int tiles, cudaStream_t s) {
+static int launch_tc_layer_t(dsx_handle* h, const TcLayerParams& prm, int grid, int csize, cudaStream_t s) {
   using Cfg = TcCfg<P>;
   static bool attr_done = false;
   if (!attr_done) {
     DSX_CUDA(cudaFuncSetAttribute(k_tc_layer<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DSX_CUDA(cudaFuncSetAttribute(k_tc_layer<P>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>((tiles + kG - 1) / kG * kG));
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kG;
+  attr[0].val.clusterDim.x = csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -1107,34 +1199,94 @@ static int launch_tc_layer_t(dsx_handle* h, const TcLayerParams& prm, int tiles,
   return DSX_OK;
 }
 
-int launch_tc_layer(dsx_handle* h, int layer, const Geom& g, int row0, int row_per_b, cudaStream_t s) {
+// Can a cluster of `csize` CTAs of the layer kernel be scheduled on this device?  (cached per size)
+template <int P>
+static int cluster_occupancy(int csize) {
+  static int cache[17] = {0};   // 0 unknown, >0 max co-resident clusters, -1 none
+  if (csize > 16) return -1;
+  if (cache[csize] == 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(csize));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = TcCfg<P>::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaFuncSetAttribute(k_tc_layer<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<P>::SMEM_BYTES);
+    cudaFuncSetAttribute(k_tc_layer<P>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, k_tc_layer<P>, &cfg);
+    if (e != cudaSuccess) cudaGetLastError();
+    cache[csize] = (e == cudaSuccess && n >= 1) ? n : -1;
+  }
+  return cache[csize];
+}
+
+static int ensure_flags(dsx_handle* h, int n) {
+  if (h->flags_cap >= n) return DSX_OK;
+  if (h->flags_dev) cudaFree(h->flags_dev);
+  h->flags_dev = nullptr;
+  DSX_CUDA(cudaMalloc(&h->flags_dev, static_cast<size_t>(n) * sizeof(unsigned int)));
+  DSX_CUDA(cudaMemset(h->flags_dev, 0, static_cast<size_t>(n) * sizeof(unsigned int)));
+  h->flags_cap = n;
+  h->flag_count = 0;
+  return DSX_OK;
+}
+
+// Layers [l0, l1) of one evaluation: a single launch when every CTA can be co-resident (stack mode), otherwise one
+// launch per layer.  Always clusters of two CTAs (cta_group::2 pairs).
+int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int row_per_b, cudaStream_t s) {
   const ModelDev& m = h->m;
   TcLayerParams prm;
   memset(&prm, 0, sizeof(prm));
-  const int cur = layer & 1;
   prm.tm_w = h->tm_w;
-  prm.tm_y[0] = h->tm_y[cur][0];
-  prm.tm_y[1] = h->tm_y[cur][1];
+  for (int bf = 0; bf < 2; ++bf)
+    for (int pl = 0; pl < 2; ++pl) prm.tm_y[bf][pl] = h->tm_y[bf][pl];
   prm.tm_cond[0] = h->tm_cond[0];
   prm.tm_cond[1] = h->tm_cond[1];
   prm.X = h->ws.X;
   prm.SKIP = h->ws.SKIP;
+  prm.Y = h->ws.Y;
   prm.plane_elems = g.frames_padded() * kC;
-  prm.Yout = h->ws.Y + static_cast<size_t>((cur ^ 1) * 2) * prm.plane_elems;
-  prm.b1p = m.b1p + static_cast<size_t>(layer) * 512;
-  prm.b2 = m.b2f + static_cast<size_t>(layer) * 512;
-  prm.dnext = (layer + 1 < m.L) ? h->ws.DTAB + (static_cast<size_t>(row0) * m.L + layer + 1) * kC : nullptr;
+  prm.b1p = m.b1p;
+  prm.b2 = m.b2f;
+  prm.dtab = h->ws.DTAB + static_cast<size_t>(row0) * m.L * kC;
   prm.d_row_stride = row_per_b * m.L * kC;
   prm.T = g.T; prm.Tp = g.Tp; prm.tiles_per_utt = g.tiles_per_utt; prm.tiles = g.tiles; prm.B = g.B;
-  prm.dil = 1 << (layer % m.cycle);
-  prm.w_row0 = layer * kRowsPerLayer;
-  prm.skip_init = (layer == 0);
-  prm.s16 = (layer == m.L - 1) ? h->ws.S16 : nullptr;
+  prm.L = m.L; prm.cycle = m.cycle;
+  prm.s16 = h->ws.S16;
   prm.inv_sqrt_l = 1.0f / sqrtf(static_cast<float>(m.L));
   prm.status = h->status_dev;
-  prm.budget_ns = 2000000000ull;
+  prm.budget_ns = 4000000000ull;
   prm.trace = h->trace_dev;
-  return (h->precision == DSX_PREC_FP16) ? launch_tc_layer_t<1>(h, prm, g.tiles, s) : launch_tc_layer_t<3>(h, prm, g.tiles, s);
+  const bool p1 = (h->precision == DSX_PREC_FP16);
+  const int grid = (g.tiles + kG - 1) / kG * kG;
+  const int occ = p1 ? cluster_occupancy<1>(kG) : cluster_occupancy<3>(kG);
+  h->cluster_occ = occ;
+  // the stack needs every CTA co-resident (tiles wait on their neighbours' publish counters)
+  const bool stack = h->stack_mode && (l1 - l0 > 1) && occ >= 1 && grid <= occ * kG;
+  if (stack) {
+    DSX_TRY(ensure_flags(h, grid));
+    if (h->flags_grid != grid) {      // counters are only in lockstep among the CTAs of one grid size
+      DSX_CUDA(cudaMemsetAsync(h->flags_dev, 0, static_cast<size_t>(h->flags_cap) * sizeof(unsigned int), s));
+      h->flag_count = 0;
+      h->flags_grid = grid;
+    }
+    prm.l0 = l0; prm.l1 = l1;
+    prm.flags = h->flags_dev;
+    prm.flag_base = h->flag_count;
+    h->flag_count += static_cast<unsigned int>(kEpiWarps * (l1 - l0 - 1));
+    return p1 ? launch_tc_layer_t<1>(h, prm, grid, kG, s) : launch_tc_layer_t<3>(h, prm, grid, kG, s);
+  }
+  for (int l = l0; l < l1; ++l) {
+    prm.l0 = l; prm.l1 = l + 1;
+    DSX_TRY(p1 ? launch_tc_layer_t<1>(h, prm, grid, kG, s) : launch_tc_layer_t<3>(h, prm, grid, kG, s));
+  }
+  return DSX_OK;
 }
 
 template <int P>

@@ -162,14 +162,19 @@ enum {
   DSX_INFO_TC_CTA_GROUP = 4,    /* 1 or 2: cta_group of the tcgen05 path in use          */
   DSX_INFO_LAYER_KERNEL_NS = 5, /* DSX_OPT_PROFILE: summed device time of the residual-layer kernels since the
                                    option was set (CUDA events on the launching stream; synchronises)     */
-  DSX_INFO_LAYER_KERNEL_LAUNCHES = 6
+  DSX_INFO_LAYER_KERNEL_LAUNCHES = 6, /* number of (start, stop) brackets = evaluations profiled */
+  DSX_INFO_STACK_MODE = 7,
+  DSX_INFO_CLUSTER_OCCUPANCY = 8 /* co-resident CTA pairs of the layer kernel reported by the driver */
 };
 /* Tuning knobs (tests exercise every variant): */
 int dsx_set_option(dsx_handle* h, int what, int64_t value);
 enum {
   DSX_OPT_TC_CTA_GROUP = 0, /* 2 (the layer kernel pairs CTAs; kept for forward compatibility) */
   DSX_OPT_USE_GRAPH = 1,    /* capture each sampling loop into a CUDA graph (0 | 1)   */
-  DSX_OPT_PROFILE = 2       /* 1: bracket every residual-layer kernel with CUDA events; setting it resets the sums */
+  DSX_OPT_PROFILE = 2,      /* 1: bracket the residual-layer kernel(s) of every evaluation with CUDA events; setting it
+                               resets the sums */
+  DSX_OPT_STACK_MODE = 3    /* 1 (default): all residual layers of an evaluation in ONE persistent launch whenever every
+                               128-frame tile can own an SM at once (tiles <= co-resident CTAs); 0: one launch per layer */
 };
 
 /* Debug taps for layer-by-layer parity (tests only): copies internal fp32 frames-major

@@ -7,9 +7,11 @@ from diffsinger_b200 import _capi
 from oracle import diffnet_oracle as O
 dev = torch.device("cuda", 0)
 net = bench.make_net(dsx, dev)
-for prec in ("fp16", "fp16x3"):
+import itertools
+for prec, mode in itertools.product(("fp16", "fp16x3"), (0, 1)):
     s = dsx.DsxSampler(net, prec, 1)
     s.ensure_weights(dev)
+    s.set_option(_capi.OPT_STACK_MODE, mode)
     s.set_schedule(O.make_schedule(O.linear_beta_schedule(100, 0.06)))
     cond, xT = bench.make_inputs(16, 1024, 0)
     cond, xT = cond.to(dev).transpose(1, 2), xT.to(dev)
@@ -24,5 +26,5 @@ for prec in ("fp16", "fp16x3"):
     s.sample_ddpm(xT, cond, 100, K, seed=1)
     ns, n = s.info(_capi.INFO_LAYER_KERNEL_NS), s.info(_capi.INFO_LAYER_KERNEL_LAUNCHES)
     s.set_option(_capi.OPT_PROFILE, 0)
-    print(f"{prec}: {K} DDPM steps {total:.2f} ms -> {total/K*1e3:.0f} us/eval; layer kernels (events) {ns/1e3/n:.1f} us avg x {n//K}/eval = {ns/1e3/K:.0f} us/eval")
+    print(f"stack_mode={mode} cluster_occ={s.info(_capi.INFO_CLUSTER_OCCUPANCY)} {prec}: {K} DDPM steps {total:.2f} ms -> {total/K*1e3:.0f} us/eval; layer stack (events) {ns/1e3/n:.1f} us per eval = {ns/1e3/n/20:.1f} us/layer")
     s.close()
