@@ -182,7 +182,7 @@ static int sample_ddpm_impl(dsx_handle* h, float* x, const Geom& g, int t_start,
       const int flags = TC_HEAD | TC_UPDATE | (j + 1 < n_steps ? TC_INPROJ : 0);
       DSX_TRY(launch_tc_head(h, g, flags, x, xs, nullptr, nz, seed, static_cast<uint64_t>(j), c, j + 1, 0, s));
     } else {
-      DSX_TRY(launch_ddpm_update(h, x, h->ws.EPS, nz, seed, static_cast<uint64_t>(j), c, mel, s));
+      DSX_TRY(launch_ddpm_update(h, x, h->ws.EPS, nz, seed, static_cast<uint64_t>(j), c, mel, g.T, s));
     }
   }
   return DSX_OK;

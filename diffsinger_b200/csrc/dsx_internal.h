@@ -143,7 +143,7 @@ int launch_simt_layer(dsx_handle* h, int layer, const Geom& g, int row0, int row
 int launch_head(dsx_handle* h, const Geom& g, float* eps, cudaStream_t s);
 struct DdpmCoef { float A, Bc, c1, c2, sigma; };
 int launch_ddpm_update(dsx_handle* h, float* x, const float* eps, const float* noise, uint64_t seed,
-                       uint64_t offset, DdpmCoef c, size_t n, cudaStream_t s);
+                       uint64_t offset, DdpmCoef c, size_t n, int T, cudaStream_t s);
 struct PlmsCoef { float kx, ke, a_diff, denom, w0, w1, w2, w3; };   // see k_plms_update
 int launch_plms_update(dsx_handle* h, float* x_out, const float* x_in, const float* e0, const float* e1,
                        const float* e2, const float* e3, PlmsCoef c, size_t n, cudaStream_t s);

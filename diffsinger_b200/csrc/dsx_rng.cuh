@@ -42,4 +42,17 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t offset, s
 }
 
 
+// Four normals from one Philox block.  Sampler noise for mel element (b, m, t) of a [B][M][T] tensor is lane (m & 3)
+// of block ((b * (M/4) + m/4) * T + t), so a thread that owns one frame draws four bins per call.
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t offset, size_t blk) {
+  uint4 ctr = make_uint4(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32),
+                         static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32));
+  uint4 r = philox4x32_10(ctr, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  float2 n01 = box_muller(r.x, r.y), n23 = box_muller(r.z, r.w);
+  return make_float4(n01.x, n01.y, n23.x, n23.y);
+}
+__device__ __forceinline__ size_t mel_noise_block(int b, int m, int t, int M, int T) {
+  return (static_cast<size_t>(b) * (M >> 2) + (m >> 2)) * T + t;
+}
+
 }  // namespace dsx

@@ -421,7 +421,7 @@ int launch_head(dsx_handle* h, const Geom& g, float* eps, cudaStream_t s) {
 // p_sample after the network (shallow_diffusion_tts.py:134-166), same fp32 operation order
 // (no FMA contraction): x_recon = A*x - Bc*eps; clamp; mean = c1*x_recon + c2*x; + sigma*noise.
 __global__ void k_ddpm_update(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
-                              uint64_t seed, uint64_t offset, DdpmCoef c, size_t n) {
+                              uint64_t seed, uint64_t offset, DdpmCoef c, size_t n, int M, int T) {
   size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   float xv = x[i];
@@ -429,13 +429,21 @@ __global__ void k_ddpm_update(float* __restrict__ x, const float* __restrict__ e
   xr = fminf(fmaxf(xr, -1.f), 1.f);
   float mean = __fadd_rn(__fmul_rn(c.c1, xr), __fmul_rn(c.c2, xv));
   float z = 0.f;
-  if (c.sigma != 0.f) z = noise ? noise[i] : philox_normal(seed, offset, i);
+  if (c.sigma != 0.f) {
+    if (noise) {
+      z = noise[i];
+    } else {
+      const int t = static_cast<int>(i % T), m = static_cast<int>((i / T) % M), b = static_cast<int>(i / (static_cast<size_t>(T) * M));
+      const float4 z4 = philox_normal4(seed, offset, mel_noise_block(b, m, t, M, T));
+      z = (m & 3) == 0 ? z4.x : (m & 3) == 1 ? z4.y : (m & 3) == 2 ? z4.z : z4.w;
+    }
+  }
   x[i] = __fadd_rn(mean, __fmul_rn(c.sigma, z));
 }
 
 int launch_ddpm_update(dsx_handle* h, float* x, const float* eps, const float* noise, uint64_t seed, uint64_t offset,
-                       DdpmCoef c, size_t n, cudaStream_t s) {
-  k_ddpm_update<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, eps, noise, seed, offset, c, n);
+                       DdpmCoef c, size_t n, int T, cudaStream_t s) {
+  k_ddpm_update<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, eps, noise, seed, offset, c, n, h->m.M, T);
   h->launches++;
   DSX_CUDA(cudaGetLastError());
   return DSX_OK;

@@ -637,7 +637,13 @@ struct TcHeadParams {
   int flags;
   int* status;
   unsigned long long budget_ns;
+  long long* trace;        // debug: CTA 0 writes clock64 stamps at [2*256 + 100 ...]
 };
+
+#define DSX_HTRACE(slot)                                                        \
+  do {                                                                          \
+    if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0) p.trace[2 * 256 + 100 + (slot)] = clock64(); \
+  } while (0)
 
 template <int P>
 struct HeadCfg {
@@ -854,9 +860,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
       if (lane == 0) okv = mbar_wait(bar, parity, wd, code) ? 1 : 0;
       return __shfl_sync(0xffffffffu, okv, 0) != 0;
     };
+    DSX_HTRACE(0);
     if (do_head) {
       // ---- epi-H1: h = relu(D1 + b_s) -> fp16 planes, K-major swizzled rows ----
       ok = wait_warp(&tf[0], 0, 311);
+      DSX_HTRACE(1);
       if (ok) {
         tc_fence_after();
 #pragma unroll 1
@@ -890,9 +898,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(hfull);
       }
+      DSX_HTRACE(2);
     }
     // ---- mel phase: eps, DDPM update, x_in operand.  half 0: bins [0,48), half 1: bins [48,80) ----
     if (ok && do_head) ok = wait_warp(&tf[1], 0, 312);
+    DSX_HTRACE(3);
     if (ok) {
       tc_fence_after();
       const int m_lo = half ? 48 : 0, m_hi = half ? p.M : 48;
@@ -910,6 +920,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
             xv[i] = p.x[static_cast<size_t>(b) * p.xs.b + static_cast<size_t>(m0 + i) * p.xs.c + static_cast<size_t>(t) * p.xs.t];
         }
         if (do_head) tmem_ld_wait();
+        float zn[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) zn[i] = 0.f;
+        if ((p.flags & TC_UPDATE) && p.c.sigma != 0.f && row_valid) {
+          if (p.noise) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) zn[i] = p.noise[(static_cast<size_t>(b) * p.M + m0 + i) * p.T + t];
+          } else {
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 z4 = philox_normal4(p.seed, p.offset, mel_noise_block(b, m0 + i4 * 4, t, p.M, p.T));
+              zn[i4 * 4] = z4.x; zn[i4 * 4 + 1] = z4.y; zn[i4 * 4 + 2] = z4.z; zn[i4 * 4 + 3] = z4.w;
+            }
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int m = m0 + i;
@@ -921,9 +946,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
             float xr = __fsub_rn(__fmul_rn(p.c.A, xv[i]), __fmul_rn(p.c.Bc, ev));
             xr = fminf(fmaxf(xr, -1.f), 1.f);
             const float mean = __fadd_rn(__fmul_rn(p.c.c1, xr), __fmul_rn(p.c.c2, xv[i]));
-            float z = 0.f;
-            if (p.c.sigma != 0.f && row_valid) z = p.noise ? p.noise[idx] : philox_normal(p.seed, p.offset, idx);
-            xv[i] = __fadd_rn(mean, __fmul_rn(p.c.sigma, z));
+            xv[i] = __fadd_rn(mean, __fmul_rn(p.c.sigma, zn[i]));
             if (row_valid) p.x[static_cast<size_t>(b) * p.xs.b + static_cast<size_t>(m) * p.xs.c + static_cast<size_t>(t) * p.xs.t] = xv[i];
           }
         }
@@ -965,7 +988,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
       }
     }
     // ---- epi-I: x0 = relu(D3 + b_in) -> X ; y0 = split(x0 + d_0) -> Y (row-contiguous stores via the transpose staging) ----
+    DSX_HTRACE(4);
     if (ok && do_in) ok = wait_warp(&tf[2], 0, 313);
+    DSX_HTRACE(5);
     if (ok && do_in) {
       tc_fence_after();
       uint8_t* stg = staging + (warp - 4) * 32 * kStageRowBytes;
@@ -1008,6 +1033,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
       }
     }
   }
+  DSX_HTRACE(6);
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -1331,6 +1357,7 @@ int launch_tc_head(dsx_handle* h, const Geom& g, int flags, float* x_state, dsx_
   prm.flags = flags;
   prm.status = h->status_dev;
   prm.budget_ns = 2000000000ull;
+  prm.trace = h->trace_dev;
   return (h->precision == DSX_PREC_FP16) ? launch_tc_head_t<1>(h, prm, g.tiles, s) : launch_tc_head_t<3>(h, prm, g.tiles, s);
 }
 
