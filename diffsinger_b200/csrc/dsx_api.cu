@@ -305,6 +305,8 @@ void dsx_destroy(dsx_handle* h) {
   free_model(h);
   free_ws(h->ws);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  for (void* p : h->stage)
+    if (p) cudaFree(p);
   if (h->trace_dev) cudaFree(h->trace_dev);
   if (h->flags_dev) cudaFree(h->flags_dev);
   if (h->status_dev) cudaFree(h->status_dev);
@@ -427,26 +429,34 @@ int dsx_infer_host(dsx_handle* h, const float* cond_host, dsx_strides cs, const 
   DSX_CUDA(cudaSetDevice(h->device));
   const int M = h->m.M, H = h->m.H;
   const size_t mel = static_cast<size_t>(B) * M * T;
-  // the host cond tensor must be dense in some permutation of [B,H,T]; copy its full extent
+  // the host cond tensor must be dense in some permutation of [B,H,T]; copy its full extent.  Device staging
+  // buffers live in the handle (grow-only) so a call costs copies, not cudaMalloc / cudaFree.
   const size_t cond_elems = static_cast<size_t>(B) * H * T;
-  float *d_cond = nullptr, *d_fs2 = nullptr, *d_x = nullptr, *d_min = nullptr, *d_max = nullptr, *d_out = nullptr;
-  int64_t* d_m2p = nullptr;
   int rc = DSX_OK;
-  auto up = [&](void** d, const void* src, size_t bytes) {
-    if (rc != DSX_OK || !src) return;
-    rc = dev_alloc(h, d, bytes, false);
-    if (rc == DSX_OK && cudaMemcpyAsync(*d, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+  auto up = [&](int slot, const void* src, size_t bytes) -> void* {
+    if (rc != DSX_OK || !src) return nullptr;
+    if (h->stage_cap[slot] < bytes) {
+      if (h->stage[slot]) cudaFree(h->stage[slot]);
+      h->stage[slot] = nullptr;
+      h->stage_cap[slot] = 0;
+      rc = dev_alloc(h, &h->stage[slot], bytes, false);
+      if (rc != DSX_OK) return nullptr;
+      h->stage_cap[slot] = bytes;
+    }
+    if (src != reinterpret_cast<const void*>(1) &&
+        cudaMemcpyAsync(h->stage[slot], src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) {
       set_error("host->device copy failed");
       rc = DSX_E_CUDA;
     }
+    return h->stage[slot];
   };
-  up(reinterpret_cast<void**>(&d_cond), cond_host, cond_elems * 4);
-  up(reinterpret_cast<void**>(&d_fs2), fs2_mel_host, mel * 4);
-  up(reinterpret_cast<void**>(&d_x), x_start_host, mel * 4);
-  up(reinterpret_cast<void**>(&d_min), spec_min_host, M * 4);
-  up(reinterpret_cast<void**>(&d_max), spec_max_host, M * 4);
-  up(reinterpret_cast<void**>(&d_m2p), mel2ph_host, static_cast<size_t>(B) * T * 8);
-  if (rc == DSX_OK) rc = dev_alloc(h, reinterpret_cast<void**>(&d_out), mel * 4, false);
+  float* d_cond = static_cast<float*>(up(0, cond_host, cond_elems * 4));
+  float* d_fs2 = static_cast<float*>(up(1, fs2_mel_host, mel * 4));
+  float* d_x = static_cast<float*>(up(2, x_start_host, mel * 4));
+  float* d_min = static_cast<float*>(up(3, spec_min_host, M * 4));
+  float* d_max = static_cast<float*>(up(4, spec_max_host, M * 4));
+  int64_t* d_m2p = static_cast<int64_t*>(up(5, mel2ph_host, static_cast<size_t>(B) * T * 8));
+  float* d_out = static_cast<float*>(up(6, reinterpret_cast<const void*>(1), mel * 4));   // output buffer only
   if (rc == DSX_OK)
     rc = dsx_infer(h, d_cond, cs, d_fs2, nullptr, d_x, nullptr, seed, d_m2p, d_min, d_max, B, T, K_step, pndm_interval,
                    d_out, stream);
@@ -455,9 +465,6 @@ int dsx_infer_host(dsx_handle* h, const float* cond_host, dsx_strides cs, const 
     rc = DSX_E_CUDA;
   }
   cudaStreamSynchronize(s);
-  void* frees[] = {d_cond, d_fs2, d_x, d_min, d_max, d_m2p, d_out};
-  for (void* p : frees)
-    if (p) cudaFree(p);
   return rc;
 }
 

@@ -118,6 +118,8 @@ struct dsx_handle {
   dsx::Geom tm_geom;           // geometry the activation maps were built for
   int tm_group = 0;
   int profile = 0;
+  void* stage[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // dsx_infer_host device staging
+  size_t stage_cap[7] = {0, 0, 0, 0, 0, 0, 0};
   unsigned int* flags_dev = nullptr;   // per-tile publish counters of the stack kernel
   int flags_cap = 0;
   int flags_grid = 0;                  // grid size of the last stack launch

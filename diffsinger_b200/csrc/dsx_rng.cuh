@@ -23,9 +23,10 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   // u1 in (0,1], u2 in [0,1)
   float u1 = (static_cast<float>(a) + 1.0f) * 2.3283064365386963e-10f;
   float u2 = static_cast<float>(b) * 2.3283064365386963e-10f;
-  float r = sqrtf(-2.0f * logf(u1));
+  // fast intrinsics (MUFU.LG2 / SIN / COS): |error| ~1e-6, far below what a sampler can resolve
+  float r = sqrtf(-2.0f * __logf(u1));
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  __sincosf(6.283185307179586f * u2, &s, &c);
   return make_float2(r * c, r * s);
 }
 __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t offset, size_t i) {

@@ -117,36 +117,39 @@ __global__ void k_embed_table(ModelDev m, const int64_t* __restrict__ tvals, flo
     e0[half + i] = static_cast<float>(cos(static_cast<double>(ang)));
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < 4 * C; j += blockDim.x) {
-    const float* w = m.mlp0_w + static_cast<size_t>(j) * C;
+  // matvecs: one warp per output, lanes stride over k (coalesced weight rows), shuffle reduction
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  auto dot = [&](const float* __restrict__ w, const float* __restrict__ v, int n) {
     float acc = 0.f;
-    for (int k = 0; k < C; ++k) acc = fmaf(w[k], e0[k], acc);
-    acc += m.mlp0_b[j];
+    for (int k = lane; k < n; k += 32) acc = fmaf(w[k], v[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+  };
+  for (int j = warp; j < 4 * C; j += nwarps) {
+    float acc = dot(m.mlp0_w + static_cast<size_t>(j) * C, e0, C) + m.mlp0_b[j];
     // Mish: x * tanh(softplus(x)); softplus with torch's threshold (20) semantics
     float sp = acc > 20.f ? acc : log1pf(expf(acc));
-    h1[j] = acc * tanhf(sp);
+    if (lane == 0) h1[j] = acc * tanhf(sp);
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < C; j += blockDim.x) {
-    const float* w = m.mlp2_w + static_cast<size_t>(j) * 4 * C;
-    float acc = 0.f;
-    for (int k = 0; k < 4 * C; ++k) acc = fmaf(w[k], h1[k], acc);
-    e2[j] = acc + m.mlp2_b[j];
-    if (emb_out) emb_out[static_cast<size_t>(row) * C + j] = e2[j];
+  for (int j = warp; j < C; j += nwarps) {
+    float acc = dot(m.mlp2_w + static_cast<size_t>(j) * 4 * C, h1, 4 * C) + m.mlp2_b[j];
+    if (lane == 0) {
+      e2[j] = acc;
+      if (emb_out) emb_out[static_cast<size_t>(row) * C + j] = acc;
+    }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < L * C; idx += blockDim.x) {
-    const int l = idx / C, j = idx % C;
-    const float* w = m.dif_w + (static_cast<size_t>(l) * C + j) * C;
-    float acc = 0.f;
-    for (int k = 0; k < C; ++k) acc = fmaf(w[k], e2[k], acc);
-    dtab[(static_cast<size_t>(row) * L + l) * C + j] = acc + m.dif_b[static_cast<size_t>(l) * C + j];
+  for (int idx = warp; idx < L * C; idx += nwarps) {
+    float acc = dot(m.dif_w + static_cast<size_t>(idx) * C, e2, C) + m.dif_b[idx];
+    if (lane == 0) dtab[static_cast<size_t>(row) * L * C + idx] = acc;
   }
 }
 
 int launch_embed_table(dsx_handle* h, const int64_t* t_dev, int rows, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(6) * h->m.C * sizeof(float);
-  k_embed_table<<<rows, 256, smem, s>>>(h->m, t_dev, h->ws.DTAB, h->ws.EMB);
+  k_embed_table<<<rows, 512, smem, s>>>(h->m, t_dev, h->ws.DTAB, h->ws.EMB);
   h->launches++;
   DSX_CUDA(cudaGetLastError());
   return DSX_OK;

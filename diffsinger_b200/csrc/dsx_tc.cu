@@ -54,7 +54,7 @@ struct TcCfg {
   // after GEMM1 has finished and alias the last Z23_UNITS ring units, so GEMM2's weight ring is the first
   // UNITS2 units only.
   // Epilogue 2 transposes the accumulator through STG_UNITS more ring units (free once GEMM1 is done).
-  static constexpr int UNITS = (P == 1) ? 11 : 9;
+  static constexpr int UNITS = (P == 1) ? 11 : 10;
   static constexpr int Z23_UNITS = 2 * Z_PLANES;
   static constexpr int STG_UNITS = 2;                           // 8 warps x 32 rows x 128 B
   static constexpr int UNITS2 = UNITS - Z23_UNITS - STG_UNITS;   // ring layout: [ring2 | z23 | staging]
@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   uint64_t* empty2 = full2 + NU2;    // [NU2]
   uint64_t* tfull = empty2 + NU2;    // [2]
   uint64_t* tempty = tfull + 2;      // [2]
-  uint64_t* zfull = tempty + 2;      // z complete (both CTAs of the pair)
-  uint64_t* g1done = zfull + 1;      // all GEMM1 MMAs of the layer complete
+  uint64_t* zf = tempty + 2;         // [2] z k-block 2 / 3 written (both CTAs of the pair); k-blocks 0,1 ride on tempty[0]
+  uint64_t* g1done = zf + 2;         // all GEMM1 MMAs of the layer complete
   uint64_t* g2done = g1done + 1;     // all GEMM2 MMAs of the layer complete (ring2 / z units reusable)
   uint64_t* edone = g2done + 1;      // this CTA's epilogue has left the staging units
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(edone + 1);
@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kEpiWarps * G);
     }
-    mbar_init(zfull, kEpiWarps * G);
+    mbar_init(&zf[0], kEpiWarps * G);
+    mbar_init(&zf[1], kEpiWarps * G);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<G>(tmem_slot, 512);
@@ -357,9 +358,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       }
       if (ok) umma_commit<G>(g1done, pair_mask);
       DSX_TRACE(1, 200);
-      if (ok) ok = mbar_wait(zfull, li & 1, wd, 203);
-      DSX_TRACE(1, 201);
-      tc_fence_after();
+      // GEMM2 reads z k-blocks 0,1 as soon as its TMEM buffer is free (tempty[0] is released after epi1 of chunk 0,
+      // which also made z01 visible), then k-blocks 2 and 3 as the chunk-1 epilogue delivers them.
       for (int q = 0; q < 2 && ok; ++q) {
         const int buf = q;
         ok = mbar_wait(&tempty[buf], (tuse[buf] & 1) ^ 1, wd, 204);
@@ -370,6 +370,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         const uint32_t d = tmem_base + buf * 256;
         uint32_t acc = 0;
         for (int kb = 0; kb < 4 && ok; ++kb) {
+          if (q == 0 && kb >= 2) {
+            ok = mbar_wait(&zf[kb - 2], li & 1, wd, 203);
+            if (kb == 3) DSX_TRACE(1, 201);
+            if (!ok) break;
+            tc_fence_after();
+          }
           const uint64_t z_hi = umma_desc_sw128(smem_u32(zaddr(0, kb)));
           const uint64_t w_hi = wait_unit2(u2, 205);
           if (!ok) break;
@@ -433,14 +439,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         if (tracer) DSX_TRACE(2, h * 4 + 1);
         tf[h]++;
         tc_fence_after();
-        const float* bg = b1p + h * 256 + half * 64;          // gate biases; filter biases at +128
-        uint8_t* zrow = zaddr(0, 2 * h + half) + r * 128;
-        uint8_t* zrow_lo = zaddr(1, 2 * h + half) + r * 128;
+        // two passes of 32 gate/filter column pairs: pass `it` of all 8 warps completes z k-block 2h + it, so
+        // GEMM2 can start on k-block 2 while k-block 3 is still being gated
 #pragma unroll 1
-        for (int j = 0; j < 64; j += 32) {
+        for (int it = 0; it < 2; ++it) {
+          const int gcol = it * 64 + half * 32;               // first gate column of this warp in this pass
+          const float* bg = b1p + h * 256 + gcol;             // gate biases; filter biases at +128
+          uint8_t* zrow = zaddr(0, 2 * h + it) + r * 128;
+          uint8_t* zrow_lo = zaddr(1, 2 * h + it) + r * 128;
           uint32_t g[32], f[32];
-          tmem_ld_32x32(tmem_base + tlane + h * 256 + half * 64 + j, g);
-          tmem_ld_32x32(tmem_base + tlane + h * 256 + 128 + half * 64 + j, f);
+          tmem_ld_32x32(tmem_base + tlane + h * 256 + gcol, g);
+          tmem_ld_32x32(tmem_base + tlane + h * 256 + 128 + gcol, f);
           tmem_ld_wait();
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
@@ -448,8 +457,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
 #pragma unroll
             for (int e = 0; e < 4; e += 2) {
               const int i = c8 * 8 + e * 2;
-              const float4 bgv = __ldg(reinterpret_cast<const float4*>(bg + j + i));
-              const float4 bfv = __ldg(reinterpret_cast<const float4*>(bg + 128 + j + i));
+              const float4 bgv = __ldg(reinterpret_cast<const float4*>(bg + i));
+              const float4 bfv = __ldg(reinterpret_cast<const float4*>(bg + 128 + i));
               float z4[4];
               const float vg[4] = {__uint_as_float(g[i]) + bgv.x, __uint_as_float(g[i + 1]) + bgv.y,
                                    __uint_as_float(g[i + 2]) + bgv.z, __uint_as_float(g[i + 3]) + bgv.w};
@@ -467,9 +476,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
                 lo[e + 1] = h2_bits(__floats2half2_rn(z4[2] - f23.x, z4[3] - f23.y));
               }
             }
-            const int off = (((j >> 3) + c8) ^ (r & 7)) << 4;
+            const int off = ((half * 4 + c8) ^ (r & 7)) << 4;   // this warp's 32 channels = chunks 4*half .. +3
             *reinterpret_cast<uint4*>(zrow + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             if (P == 3) *reinterpret_cast<uint4*>(zrow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          if (h == 1) {
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            release(&zf[it]);
           }
         }
         tc_fence_before();
@@ -477,7 +492,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         __syncwarp();
         if (tracer) DSX_TRACE(2, h * 4 + 2);
         release(&tempty[h]);
-        if (h == 1) release(zfull);
       }
       // ---- epi2: each warp moves its 32 rows x 32 columns through a swizzled shared-memory tile so that every
       //      global access instruction covers whole 128-byte row segments (2 rows x 32 columns of fp32).  All
@@ -647,10 +661,11 @@ struct TcHeadParams {
 
 template <int P>
 struct HeadCfg {
-  static constexpr int UNITS = 5;
+  static constexpr int UNITS = (P == 1) ? 9 : 5;              // ring of the H2 / I phases
   static constexpr int Z_PLANES = (P == 1) ? 1 : 2;
   static constexpr int H_BYTES = Z_PLANES * 4 * kUnitBytes;
-  static constexpr int SMEM_BYTES = 1024 + UNITS * kUnitBytes + H_BYTES + kStagingBytes + 256;
+  static constexpr int UNITS_H1 = UNITS + H_BYTES / kUnitBytes;   // H1 also streams through the not-yet-written h buffer
+  static constexpr int SMEM_BYTES = 1024 + UNITS * kUnitBytes + H_BYTES + kStagingBytes + 512;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
@@ -665,7 +680,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* full = bars;           // [NU]
   uint64_t* empty = full + NU;     // [NU]
-  uint64_t* tf = empty + NU;       // [3]  accumulator ready: H1, H2, I
+  constexpr int NA = Cfg::UNITS_H1;
+  uint64_t* fullA = empty + NU;    // [NA]  H1 ring (ring + h buffer)
+  uint64_t* emptyA = fullA + NA;   // [NA]
+  uint64_t* tf = emptyA + NA;      // [3]  accumulator ready: H1, H2, I
   uint64_t* hfull = tf + 3;        // h written
   uint64_t* xfull = hfull + 1;     // x_in written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull + 1);
@@ -685,6 +703,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
     for (int s = 0; s < NU; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < NA; ++s) {
+      mbar_init(&fullA[s], 1);
+      mbar_init(&emptyA[s], 1);
     }
     for (int i = 0; i < 3; ++i) mbar_init(&tf[i], 1);
     mbar_init(hfull, kEpiWarps);
@@ -724,16 +746,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
       ++u;
     };
     if (do_head) {
+      // H1 streams through ring A = ring + h buffer (h is only written after H1's accumulator is complete)
+      uint32_t ua = 0;
+      auto acquireA = [&]() -> uint8_t* {
+        const int s = ua % NA;
+        ok = mbar_wait(&emptyA[s], ((ua / NA) & 1) ^ 1, wd, 113);
+        if (!ok) return nullptr;
+        mbar_arrive_expect_tx(&fullA[s], kUnitBytes);
+        return ring + s * kUnitBytes;
+      };
+      auto loadA_a = [&](int plane, int kb) {
+        const int s = ua % NA;
+        uint8_t* dst = acquireA();
+        if (!dst) return;
+        tma_load_3d<1>(&p.tm_s16[plane], &fullA[s], dst, kb * 64, t0, b);
+        ++ua;
+      };
+      auto loadA_w = [&](int tileidx) {
+        const int s = ua % NA;
+        uint8_t* dst = acquireA();
+        if (!dst) return;
+        tma_load_2d<1>(&p.tm_wh, &fullA[s], dst, 0, tileidx * 128);
+        ++ua;
+      };
       for (int kb = 0; kb < 4 && ok; ++kb) {
-        load_a(0, kb);
-        if (ok) load_w((0 * 2 + 0) * 4 + kb);
-        if (ok) load_w((0 * 2 + 1) * 4 + kb);
+        loadA_a(0, kb);
+        if (ok) loadA_w((0 * 2 + 0) * 4 + kb);
+        if (ok) loadA_w((0 * 2 + 1) * 4 + kb);
         if (P == 3) {
-          if (ok) load_w((1 * 2 + 0) * 4 + kb);
-          if (ok) load_w((1 * 2 + 1) * 4 + kb);
-          if (ok) load_a(1, kb);
+          if (ok) loadA_w((1 * 2 + 0) * 4 + kb);
+          if (ok) loadA_w((1 * 2 + 1) * 4 + kb);
+          if (ok) loadA_a(1, kb);
         }
       }
+      // the H2 / I weights use the small ring, whose units alias ring A: wait for H1's MMAs
+      if (ok) ok = mbar_wait(&tf[0], 0, wd, 114);
       for (int kb = 0; kb < 4 && ok; ++kb) {
         load_w(16 + 0 * 4 + kb);
         if (P == 3 && ok) load_w(16 + 1 * 4 + kb);
@@ -771,35 +818,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
       u += n;
     };
     if (do_head) {
-      uint32_t acc0 = 0, acc1 = 0;
+      uint32_t acc0 = 0, acc1 = 0, ua = 0;
+      auto waitA = [&](uint32_t uu) -> uint64_t {
+        const int s = uu % NA;
+        ok = ok && mbar_wait(&fullA[s], (uu / NA) & 1, wd, 211);
+        return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
+      };
       for (int kb = 0; kb < 4 && ok; ++kb) {
-        const uint64_t a_hi = wait_unit(u, 211), w0 = wait_unit(u + 1, 211), w1 = wait_unit(u + 2, 211);
+        const uint64_t a_hi = waitA(ua), w0 = waitA(ua + 1), w1 = waitA(ua + 2);
         if (!ok) break;
         tc_fence_after();
         mma4(tmem_base, a_hi, w0, acc0);
         mma4(tmem_base + 128, a_hi, w1, acc1);
         if (P == 3) {
-          // 6 units per k-block but only 5 ring slots: free A_hi and the two W_lo units before A_lo is needed
-          const uint64_t l0 = wait_unit(u + 3, 211), l1 = wait_unit(u + 4, 211);
+          const uint64_t l0 = waitA(ua + 3), l1 = waitA(ua + 4), a_lo = waitA(ua + 5);
           if (!ok) break;
           tc_fence_after();
           mma4(tmem_base, a_hi, l0, acc0);
           mma4(tmem_base + 128, a_hi, l1, acc1);
-          umma_commit<1>(&empty[u % NU]);
-          umma_commit<1>(&empty[(u + 3) % NU]);
-          umma_commit<1>(&empty[(u + 4) % NU]);
-          const uint64_t a_lo = wait_unit(u + 5, 211);
-          if (!ok) break;
-          tc_fence_after();
           mma4(tmem_base, a_lo, w0, acc0);
           mma4(tmem_base + 128, a_lo, w1, acc1);
-          umma_commit<1>(&empty[(u + 1) % NU]);
-          umma_commit<1>(&empty[(u + 2) % NU]);
-          umma_commit<1>(&empty[(u + 5) % NU]);
-          u += 6;
-        } else {
-          release(3);
         }
+        const int nrel = (P == 1) ? 3 : 6;
+        for (int i = 0; i < nrel; ++i) umma_commit<1>(&emptyA[(ua + i) % NA]);
+        ua += nrel;
       }
       if (ok) umma_commit<1>(&tf[0]);
       if (ok) ok = mbar_wait(hfull, 0, wd, 212);
@@ -900,75 +942,68 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
       }
       DSX_HTRACE(2);
     }
-    // ---- mel phase: eps, DDPM update, x_in operand.  half 0: bins [0,48), half 1: bins [48,80) ----
+    // ---- mel phase: eps, DDPM update, x_in operand.  half 0: bins [0,40), half 1: bins [40,80), 8 bins a time ----
     if (ok && do_head) ok = wait_warp(&tf[1], 0, 312);
     DSX_HTRACE(3);
     if (ok) {
       tc_fence_after();
-      const int m_lo = half ? 48 : 0, m_hi = half ? p.M : 48;
+      const int m_lo = half * 40;
+      const bool need_x = (p.flags & (TC_UPDATE | TC_INPROJ)) != 0;
+      const bool need_z = (p.flags & TC_UPDATE) && p.c.sigma != 0.f;
+      const size_t xrow = static_cast<size_t>(b) * p.xs.b + static_cast<size_t>(t) * p.xs.t;
 #pragma unroll 1
-      for (int m0 = m_lo; m0 < m_hi; m0 += 16) {
-        uint32_t e16[16];
-        if (do_head) {
-          tmem_ld_32x16(tmem_base + tlane + 256 + m0, e16);
-        }
-        float xv[16];
+      for (int m0 = m_lo; m0 < m_lo + 40; m0 += 8) {
+        uint32_t e8[8];
+        if (do_head) tmem_ld_32x8(tmem_base + tlane + 256 + m0, e8);
+        float xv[8], zn[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           xv[i] = 0.f;
-          if (row_valid && (p.flags & (TC_UPDATE | TC_INPROJ)))
-            xv[i] = p.x[static_cast<size_t>(b) * p.xs.b + static_cast<size_t>(m0 + i) * p.xs.c + static_cast<size_t>(t) * p.xs.t];
+          zn[i] = 0.f;
+          if (row_valid && need_x) xv[i] = p.x[xrow + static_cast<size_t>(m0 + i) * p.xs.c];
         }
-        if (do_head) tmem_ld_wait();
-        float zn[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) zn[i] = 0.f;
-        if ((p.flags & TC_UPDATE) && p.c.sigma != 0.f && row_valid) {
+        if (need_z && row_valid) {
           if (p.noise) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) zn[i] = p.noise[(static_cast<size_t>(b) * p.M + m0 + i) * p.T + t];
+            for (int i = 0; i < 8; ++i) zn[i] = p.noise[(static_cast<size_t>(b) * p.M + m0 + i) * p.T + t];
           } else {
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
+            for (int i4 = 0; i4 < 2; ++i4) {
               const float4 z4 = philox_normal4(p.seed, p.offset, mel_noise_block(b, m0 + i4 * 4, t, p.M, p.T));
               zn[i4 * 4] = z4.x; zn[i4 * 4 + 1] = z4.y; zn[i4 * 4 + 2] = z4.z; zn[i4 * 4 + 3] = z4.w;
             }
           }
         }
+        if (do_head) tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const int m = m0 + i;
-          const size_t idx = (static_cast<size_t>(b) * p.M + m) * p.T + t;      // contiguous [B][M][T]
           float ev = 0.f;
-          if (do_head) ev = __uint_as_float(e16[i]) + __ldg(p.bf + m);
-          if ((p.flags & TC_WRITE_EPS) && row_valid) p.eps[idx] = ev;
+          if (do_head) ev = __uint_as_float(e8[i]) + __ldg(p.bf + m);
+          if ((p.flags & TC_WRITE_EPS) && row_valid) p.eps[(static_cast<size_t>(b) * p.M + m) * p.T + t] = ev;
           if (p.flags & TC_UPDATE) {
             float xr = __fsub_rn(__fmul_rn(p.c.A, xv[i]), __fmul_rn(p.c.Bc, ev));
             xr = fminf(fmaxf(xr, -1.f), 1.f);
             const float mean = __fadd_rn(__fmul_rn(p.c.c1, xr), __fmul_rn(p.c.c2, xv[i]));
             xv[i] = __fadd_rn(mean, __fmul_rn(p.c.sigma, zn[i]));
-            if (row_valid) p.x[static_cast<size_t>(b) * p.xs.b + static_cast<size_t>(m) * p.xs.c + static_cast<size_t>(t) * p.xs.t] = xv[i];
+            if (row_valid) p.x[xrow + static_cast<size_t>(m) * p.xs.c] = xv[i];
           }
         }
         if (do_in) {
-          // 16 bins = two 16-byte chunks of row r in k-block m0 >> 6
-          const int kb = m0 >> 6, chunk0 = (m0 & 63) >> 3;
+          // 8 bins = one 16-byte chunk of row r in k-block m0 >> 6
+          uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int c8 = 0; c8 < 2; ++c8) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = c8 * 8 + e * 2;
-              const float a0 = row_valid ? xv[i] : 0.f, a1 = row_valid ? xv[i + 1] : 0.f;
-              const __half2 hh = __floats2half2_rn(a0, a1);
-              hi[e] = h2_bits(hh);
-              const float2 hf = __half22float2(hh);
-              lo[e] = h2_bits(__floats2half2_rn(a0 - hf.x, a1 - hf.y));
-            }
-            const int off = r * 128 + (((chunk0 + c8) ^ (r & 7)) << 4);
-            *reinterpret_cast<uint4*>(hk(0, kb) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (P == 3) *reinterpret_cast<uint4*>(hk(1, kb) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          for (int e = 0; e < 4; ++e) {
+            const float a0 = row_valid ? xv[2 * e] : 0.f, a1 = row_valid ? xv[2 * e + 1] : 0.f;
+            const __half2 hh = __floats2half2_rn(a0, a1);
+            hi[e] = h2_bits(hh);
+            const float2 hf = __half22float2(hh);
+            lo[e] = h2_bits(__floats2half2_rn(a0 - hf.x, a1 - hf.y));
           }
+          const int kb = m0 >> 6, chunk = (m0 & 63) >> 3;
+          const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(hk(0, kb) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (P == 3) *reinterpret_cast<uint4*>(hk(1, kb) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
       if (do_in) {
