@@ -450,6 +450,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
           uint32_t g[32], f[32];
           tmem_ld_32x32(tmem_base + tlane + h * 256 + gcol, g);
           tmem_ld_32x32(tmem_base + tlane + h * 256 + 128 + gcol, f);
+          float4 bgq[8], bfq[8];
+#pragma unroll
+          for (int v4 = 0; v4 < 8; ++v4) {
+            bgq[v4] = __ldg(reinterpret_cast<const float4*>(bg) + v4);
+            bfq[v4] = __ldg(reinterpret_cast<const float4*>(bg + 128) + v4);
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
@@ -457,8 +463,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
 #pragma unroll
             for (int e = 0; e < 4; e += 2) {
               const int i = c8 * 8 + e * 2;
-              const float4 bgv = __ldg(reinterpret_cast<const float4*>(bg + i));
-              const float4 bfv = __ldg(reinterpret_cast<const float4*>(bg + 128 + i));
+              const float4 bgv = bgq[i >> 2];
+              const float4 bfv = bfq[i >> 2];
               float z4[4];
               const float vg[4] = {__uint_as_float(g[i]) + bgv.x, __uint_as_float(g[i + 1]) + bgv.y,
                                    __uint_as_float(g[i + 2]) + bgv.z, __uint_as_float(g[i + 3]) + bgv.w};
@@ -506,6 +512,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         const bool do_load = (mode == 0 || mode == 2);
         const float* dn = (q == 0 && dnext) ? dnext + static_cast<size_t>(tile_valid ? b : 0) * p.d_row_stride + half * 128 + lc2 * 2 : nullptr;
         const float* bp = b2 + q * 256 + half * 128 + lc2 * 2;
+        // per-column vectors of the four 32-column groups: requested before the accumulator wait (these come
+        // from L2: the proxy / gpu fences of the hand-over invalidate L1)
+        float2 biasv[4], dnvv[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          biasv[jj] = __ldg(reinterpret_cast<const float2*>(bp + jj * 32));
+          dnvv[jj] = dn ? __ldg(reinterpret_cast<const float2*>(dn + jj * 32)) : make_float2(0.f, 0.f);
+        }
         float2 pre[16];
         auto prefetch = [&](int j) {
 #pragma unroll
@@ -520,8 +534,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         if (tracer) DSX_TRACE(2, 9 + 2 * q);
         tf[q]++;
         tc_fence_after();
-#pragma unroll 1
-        for (int j = 0; j < 128; j += 32) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = jj * 32;
           uint32_t o[32];
           tmem_ld_32x32(tmem_base + tlane + q * 256 + half * 128 + j, o);
           tmem_ld_wait();
@@ -531,9 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
             *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
                 make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
           __syncwarp();
-          const float2 bias = __ldg(reinterpret_cast<const float2*>(bp + j));
-          float2 dnv = make_float2(0.f, 0.f);
-          if (dn) dnv = __ldg(reinterpret_cast<const float2*>(dn + j));
+          const float2 bias = biasv[jj], dnv = dnvv[jj];
           float2 res[16];
 #pragma unroll
           for (int it = 0; it < 16; ++it) {
