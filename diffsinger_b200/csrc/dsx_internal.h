@@ -122,8 +122,10 @@ struct dsx_handle {
   size_t stage_cap[7] = {0, 0, 0, 0, 0, 0, 0};
   unsigned int* flags_dev = nullptr;   // per-tile publish counters of the stack kernel
   int flags_cap = 0;
-  int flags_grid = 0;                  // grid size of the last stack launch
+  int flags_geom_b = 0, flags_geom_t = 0;   // geometry of the last stack launch
   unsigned int flag_count = 0;         // value of every counter before the next stack launch
+  bool attr_layer[2] = {false, false}, attr_head[2] = {false, false};
+  int occ_cache[2][17] = {};
   int cluster_occ = 0;              // max co-resident utterance clusters reported by the driver (last launch)
   int stack_mode = 1;               // 1: all residual layers of an evaluation in one cluster-per-utterance launch
   long long* trace_dev = nullptr;   // debug timeline buffer (dsx_debug_trace)

@@ -90,6 +90,76 @@ __global__ void __launch_bounds__(256, 1) k_selftest(const __grid_constant__ Sel
   }
 }
 
+// ---- experiment (informational): can a K-major SWIZZLE_128B A descriptor start `shift` rows into a tile?
+// (would let the three dilated taps share one shared-memory copy of the activations)  One CTA, cta_group::1:
+// A box = 160 rows x 64 channels, D = A[shift : shift+128] . W^T with K = 64.
+struct ShiftParams {
+  CUtensorMap tm_a;   // 3D [1][T][128] fp16, box 64 x 160 x 1
+  CUtensorMap tm_w;   // 2D [512][64], box 64 x 256
+  float* out;         // [128][256]
+  int shift, use_base_offset;
+  int* status;
+};
+
+__global__ void __launch_bounds__(256, 1) k_shift_test(const __grid_constant__ ShiftParams p) {
+  constexpr int A_BYTES = 160 * 128, W_BYTES = 256 * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wbuf = base + 20480 + 1024;   // keep W 1024-aligned: 21504 = 21 * 1024
+  uint64_t* full = reinterpret_cast<uint64_t*>(wbuf + W_BYTES);
+  uint64_t* tfull = full + 1;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1 && lane == 0) {
+    mbar_init(full, 1);
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(slot);
+  Watchdog wd{p.status, globaltimer_ns() + 500000000ull};
+  if (warp == 0 && lane == 0) {
+    mbar_arrive_expect_tx(full, A_BYTES + W_BYTES);
+    tma_load_3d<1>(&p.tm_a, full, base, 0, 0, 0);
+    tma_load_2d<1>(&p.tm_w, full, wbuf, 0, 0);
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = umma_idesc_f16(128, 256);
+    if (mbar_wait(full, 0, wd, 911)) {
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(base) + p.shift * 128;
+      uint64_t ad = umma_desc_sw128(a_addr);
+      if (p.use_base_offset) ad |= static_cast<uint64_t>((a_addr >> 7) & 7) << 49;
+      const uint64_t bd = umma_desc_sw128(smem_u32(wbuf));
+      uint32_t acc = 0;
+      for (int k4 = 0; k4 < 4; ++k4) {
+        umma_f16<1>(tmem_base, ad + 2 * k4, bd + 2 * k4, idesc, acc);
+        acc = 1;
+      }
+      umma_commit<1>(tfull);
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3, r = quad * 32 + lane;
+    if (mbar_wait(tfull, 0, wd, 912)) {
+      tc_fence_after();
+      for (int j = 0; j < 256; j += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + j, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) p.out[static_cast<size_t>(r) * 256 + j + i] = __uint_as_float(v[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 256);
+  }
+}
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -184,6 +254,75 @@ static int run_selftest(std::string& report) {
   return (status == 0 && bad == 0) ? DSX_OK : DSX_E_KERNEL;
 }
 
+static int run_shift_experiment(std::string& report) {
+  const int T = 300, CH = 128;
+  std::vector<__half> ha(static_cast<size_t>(T) * CH), hw(512 * 64);
+  auto aval = [](int t, int c) { return static_cast<float>((t * 131 + c * 71) % 61 - 30) / 64.f; };
+  auto wval = [](int n, int k) { return static_cast<float>((n * 37 + k * 11) % 53 - 26) / 128.f; };
+  for (int t = 0; t < T; ++t)
+    for (int c = 0; c < CH; ++c) ha[static_cast<size_t>(t) * CH + c] = __float2half(aval(t, c));
+  for (int n = 0; n < 256; ++n)
+    for (int kk = 0; kk < 64; ++kk) hw[static_cast<size_t>(n) * 64 + kk] = __float2half(wval(n, kk));
+  __half *da = nullptr, *dw = nullptr;
+  float* dout = nullptr;
+  int* dstatus = nullptr;
+  DSX_CUDA(cudaMalloc(&da, ha.size() * 2));
+  DSX_CUDA(cudaMalloc(&dw, hw.size() * 2));
+  DSX_CUDA(cudaMalloc(&dout, 128 * 256 * 4));
+  DSX_CUDA(cudaMalloc(&dstatus, 4));
+  DSX_CUDA(cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice));
+  DSX_CUDA(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  DSX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
+  PFN_tmapEncodeTiled enc = reinterpret_cast<PFN_tmapEncodeTiled>(fp);
+  ShiftParams prm;
+  memset(&prm, 0, sizeof(prm));
+  {
+    cuuint64_t dims[3] = {CH, T, 1};
+    cuuint64_t strides[2] = {CH * 2, static_cast<cuuint64_t>(T) * CH * 2};
+    cuuint32_t box[3] = {64, 160, 1}, es[3] = {1, 1, 1};
+    CUresult r = enc(&prm.tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, da, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSX_CHECK(r == CUDA_SUCCESS, DSX_E_CUDA, "shift experiment: encode A map failed %d", static_cast<int>(r));
+    cuuint64_t d2[2] = {64, 512};
+    cuuint64_t s2[1] = {128};
+    cuuint32_t b2[2] = {64, 256}, e2[2] = {1, 1};
+    r = enc(&prm.tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dw, d2, s2, b2, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSX_CHECK(r == CUDA_SUCCESS, DSX_E_CUDA, "shift experiment: encode W map failed %d", static_cast<int>(r));
+  }
+  prm.out = dout;
+  prm.status = dstatus;
+  const int smem = 1024 + 21504 + 256 * 128 + 64;
+  DSX_CUDA(cudaFuncSetAttribute(k_shift_test, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int shifts[] = {0, 1, 2, 3, 4, 8, 16};
+  for (int ubo = 0; ubo < 2; ++ubo)
+    for (int si = 0; si < 7; ++si) {
+      prm.shift = shifts[si];
+      prm.use_base_offset = ubo;
+      DSX_CUDA(cudaMemset(dout, 0xff, 128 * 256 * 4));
+      DSX_CUDA(cudaMemset(dstatus, 0, 4));
+      k_shift_test<<<1, 256, smem>>>(prm);
+      DSX_CUDA(cudaDeviceSynchronize());
+      std::vector<float> out(128 * 256);
+      DSX_CUDA(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+      int bad = 0;
+      for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < 256; ++n) {
+          double ref = 0;
+          for (int k = 0; k < 64; ++k) ref += static_cast<double>(aval(m + shifts[si], k)) * wval(n, k);
+          if (!(fabs(ref - out[static_cast<size_t>(m) * 256 + n]) <= 1e-4)) bad++;
+        }
+      char line[160];
+      snprintf(line, sizeof(line), "shifted_A_desc shift=%d base_offset_field=%d: bad=%d/32768\n", shifts[si], ubo, bad);
+      report += line;
+    }
+  cudaFree(da); cudaFree(dw); cudaFree(dout); cudaFree(dstatus);
+  return DSX_OK;
+}
+
 }  // namespace dsx
 
 extern "C" int dsx_selftest(int device, int which, char* report, int report_bytes) {
@@ -199,6 +338,10 @@ extern "C" int dsx_selftest(int device, int which, char* report, int report_byte
   if (which < 0 || which == 1) {
     int r = run_selftest<2>(rep);
     if (r != DSX_OK) { rc = DSX_E_KERNEL; failed += " umma_cta_group2"; }
+  }
+  if (which == 2) {   // informational experiment, not part of which = -1
+    int r = run_shift_experiment(rep);
+    if (r != DSX_OK) rc = r;
   }
   if (report && report_bytes > 0) {
     strncpy(report, rep.c_str(), static_cast<size_t>(report_bytes) - 1);

@@ -26,6 +26,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <cmath>
 #include <type_traits>
 #include <vector>
@@ -80,6 +81,7 @@ struct TcLayerParams {
   const float* dtab;         // FiLM table row of this evaluation: [L][256], utterance b at + b * d_row_stride
   int d_row_stride;
   int T, Tp, tiles_per_utt, tiles, B;
+  int tile0, tile_end;       // this launch covers tiles [tile0, tile_end) (whole utterances); CTA i -> tile tile0 + i
   int l0, l1, L, cycle;      // layers [l0, l1); dilation of layer l = 1 << (l % cycle)
   unsigned int* flags;       // [tiles] monotonic publish counters (multi-layer launches), else nullptr
   unsigned int flag_base;    // counter value every valid tile had when this launch started
@@ -168,8 +170,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
     if (p.trace && blockIdx.x < 2) p.trace[(blockIdx.x * 3 + 1) * 256 + 250] = static_cast<long long>(globaltimer_ns());
   }
   // tile -> (utterance, 128-frame tile in the utterance); the grid is padded to an even number of CTAs
-  const int tile = blockIdx.x;
-  const bool tile_valid = tile < p.tiles;
+  const int tile = p.tile0 + blockIdx.x;
+  const bool tile_valid = tile < p.tile_end;
   const int b = tile / p.tiles_per_utt, tr = tile % p.tiles_per_utt;
   const int bq = tile_valid ? b : p.B;            // b == B -> every TMA row is out of bounds (zeros)
   const int t0 = tile_valid ? tr * kTile : 0;
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       };
       for (int q = 0; q < 2 && ok; ++q) {
         ok = (nrows == 32) ? epi2_half(std::true_type{}, q) : epi2_half(std::false_type{}, q);
-        if (q == 0 && ok && multi && l + 1 < p.l1) {      // padding tiles publish too: all counters stay in lockstep
+        if (q == 0 && ok && multi && l + 1 < p.l1 && tile_valid) {   // (nobody waits on a padding tile)
           // publish y_{l+1}: generic-proxy global stores of every lane -> async-proxy (TMA) readers in this CTA and
           // its neighbours.  Proxy fence + gpu fence per lane, warp sync, then one release-increment per warp.
           fence_proxy_async_all();
@@ -1250,10 +1252,9 @@ int tc_prepare_maps(dsx_handle* h, const Geom& g) {
 template <int P>
 static int launch_tc_layer_t(dsx_handle* h, const TcLayerParams& prm, int grid, int csize, cudaStream_t s) {
   using Cfg = TcCfg<P>;
-  static bool attr_done = false;
+  bool& attr_done = h->attr_layer[P == 1 ? 0 : 1];      // function attributes are per device -> per handle
   if (!attr_done) {
     DSX_CUDA(cudaFuncSetAttribute(k_tc_layer<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    DSX_CUDA(cudaFuncSetAttribute(k_tc_layer<P>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -1275,8 +1276,8 @@ static int launch_tc_layer_t(dsx_handle* h, const TcLayerParams& prm, int grid, 
 
 // Can a cluster of `csize` CTAs of the layer kernel be scheduled on this device?  (cached per size)
 template <int P>
-static int cluster_occupancy(int csize) {
-  static int cache[17] = {0};   // 0 unknown, >0 max co-resident clusters, -1 none
+static int cluster_occupancy(dsx_handle* h, int csize) {
+  int* cache = h->occ_cache[P == 1 ? 0 : 1];   // per handle (= per device): 0 unknown, >0 max co-resident clusters, -1 none
   if (csize > 16) return -1;
   if (cache[csize] == 0) {
     cudaLaunchConfig_t cfg{};
@@ -1292,7 +1293,6 @@ static int cluster_occupancy(int csize) {
     cfg.numAttrs = 1;
     int n = 0;
     cudaFuncSetAttribute(k_tc_layer<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<P>::SMEM_BYTES);
-    cudaFuncSetAttribute(k_tc_layer<P>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaError_t e = cudaOccupancyMaxActiveClusters(&n, k_tc_layer<P>, &cfg);
     if (e != cudaSuccess) cudaGetLastError();
     cache[csize] = (e == cudaSuccess && n >= 1) ? n : -1;
@@ -1338,24 +1338,37 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
   prm.budget_ns = 4000000000ull;
   prm.trace = h->trace_dev;
   const bool p1 = (h->precision == DSX_PREC_FP16);
-  const int grid = (g.tiles + kG - 1) / kG * kG;
-  const int occ = p1 ? cluster_occupancy<1>(kG) : cluster_occupancy<3>(kG);
+  const int occ = p1 ? cluster_occupancy<1>(h, kG) : cluster_occupancy<3>(h, kG);
   h->cluster_occ = occ;
-  // the stack needs every CTA co-resident (tiles wait on their neighbours' publish counters)
-  const bool stack = h->stack_mode && (l1 - l0 > 1) && occ >= 1 && grid <= occ * kG;
+  // Stack mode needs every CTA of a launch co-resident (tiles wait on their neighbours' publish counters): the batch is
+  // cut into groups of whole utterances that fit the machine, one persistent launch per group and evaluation.
+  const int cap_tiles = occ > 0 ? occ * kG : 0;
+  const int utt_per_group = (g.tiles_per_utt > 0) ? cap_tiles / g.tiles_per_utt : 0;
+  const bool stack = h->stack_mode && (l1 - l0 > 1) && utt_per_group >= 1;
   if (stack) {
-    DSX_TRY(ensure_flags(h, grid));
-    if (h->flags_grid != grid) {      // counters are only in lockstep among the CTAs of one grid size
+    DSX_TRY(ensure_flags(h, g.tiles + 2));
+    if (h->flags_geom_b != g.B || h->flags_geom_t != g.T) {   // counters are in lockstep only within one geometry
       DSX_CUDA(cudaMemsetAsync(h->flags_dev, 0, static_cast<size_t>(h->flags_cap) * sizeof(unsigned int), s));
       h->flag_count = 0;
-      h->flags_grid = grid;
+      h->flags_geom_b = g.B;
+      h->flags_geom_t = g.T;
     }
     prm.l0 = l0; prm.l1 = l1;
     prm.flags = h->flags_dev;
     prm.flag_base = h->flag_count;
+    for (int b0 = 0; b0 < g.B; b0 += utt_per_group) {
+      const int nb = std::min(utt_per_group, g.B - b0);
+      prm.tile0 = b0 * g.tiles_per_utt;
+      prm.tile_end = (b0 + nb) * g.tiles_per_utt;
+      const int grid = (prm.tile_end - prm.tile0 + kG - 1) / kG * kG;
+      DSX_TRY(p1 ? launch_tc_layer_t<1>(h, prm, grid, kG, s) : launch_tc_layer_t<3>(h, prm, grid, kG, s));
+    }
     h->flag_count += static_cast<unsigned int>(kEpiWarps * (l1 - l0 - 1));
-    return p1 ? launch_tc_layer_t<1>(h, prm, grid, kG, s) : launch_tc_layer_t<3>(h, prm, grid, kG, s);
+    return DSX_OK;
   }
+  const int grid = (g.tiles + kG - 1) / kG * kG;
+  prm.tile0 = 0;
+  prm.tile_end = g.tiles;
   for (int l = l0; l < l1; ++l) {
     prm.l0 = l; prm.l1 = l + 1;
     DSX_TRY(p1 ? launch_tc_layer_t<1>(h, prm, grid, kG, s) : launch_tc_layer_t<3>(h, prm, grid, kG, s));
@@ -1366,7 +1379,7 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
 template <int P>
 static int launch_tc_head_t(dsx_handle* h, const TcHeadParams& prm, int tiles, cudaStream_t s) {
   using Cfg = HeadCfg<P>;
-  static bool attr_done = false;
+  bool& attr_done = h->attr_head[P == 1 ? 0 : 1];
   if (!attr_done) {
     DSX_CUDA(cudaFuncSetAttribute(k_tc_head<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;

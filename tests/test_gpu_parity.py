@@ -198,7 +198,7 @@ def test_stack_mode_matches_per_layer_launches(dsx):
         s, dev = make_sampler(dsx, 4, "fp16x3")
         s.set_option(_capi.OPT_STACK_MODE, mode)
         outs = []
-        for B, T in ((1, 96), (2, 96), (3, 333), (1, 300), (2, 1000)):
+        for B, T in ((1, 96), (2, 96), (3, 333), (1, 300), (2, 1000), (40, 520)):     # last: 200 tiles -> 2 groups
             x, cond = rs_normal(40 + B, (B, 1, 80, T)).to(dev), rs_normal(50 + T, (B, 256, T)).to(dev)
             t = torch.full((B,), 7, dtype=torch.long, device=dev)
             outs.append(s.diffnet_forward(x, t, cond).cpu())
@@ -264,3 +264,37 @@ def test_full_size_eval_against_fp32_path(dsx, prec, tol):
     with torch.no_grad():
         ref = O.diffnet_forward(sd, x[:1], t[:1], cond[:1], 1)
     assert (res["fp32"][:1] - ref).abs().max() < 2e-4
+
+
+def test_error_behaviour_is_loud(dsx):
+    """Call-order and argument errors come back as DsxError with the C ABI's message; no silent fallback."""
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    dev = torch.device("cuda", 0)
+    net = make_net(dsx, 1, dev)
+    s = dsx.DsxSampler(net, "fp16x3", 1)
+    s.ensure_weights(dev)
+    x, cond = torch.zeros(1, 1, 80, 64, device=dev), torch.zeros(1, 256, 64, device=dev)
+    with pytest.raises(dsx.DsxError, match="dsx_set_schedule"):
+        s.sample_ddpm(x, cond, 100, 2)                      # schedule not loaded
+    s.set_schedule(S)
+    with pytest.raises(dsx.DsxError, match="outside schedule"):
+        s.sample_ddpm(x, cond, 101, 2)                      # t_start beyond the schedule
+    with pytest.raises(dsx.DsxError):
+        s.sample_ddpm(x.cpu(), cond, 100, 2)                # CPU tensor
+    out = s.sample_ddpm(x, cond, 100, 2, seed=3)            # still usable afterwards
+    assert torch.isfinite(out).all()
+    # a model the tensor-core path cannot take (channels != 256) is refused for fp16 modes, served by fp32
+    hp = dict(HP, residual_channels=64, hidden_size=64, residual_layers=3)
+    torch.manual_seed(0)
+    small = dsx.DiffNet(80, hparams=hp).to(dev).eval()
+    with pytest.raises(dsx.DsxError, match="256"):
+        dsx.DsxSampler(small, "fp16x3", 1).ensure_weights(dev)
+    s32 = dsx.DsxSampler(small, "fp32", 1)
+    xs, cs, ts = rs_normal(1, (2, 1, 80, 70)), rs_normal(2, (2, 64, 70)), torch.tensor([3, 9])
+    eps = s32.diffnet_forward(xs.to(dev), ts.to(dev), cs.to(dev)).cpu()
+    sd = {k: v.detach().cpu() for k, v in small.state_dict().items()}
+    with torch.no_grad():
+        ref = O.diffnet_forward(sd, xs, ts, cs, 1)
+    assert (eps - ref).abs().max() < 1e-5
+    s.close()
+    s32.close()
