@@ -66,6 +66,11 @@ struct TcCfg {
   // ring units consumed per k-block: GEMM1 {A_hi, W_hi [, W_lo, A_lo]}, GEMM2 {W_hi [, W_lo]}
   static constexpr int U1 = (P == 1) ? 2 : 4;
   static constexpr int U2 = (P == 1) ? 1 : 2;
+  // Ring slot of unit `ul` of a layer.  The first four k-blocks (the conditioner k-blocks, which do not depend on the
+  // previous layer) cycle through the non-staging slots only, so they can be loaded and multiplied while the previous
+  // layer's skip epilogue still owns the staging slots; after that the whole ring is used.
+  static constexpr int S0 = 4 * U1;
+  __host__ __device__ static constexpr int slot(int ul) { return ul < S0 ? ul % (UNITS - STG_UNITS) : (ul - S0) % UNITS; }
 };
 
 struct TcLayerParams {
@@ -99,6 +104,11 @@ __device__ __forceinline__ float tanh_acc(float x) {
   return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * x)), -1.f);
 }
 __device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+
+// Order in which GEMM1 consumes its 16 k-blocks (k-block = tap*4 + channel block, 12..15 = conditioner): conditioner
+// first (no dependency on the previous layer), then the centre tap (this tile's own y), the halo taps last (they
+// need the neighbour tiles' y) -- so a layer starts its MMAs while the neighbours are still publishing.
+__device__ __forceinline__ int kb_order(int ko) { return ko < 4 ? 12 + ko : (ko < 8 ? ko : (ko < 12 ? ko - 8 : ko - 4)); }
 
 // publish / wait on a tile's counter in global memory (gpu scope)
 __device__ __forceinline__ void flag_publish(unsigned int* f) {
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       if (li > 0) ok = mbar_wait(g2done, prev, wd, 105);            // ring-2 / z units of the previous layer are free
       int ul = 0;                                                   // unit index within the layer
       auto acquire = [&](int code) -> uint8_t* {
-        const int s = ul % NU;
+        const int s = Cfg::slot(ul);
         if (!e_ok && s >= NU - Cfg::STG_UNITS) {                    // staging units: previous epilogue must be done
           ok = mbar_wait(edone, prev, wd, 106);
           e_ok = true;
@@ -246,17 +256,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         if (prank == 0) mbar_arrive_expect_tx(&full[s], G * kUnitBytes);
         return ring + s * kUnitBytes;
       };
+      bool yn_ok = y_ok;                                            // neighbours' y (halo taps)
       auto load_a = [&](int plane, int kb) {
-        if (!y_ok) {                                                // y_l of this tile and its neighbours
-          const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
+        const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
+        if (kb < 12 && !y_ok) {                                     // centre tap: y_l of this tile
           ok = flag_wait(p.flags + tile, target, wd, 107);
-          if (ok && nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
-          if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
           fence_proxy_async_all();
           y_ok = true;
           if (!ok) return;
         }
-        const int s = ul % NU;
+        if (kb < 12 && (kb >> 2) != 1 && !yn_ok) {                  // halo taps: y_l of the neighbour tiles
+          if (nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
+          if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
+          fence_proxy_async_all();
+          yn_ok = true;
+          if (!ok) return;
+        }
+        const int s = Cfg::slot(ul);
         uint8_t* dst = acquire(101);
         if (!dst) return;
         if (kb < 12)
@@ -266,14 +282,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         ++ul;
       };
       auto load_w = [&](int tileidx) {
-        const int s = ul % NU;
+        const int s = Cfg::slot(ul);
         uint8_t* dst = acquire(102);
         if (!dst) return;
         tma_load_2d<G>(&p.tm_w, &full[s], dst, 0, w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
         ++ul;
       };
       for (int h = 0; h < 2 && ok; ++h)
-        for (int kb = 0; kb < 16 && ok; ++kb) {
+        for (int ko = 0; ko < 16 && ok; ++ko) {
+          const int kb = kb_order(ko);
           load_a(0, kb);
           if (ok) load_w((0 * 2 + h) * 16 + kb);
           if (P == 3) {
@@ -317,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       const int li = l - p.l0;
       int ul = 0, u2 = 0;
       auto wait_unit = [&](int uu, int code) -> uint64_t {
-        const int s = uu % NU;
+        const int s = Cfg::slot(uu);
         ok = ok && mbar_wait(&full[s], (mbits >> s) & 1, wd, code);
         mbits ^= 1u << s;
         return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
@@ -353,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
             tc_fence_after();
             mma4(d, a_lo, w_hi, acc);
           }
-          for (int i = 0; i < Cfg::U1; ++i) umma_commit<G>(&empty[(ul + i) % NU], pair_mask);
+          for (int i = 0; i < Cfg::U1; ++i) umma_commit<G>(&empty[Cfg::slot(ul + i)], pair_mask);
           ul += Cfg::U1;
         }
         if (ok) umma_commit<G>(&tfull[buf], pair_mask);
