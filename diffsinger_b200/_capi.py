@@ -6,8 +6,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DSX_LIB", os.path.join(_HERE, "lib", "libdsx.so"))
 
-PREC_FP32_SIMT, PREC_FP16, PREC_FP16X3 = 0, 1, 3
-PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "fp16": PREC_FP16, "fp16x3": PREC_FP16X3}
+PREC_FP32_SIMT, PREC_FP16, PREC_FP16X2, PREC_FP16X3 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "fp16": PREC_FP16, "fp16x2": PREC_FP16X2,
+              "fp16x3": PREC_FP16X3}
 (INFO_PRECISION, INFO_KERNEL_LAUNCHES, INFO_WORKSPACE_BYTES, INFO_SM_COUNT, INFO_TC_CTA_GROUP, INFO_LAYER_KERNEL_NS,
  INFO_LAYER_KERNEL_LAUNCHES, INFO_STACK_MODE, INFO_CLUSTER_OCCUPANCY) = range(9)
 OPT_TC_CTA_GROUP, OPT_RESERVED_1, OPT_PROFILE, OPT_STACK_MODE = 0, 1, 2, 3

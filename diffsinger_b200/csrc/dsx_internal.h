@@ -124,8 +124,8 @@ struct dsx_handle {
   int flags_cap = 0;
   int flags_geom_b = 0, flags_geom_t = 0;   // geometry of the last stack launch
   unsigned int flag_count = 0;         // value of every counter before the next stack launch
-  bool attr_layer[2] = {false, false}, attr_head[2] = {false, false};
-  int occ_cache[2][17] = {};
+  bool attr_layer[3] = {false, false, false}, attr_head[2] = {false, false};
+  int occ_cache[3][17] = {};
   int cluster_occ = 0;              // max co-resident utterance clusters reported by the driver (last launch)
   int stack_mode = 1;               // 1: all residual layers of an evaluation in one cluster-per-utterance launch
   long long* trace_dev = nullptr;   // debug timeline buffer (dsx_debug_trace)

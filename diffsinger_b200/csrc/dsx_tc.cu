@@ -49,13 +49,18 @@ constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowBytes;
 
 template <int P>
 struct TcCfg {
-  static constexpr int Z_PLANES = (P == 1) ? 1 : 2;
+  // P = number of MMA passes of the parity scheme: 1 = fp16 operands; 2 = weights hi+lo, activations fp16 except the
+  // conditioner (hi+lo); 3 = hi+lo on both operands everywhere.
+  static constexpr bool WLO = (P >= 2);     // W_lo pass
+  static constexpr bool ALO_T = (P == 3);   // A_lo pass on the conv taps (y) and on z
+  static constexpr bool ALO_C = (P >= 2);   // A_lo pass on the conditioner k-blocks
+  static constexpr int Z_PLANES = ALO_T ? 2 : 1;
   // GEMM1 streams through a ring of UNITS 16 KB units.  z (the A operand of GEMM2) is [planes][4 k-blocks]
   // of 16 KB: k-blocks 0,1 (written while GEMM1 still runs) have their own buffer; k-blocks 2,3 are written
   // after GEMM1 has finished and alias the last Z23_UNITS ring units, so GEMM2's weight ring is the first
   // UNITS2 units only.
   // Epilogue 2 transposes the accumulator through STG_UNITS more ring units (free once GEMM1 is done).
-  static constexpr int UNITS = (P == 1) ? 11 : 10;
+  static constexpr int UNITS = (P == 1) ? 11 : (P == 2 ? 12 : 10);
   static constexpr int Z23_UNITS = 2 * Z_PLANES;
   static constexpr int STG_UNITS = 2;                           // 8 warps x 32 rows x 128 B
   static constexpr int UNITS2 = UNITS - Z23_UNITS - STG_UNITS;   // ring layout: [ring2 | z23 | staging]
@@ -64,12 +69,13 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = 1024 + UNITS * kUnitBytes + Z01_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   // ring units consumed per k-block: GEMM1 {A_hi, W_hi [, W_lo, A_lo]}, GEMM2 {W_hi [, W_lo]}
-  static constexpr int U1 = (P == 1) ? 2 : 4;
-  static constexpr int U2 = (P == 1) ? 1 : 2;
+  static constexpr int UT = 2 + (WLO ? 1 : 0) + (ALO_T ? 1 : 0);   // conv-tap k-block
+  static constexpr int UC = 2 + (WLO ? 1 : 0) + (ALO_C ? 1 : 0);   // conditioner k-block
+  static constexpr int U2 = 1 + (WLO ? 1 : 0);
   // Ring slot of unit `ul` of a layer.  The first four k-blocks (the conditioner k-blocks, which do not depend on the
   // previous layer) cycle through the non-staging slots only, so they can be loaded and multiplied while the previous
   // layer's skip epilogue still owns the staging slots; after that the whole ring is used.
-  static constexpr int S0 = 4 * U1;
+  static constexpr int S0 = 4 * UC;
   __host__ __device__ static constexpr int slot(int ul) { return ul < S0 ? ul % (UNITS - STG_UNITS) : (ul - S0) % UNITS; }
 };
 
@@ -193,10 +199,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
     tma_prefetch_desc(&p.tm_y[0][0]);
     tma_prefetch_desc(&p.tm_y[1][0]);
     tma_prefetch_desc(&p.tm_cond[0]);
-    if (P == 3) {
+    if (Cfg::ALO_C) tma_prefetch_desc(&p.tm_cond[1]);
+    if (Cfg::ALO_T) {
       tma_prefetch_desc(&p.tm_y[0][1]);
       tma_prefetch_desc(&p.tm_y[1][1]);
-      tma_prefetch_desc(&p.tm_cond[1]);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -293,10 +299,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
           const int kb = kb_order(ko);
           load_a(0, kb);
           if (ok) load_w((0 * 2 + h) * 16 + kb);
-          if (P == 3) {
-            if (ok) load_w((1 * 2 + h) * 16 + kb);
-            if (ok) load_a(1, kb);
-          }
+          if (Cfg::WLO && ok) load_w((1 * 2 + h) * 16 + kb);
+          if ((kb >= 12 ? Cfg::ALO_C : Cfg::ALO_T) && ok) load_a(1, kb);
         }
       // GEMM2 weights: second ring over units 0..NU2-1, usable once every GEMM1 MMA has completed
       if (ok) ok = mbar_wait(g1done, li & 1, wd, 103);
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       for (int q = 0; q < 2 && ok; ++q)
         for (int kb = 0; kb < 4 && ok; ++kb) {
           load_w2(64 + (0 * 2 + q) * 4 + kb);
-          if (P == 3 && ok) load_w2(64 + (1 * 2 + q) * 4 + kb);
+          if (Cfg::WLO && ok) load_w2(64 + (1 * 2 + q) * 4 + kb);
         }
     }
   } else if (warp == 1 && lane == 0 && prank == 0) {
@@ -353,25 +357,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         tc_fence_after();
         const uint32_t d = tmem_base + buf * 256;
         uint32_t acc = 0;
-        for (int kb = 0; kb < 16 && ok; ++kb) {
+        for (int ko = 0; ko < 16 && ok; ++ko) {
+          const bool alo = (ko < 4) ? Cfg::ALO_C : Cfg::ALO_T;    // k-blocks 0..3 of the order are the conditioner
+          const int nu = 2 + (Cfg::WLO ? 1 : 0) + (alo ? 1 : 0);
           const uint64_t a_hi = wait_unit(ul, 202);
           const uint64_t w_hi = wait_unit(ul + 1, 202);
           if (!ok) break;
-          DSX_TRACE(1, ul);
+          DSX_TRACE(1, ko + 16 * h);
           tc_fence_after();
           mma4(d, a_hi, w_hi, acc);
-          if (P == 3) {
+          if (Cfg::WLO) {
             const uint64_t w_lo = wait_unit(ul + 2, 202);
             if (!ok) break;
             tc_fence_after();
             mma4(d, a_hi, w_lo, acc);
+          }
+          if (alo) {
             const uint64_t a_lo = wait_unit(ul + 3, 202);
             if (!ok) break;
             tc_fence_after();
             mma4(d, a_lo, w_hi, acc);
           }
-          for (int i = 0; i < Cfg::U1; ++i) umma_commit<G>(&empty[Cfg::slot(ul + i)], pair_mask);
-          ul += Cfg::U1;
+          for (int i = 0; i < nu; ++i) umma_commit<G>(&empty[Cfg::slot(ul + i)], pair_mask);
+          ul += nu;
         }
         if (ok) umma_commit<G>(&tfull[buf], pair_mask);
       }
@@ -401,11 +409,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
           DSX_TRACE(1, 128 + u2);
           tc_fence_after();
           mma4(d, z_hi, w_hi, acc);
-          if (P == 3) {
+          if (Cfg::WLO) {
             const uint64_t w_lo = wait_unit2(u2 + 1, 205);
             if (!ok) break;
             tc_fence_after();
             mma4(d, z_hi, w_lo, acc);
+          }
+          if (Cfg::ALO_T) {
             const uint64_t z_lo = umma_desc_sw128(smem_u32(zaddr(1, kb)));
             mma4(d, z_lo, w_hi, acc);
           }
@@ -495,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
               const __half2 h01 = __floats2half2_rn(z4[0], z4[1]), h23 = __floats2half2_rn(z4[2], z4[3]);
               hi[e] = h2_bits(h01);
               hi[e + 1] = h2_bits(h23);
-              if (P == 3) {
+              if (Cfg::ALO_T) {
                 const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                 lo[e] = h2_bits(__floats2half2_rn(z4[0] - f01.x, z4[1] - f01.y));
                 lo[e + 1] = h2_bits(__floats2half2_rn(z4[2] - f23.x, z4[3] - f23.y));
@@ -503,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
             }
             const int off = ((half * 4 + c8) ^ (r & 7)) << 4;   // this warp's 32 channels = chunks 4*half .. +3
             *reinterpret_cast<uint4*>(zrow + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (P == 3) *reinterpret_cast<uint4*>(zrow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (Cfg::ALO_T) *reinterpret_cast<uint4*>(zrow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           if (h == 1) {
             tc_fence_before();
@@ -596,7 +606,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
                 const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l;
                 const __half2 hh = __floats2half2_rn(sa, sb);
                 *reinterpret_cast<__half2*>(sp + it * 2 * kC + j) = hh;
-                if (P == 3) {
+                if (P >= 2) {
                   const float2 hf = __half22float2(hh);
                   *reinterpret_cast<__half2*>(sp + p.plane_elems + it * 2 * kC + j) = __floats2half2_rn(sa - hf.x, sb - hf.y);
                 }
@@ -605,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
                 const float ya = v.x + dnv.x, yb = v.y + dnv.y;
                 const __half2 hh = __floats2half2_rn(ya, yb);
                 *reinterpret_cast<__half2*>(yp + it * 2 * kC + j) = hh;
-                if (P == 3) {
+                if (Cfg::ALO_T) {
                   const float2 hf = __half22float2(hh);
                   *reinterpret_cast<__half2*>(yp + p.plane_elems + it * 2 * kC + j) = __floats2half2_rn(ya - hf.x, yb - hf.y);
                 }
@@ -1269,7 +1279,7 @@ int tc_prepare_maps(dsx_handle* h, const Geom& g) {
 template <int P>
 static int launch_tc_layer_t(dsx_handle* h, const TcLayerParams& prm, int grid, int csize, cudaStream_t s) {
   using Cfg = TcCfg<P>;
-  bool& attr_done = h->attr_layer[P == 1 ? 0 : 1];      // function attributes are per device -> per handle
+  bool& attr_done = h->attr_layer[P - 1];      // function attributes are per device -> per handle
   if (!attr_done) {
     DSX_CUDA(cudaFuncSetAttribute(k_tc_layer<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
@@ -1294,7 +1304,7 @@ static int launch_tc_layer_t(dsx_handle* h, const TcLayerParams& prm, int grid, 
 // Can a cluster of `csize` CTAs of the layer kernel be scheduled on this device?  (cached per size)
 template <int P>
 static int cluster_occupancy(dsx_handle* h, int csize) {
-  int* cache = h->occ_cache[P == 1 ? 0 : 1];   // per handle (= per device): 0 unknown, >0 max co-resident clusters, -1 none
+  int* cache = h->occ_cache[P - 1];   // per handle (= per device): 0 unknown, >0 max co-resident clusters, -1 none
   if (csize > 16) return -1;
   if (cache[csize] == 0) {
     cudaLaunchConfig_t cfg{};
@@ -1354,8 +1364,12 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
   prm.status = h->status_dev;
   prm.budget_ns = 4000000000ull;
   prm.trace = h->trace_dev;
-  const bool p1 = (h->precision == DSX_PREC_FP16);
-  const int occ = p1 ? cluster_occupancy<1>(h, kG) : cluster_occupancy<3>(h, kG);
+  const int P = h->precision;   // DSX_PREC_FP16 = 1, FP16X2 = 2, FP16X3 = 3 == MMA passes
+  auto launch = [&](int grid) -> int {
+    return P == 1 ? launch_tc_layer_t<1>(h, prm, grid, kG, s)
+                  : (P == 2 ? launch_tc_layer_t<2>(h, prm, grid, kG, s) : launch_tc_layer_t<3>(h, prm, grid, kG, s));
+  };
+  const int occ = P == 1 ? cluster_occupancy<1>(h, kG) : (P == 2 ? cluster_occupancy<2>(h, kG) : cluster_occupancy<3>(h, kG));
   h->cluster_occ = occ;
   // Stack mode needs every CTA of a launch co-resident (tiles wait on their neighbours' publish counters): the batch is
   // cut into groups of whole utterances that fit the machine, one persistent launch per group and evaluation.
@@ -1378,7 +1392,7 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
       prm.tile0 = b0 * g.tiles_per_utt;
       prm.tile_end = (b0 + nb) * g.tiles_per_utt;
       const int grid = (prm.tile_end - prm.tile0 + kG - 1) / kG * kG;
-      DSX_TRY(p1 ? launch_tc_layer_t<1>(h, prm, grid, kG, s) : launch_tc_layer_t<3>(h, prm, grid, kG, s));
+      DSX_TRY(launch(grid));
     }
     h->flag_count += static_cast<unsigned int>(kEpiWarps * (l1 - l0 - 1));
     return DSX_OK;
@@ -1388,7 +1402,7 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
   prm.tile_end = g.tiles;
   for (int l = l0; l < l1; ++l) {
     prm.l0 = l; prm.l1 = l + 1;
-    DSX_TRY(p1 ? launch_tc_layer_t<1>(h, prm, grid, kG, s) : launch_tc_layer_t<3>(h, prm, grid, kG, s));
+    DSX_TRY(launch(grid));
   }
   return DSX_OK;
 }

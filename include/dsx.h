@@ -39,7 +39,9 @@ enum {
 enum {
   DSX_PREC_FP32_SIMT = 0, /* fp32 CUDA-core path, any channel count                          */
   DSX_PREC_FP16 = 1,      /* tcgen05 kind::f16, fp16 operands, fp32 accumulate (fast mode)   */
-  DSX_PREC_FP16X3 = 3     /* tcgen05, hi+lo fp16 split of both operands, 3 MMAs (parity mode)*/
+  DSX_PREC_FP16X2 = 2,    /* tcgen05, weights and conditioner hi+lo, running activations fp16: 2 MMA passes (3 on
+                             the conditioner k-blocks); max |d| ~2e-4 after 100 steps (default parity mode)       */
+  DSX_PREC_FP16X3 = 3     /* tcgen05, hi+lo fp16 split of both operands, 3 MMAs (fp32-equivalent)*/
 };
 
 typedef struct dsx_handle dsx_handle;

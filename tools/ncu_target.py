@@ -6,7 +6,7 @@ import bench
 import diffsinger_b200 as dsx
 from oracle import diffnet_oracle as O
 
-prec = sys.argv[1] if len(sys.argv) > 1 else "fp16x3"
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp16x2"
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda", 0)
 net = bench.make_net(dsx, dev)

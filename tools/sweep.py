@@ -24,7 +24,7 @@ for name, B, T, (Ts, mb), K, interval, cycle in CFG:
     S = O.make_schedule(O.linear_beta_schedule(Ts, mb))
     cond, xT = bench.make_inputs(B, T, 0)
     cond, xT = cond.to(dev).transpose(1, 2), xT.to(dev)
-    for prec in ("fp16x3", "fp16"):
+    for prec in ("fp16x3", "fp16x2", "fp16"):
         s = dsx.DsxSampler(net, prec, cycle)
         s.ensure_weights(dev)
         s.set_schedule(S)

@@ -24,16 +24,16 @@ s.diffnet_forward(xT, t, cond)
 buf = np.zeros(6 * 256, dtype=np.int64)
 check(lib.dsx_debug_trace(s._h, 0, buf.ctypes.data_as(ctypes.c_void_p)))
 tr = buf.reshape(2, 3, 256)
-P = 1 if prec == "fp16" else 3
-U1, U2 = (2, 1) if P == 1 else (4, 2)
+P = {"fp16": 1, "fp16x2": 2, "fp16x3": 3}[prec]
+U1, U2 = 1, (1 if P == 1 else 2)      # MMA stamps are per k-block now (slot = order index + 16*chunk)
 for cta in (0, 1):
     t0 = tr[cta, 0, 254]
     rel = lambda v: int(v - t0) if v else -1
     print(f"--- CTA {cta} ({prec}); cycles since setup done; all roles done at {rel(tr[cta,0,255])}; "
           f"kernel entry at {rel(tr[cta,0,250])}, exit at {rel(tr[cta,0,251])}; entry->exit {(tr[cta,1,251]-tr[cta,1,250])/1e3:.1f} us (globaltimer)")
-    print("producer ring1 issue (first unit of each k-block):", [rel(v) for v in tr[cta, 0, 0:32 * U1:U1]])
+    print("producer ring1 issue (first units):", [rel(v) for v in tr[cta, 0, 0:40]])
     print("producer ring2 issue:", [rel(v) for v in tr[cta, 0, 128:128 + 8 * U2]])
-    print("mma k-block start (GEMM1):", [rel(v) for v in tr[cta, 1, 0:32 * U1:U1]])
+    print("mma k-block start (GEMM1, chunk 0 then chunk 1, order cond|centre|halo):", [rel(v) for v in tr[cta, 1, 0:32]])
     print("mma k-block start (GEMM2):", [rel(v) for v in tr[cta, 1, 128:128 + 8 * U2:U2]])
     print("mma: before zfull wait, after zfull, tempty q0, q1:", [rel(v) for v in tr[cta, 1, 200:204]])
     e = [rel(v) for v in tr[cta, 2, :13]]
