@@ -333,6 +333,8 @@ int dsx_load_diffnet(dsx_handle* h, const dsx_diffnet_params* p, int M, int C, i
   if (precision != DSX_PREC_FP32_SIMT) {
     DSX_CHECK(h->tc_group != 0, DSX_E_INVALID, "tcgen05 precisions need an sm_100 device");
     DSX_CHECK(tc_supported(h), DSX_E_INVALID, "tcgen05 path needs residual_channels == hidden_size == 256");
+    DSX_CHECK(dilation_cycle <= 4, DSX_E_INVALID,
+              "tcgen05 path supports dilations up to 8 (dilation_cycle_length <= 4, got %d); use DSX_PREC_FP32_SIMT", dilation_cycle);
   }
   DSX_TRY(simt_pack_model(h, p, s));
   if (precision != DSX_PREC_FP32_SIMT) DSX_TRY(tc_pack_model(h, s));

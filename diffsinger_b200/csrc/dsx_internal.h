@@ -114,7 +114,7 @@ struct dsx_handle {
   dsx::Workspace ws;
   int* status_dev = nullptr;   // kernel watchdog / self-check word
   int* status_host = nullptr;  // pinned mirror
-  CUtensorMap tm_w{}, tm_y[2][2]{}, tm_cond[2]{}, tm_s16[2]{}, tm_whead{};
+  CUtensorMap tm_w{}, tm_y[2][2]{}, tm_yh[2]{}, tm_cond[2]{}, tm_s16[2]{}, tm_whead{};
   dsx::Geom tm_geom;           // geometry the activation maps were built for
   int tm_group = 0;
   int profile = 0;

@@ -60,18 +60,26 @@ struct TcCfg {
   // after GEMM1 has finished and alias the last Z23_UNITS ring units, so GEMM2's weight ring is the first
   // UNITS2 units only.
   // Epilogue 2 transposes the accumulator through STG_UNITS more ring units (free once GEMM1 is done).
-  static constexpr int UNITS = (P == 1) ? 11 : (P == 2 ? 12 : 10);
+  // SHIFT (P <= 2): the three dilated taps of a 64-channel block share ONE shared-memory copy of the activations:
+  // a slot holds [8 halo rows | 128 centre rows | 8 halo rows] (18 KB) and tap j's UMMA descriptor simply starts
+  // (8 + (j-1)*d) rows in (SWIZZLE_128B is a function of the absolute address; verified by dsx_selftest(2)).  That cuts
+  // the bytes TMA must push into each SM -- the measured limiter of GEMM1 (~35-40 B/cycle/SM) -- by 14-21 %.
+  // P == 3 has no shared memory left for 18 KB slots and keeps one 16 KB tile per tap.
+  static constexpr bool SHIFT = (P <= 2);
+  static constexpr int SLOT = SHIFT ? (kTile + 16) * 128 : kUnitBytes;
+  static constexpr int UNITS = 10;
   static constexpr int Z23_UNITS = 2 * Z_PLANES;
   static constexpr int STG_UNITS = 2;                           // 8 warps x 32 rows x 128 B
   static constexpr int UNITS2 = UNITS - Z23_UNITS - STG_UNITS;   // ring layout: [ring2 | z23 | staging]
   static constexpr int Z01_BYTES = Z_PLANES * 2 * kUnitBytes;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = 1024 + UNITS * kUnitBytes + Z01_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + UNITS * SLOT + Z01_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   // ring units consumed per k-block: GEMM1 {A_hi, W_hi [, W_lo, A_lo]}, GEMM2 {W_hi [, W_lo]}
   static constexpr int UT = 2 + (WLO ? 1 : 0) + (ALO_T ? 1 : 0);   // conv-tap k-block
   static constexpr int UC = 2 + (WLO ? 1 : 0) + (ALO_C ? 1 : 0);   // conditioner k-block
   static constexpr int U2 = 1 + (WLO ? 1 : 0);
+  static constexpr int UG = 1 + 3 * (1 + (WLO ? 1 : 0));          // SHIFT: one 64-channel block = y unit + 3 taps x {W_hi [, W_lo]}
   // Ring slot of unit `ul` of a layer.  The first four k-blocks (the conditioner k-blocks, which do not depend on the
   // previous layer) cycle through the non-staging slots only, so they can be loaded and multiplied while the previous
   // layer's skip epilogue still owns the staging slots; after that the whole ring is used.
@@ -83,6 +91,7 @@ struct TcLayerParams {
   CUtensorMap tm_w;          // packed weights, 2D [rows][64], box 64 x 128 rows
   CUtensorMap tm_y[2][2];    // conv input, [buffer = layer parity][plane hi/lo], 3D [B][T][256]
   CUtensorMap tm_cond[2];    // conditioner, planes hi/lo
+  CUtensorMap tm_yh[2];      // conv input hi plane of buffer 0 / 1 with a box of 8 frames (halo rows of the SHIFT layout)
   float* X;                  // [B][Tp][256] residual stream (in/out)
   float* SKIP;               // [B][Tp][256]
   __half* Y;                 // [2 buffers][2 planes][plane_elems]: layer l reads buffer l&1, writes buffer (l+1)&1
@@ -157,8 +166,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   constexpr int NU2 = Cfg::UNITS2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* z01 = ring + NU * kUnitBytes;
-  uint8_t* staging = ring + (NU - Cfg::STG_UNITS) * kUnitBytes;   // last ring units: epilogue-2 transpose
+  uint8_t* z01 = ring + NU * Cfg::SLOT;
+  uint8_t* staging = ring + (NU - Cfg::STG_UNITS) * Cfg::SLOT;   // last ring units: epilogue-2 transpose
   uint64_t* bars = reinterpret_cast<uint64_t*>(z01 + Cfg::Z01_BYTES);
   uint64_t* full = bars;             // [NU]   GEMM1 ring
   uint64_t* empty = full + NU;       // [NU]
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(edone + 1);
   // z k-block address: plane 0 = hi, 1 = lo.  k-blocks 2,3 alias ring units [NU2, NU2 + Z23_UNITS)
   auto zaddr = [&](int plane, int kb) -> uint8_t* {
-    return kb < 2 ? z01 + (plane * 2 + kb) * kUnitBytes : ring + (NU2 + plane * 2 + (kb - 2)) * kUnitBytes;
+    return kb < 2 ? z01 + (plane * 2 + kb) * kUnitBytes : ring + (NU2 + plane * 2 + (kb - 2)) * Cfg::SLOT;
   };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       bool y_ok = (li == 0) || !multi || !tile_valid, e_ok = (li == 0);
       if (li > 0) ok = mbar_wait(g2done, prev, wd, 105);            // ring-2 / z units of the previous layer are free
       int ul = 0;                                                   // unit index within the layer
-      auto acquire = [&](int code) -> uint8_t* {
+      auto acquire = [&](int code, int bytes = kUnitBytes) -> uint8_t* {
         const int s = Cfg::slot(ul);
         if (!e_ok && s >= NU - Cfg::STG_UNITS) {                    // staging units: previous epilogue must be done
           ok = mbar_wait(edone, prev, wd, 106);
@@ -259,8 +268,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         if (!ok) return nullptr;
         pbits ^= 1u << s;
         DSX_TRACE(0, ul);
-        if (prank == 0) mbar_arrive_expect_tx(&full[s], G * kUnitBytes);
-        return ring + s * kUnitBytes;
+        if (prank == 0) mbar_arrive_expect_tx(&full[s], G * bytes);
+        return ring + s * Cfg::SLOT;
       };
       bool yn_ok = y_ok;                                            // neighbours' y (halo taps)
       auto load_a = [&](int plane, int kb) {
@@ -294,14 +303,52 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         tma_load_2d<G>(&p.tm_w, &full[s], dst, 0, w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
         ++ul;
       };
-      for (int h = 0; h < 2 && ok; ++h)
-        for (int ko = 0; ko < 16 && ok; ++ko) {
-          const int kb = kb_order(ko);
-          load_a(0, kb);
-          if (ok) load_w((0 * 2 + h) * 16 + kb);
-          if (Cfg::WLO && ok) load_w((1 * 2 + h) * 16 + kb);
-          if ((kb >= 12 ? Cfg::ALO_C : Cfg::ALO_T) && ok) load_a(1, kb);
+      if constexpr (!Cfg::SHIFT) {
+        for (int h = 0; h < 2 && ok; ++h)
+          for (int ko = 0; ko < 16 && ok; ++ko) {
+            const int kb = kb_order(ko);
+            load_a(0, kb);
+            if (ok) load_w((0 * 2 + h) * 16 + kb);
+            if (Cfg::WLO && ok) load_w((1 * 2 + h) * 16 + kb);
+            if ((kb >= 12 ? Cfg::ALO_C : Cfg::ALO_T) && ok) load_a(1, kb);
+          }
+      } else {
+        // one activation unit per 64-channel block: [8 halo | 128 centre | 8 halo] rows, three boxes, one barrier
+        auto load_y = [&](int cb) {
+          const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
+          if (!y_ok) {
+            ok = flag_wait(p.flags + tile, target, wd, 107);
+            if (ok && nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
+            if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
+            fence_proxy_async_all();
+            y_ok = true;
+            if (!ok) return;
+          }
+          const int s = Cfg::slot(ul);
+          uint8_t* dst = acquire(110, Cfg::SLOT);
+          if (!dst) return;
+          tma_load_3d<G>(&p.tm_yh[l & 1], &full[s], dst, cb * 64, t0 - 8, bq, lead);
+          tma_load_3d<G>(&ymap[0], &full[s], dst + 8 * 128, cb * 64, t0, bq, lead);
+          tma_load_3d<G>(&p.tm_yh[l & 1], &full[s], dst + (8 + kTile) * 128, cb * 64, t0 + kTile, bq, lead);
+          ++ul;
+        };
+        for (int h = 0; h < 2 && ok; ++h) {
+          for (int cb = 0; cb < 4 && ok; ++cb) {           // conditioner k-blocks first (no dependency on layer l-1)
+            load_a(0, 12 + cb);
+            if (ok) load_w((0 * 2 + h) * 16 + 12 + cb);
+            if (Cfg::WLO && ok) load_w((1 * 2 + h) * 16 + 12 + cb);
+            if (Cfg::ALO_C && ok) load_a(1, 12 + cb);
+          }
+          for (int cb = 0; cb < 4 && ok; ++cb) {
+            load_y(cb);
+            for (int tj = 0; tj < 3 && ok; ++tj) {         // tap order: centre, left, right
+              const int tap = tj == 0 ? 1 : (tj == 1 ? 0 : 2);
+              load_w((0 * 2 + h) * 16 + tap * 4 + cb);
+              if (Cfg::WLO && ok) load_w((1 * 2 + h) * 16 + tap * 4 + cb);
+            }
+          }
         }
+      }
       // GEMM2 weights: second ring over units 0..NU2-1, usable once every GEMM1 MMA has completed
       if (ok) ok = mbar_wait(g1done, li & 1, wd, 103);
       int u2 = 0;
@@ -312,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         pbits2 ^= 1u << s;
         DSX_TRACE(0, 128 + u2);
         if (prank == 0) mbar_arrive_expect_tx(&full2[s], G * kUnitBytes);
-        tma_load_2d<G>(&p.tm_w, &full2[s], ring + s * kUnitBytes, 0,
+        tma_load_2d<G>(&p.tm_w, &full2[s], ring + s * Cfg::SLOT, 0,
                        w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
         ++u2;
       };
@@ -341,13 +388,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         const int s = Cfg::slot(uu);
         ok = ok && mbar_wait(&full[s], (mbits >> s) & 1, wd, code);
         mbits ^= 1u << s;
-        return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
+        return umma_desc_sw128(smem_u32(ring + s * Cfg::SLOT));
       };
       auto wait_unit2 = [&](int uu, int code) -> uint64_t {
         const int s = uu % NU2;
         ok = ok && mbar_wait(&full2[s], (mbits2 >> s) & 1, wd, code);
         mbits2 ^= 1u << s;
-        return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
+        return umma_desc_sw128(smem_u32(ring + s * Cfg::SLOT));
       };
       for (int h = 0; h < 2 && ok; ++h) {
         const int buf = h;
@@ -357,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         tc_fence_after();
         const uint32_t d = tmem_base + buf * 256;
         uint32_t acc = 0;
-        for (int ko = 0; ko < 16 && ok; ++ko) {
+        for (int ko = 0; ko < (Cfg::SHIFT ? 4 : 16) && ok; ++ko) {
           const bool alo = (ko < 4) ? Cfg::ALO_C : Cfg::ALO_T;    // k-blocks 0..3 of the order are the conditioner
           const int nu = 2 + (Cfg::WLO ? 1 : 0) + (alo ? 1 : 0);
           const uint64_t a_hi = wait_unit(ul, 202);
@@ -380,6 +427,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
           }
           for (int i = 0; i < nu; ++i) umma_commit<G>(&empty[Cfg::slot(ul + i)], pair_mask);
           ul += nu;
+        }
+        if constexpr (Cfg::SHIFT) {
+          const int dil = 1 << (l % p.cycle);
+          for (int cb = 0; cb < 4 && ok; ++cb) {
+            const uint64_t y = wait_unit(ul, 206);              // [8 halo | 128 centre | 8 halo] rows of 64 channels
+            if (!ok) break;
+            DSX_TRACE(1, 4 + cb + 16 * h);
+            int uu = ul + 1;
+            for (int tj = 0; tj < 3 && ok; ++tj) {
+              const int tap = tj == 0 ? 1 : (tj == 1 ? 0 : 2);
+              const uint64_t a = y + static_cast<uint64_t>(((8 + (tap - 1) * dil) * 128) >> 4);   // row-shifted start
+              const uint64_t w_hi = wait_unit(uu, 207);
+              if (!ok) break;
+              tc_fence_after();
+              mma4(d, a, w_hi, acc);
+              umma_commit<G>(&empty[Cfg::slot(uu)], pair_mask);
+              ++uu;
+              if (Cfg::WLO) {
+                const uint64_t w_lo = wait_unit(uu, 207);
+                if (!ok) break;
+                tc_fence_after();
+                mma4(d, a, w_lo, acc);
+                umma_commit<G>(&empty[Cfg::slot(uu)], pair_mask);
+                ++uu;
+              }
+            }
+            umma_commit<G>(&empty[Cfg::slot(ul)], pair_mask);   // the y unit, after its last tap
+            ul = uu;
+          }
         }
         if (ok) umma_commit<G>(&tfull[buf], pair_mask);
       }
@@ -1240,13 +1316,13 @@ static int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint32_t
   DSX_CHECK(r == CUDA_SUCCESS, DSX_E_CUDA, "cuTensorMapEncodeTiled(2D) failed: %d", static_cast<int>(r));
   return DSX_OK;
 }
-// [B][T (stride Tp)][ch] fp16, box = 64 channels x 128 frames x 1
-static int make_map_act(CUtensorMap* m, const void* base, int ch, int T, int Tp, int B) {
+// [B][T (stride Tp)][ch] fp16, box = 64 channels x box_frames frames x 1
+static int make_map_act(CUtensorMap* m, const void* base, int ch, int T, int Tp, int B, int box_frames = kTile) {
   PFN_tmapEncodeTiled enc = get_encode();
   DSX_CHECK(enc, DSX_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(ch), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ch) * 2, static_cast<cuuint64_t>(Tp) * ch * 2};
-  cuuint32_t box[3] = {64, kTile, 1};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_frames), 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1261,9 +1337,11 @@ int tc_prepare_maps(dsx_handle* h, const Geom& g) {
       h->tm_group == h->tc_group)
     return DSX_OK;
   DSX_TRY(make_map_2d(&h->tm_w, h->m.wpack, static_cast<uint64_t>(h->m.L) * kRowsPerLayer, 128));
-  for (int buf = 0; buf < 2; ++buf)
+  for (int buf = 0; buf < 2; ++buf) {
     for (int pl = 0; pl < 2; ++pl)
       DSX_TRY(make_map_act(&h->tm_y[buf][pl], h->ws.Y + (static_cast<size_t>(buf) * 2 + pl) * plane, kC, g.T, g.Tp, g.B));
+    DSX_TRY(make_map_act(&h->tm_yh[buf], h->ws.Y + static_cast<size_t>(buf) * 2 * plane, kC, g.T, g.Tp, g.B, 8));
+  }
   for (int pl = 0; pl < 2; ++pl) {
     DSX_TRY(make_map_act(&h->tm_cond[pl], h->ws.CONDH + static_cast<size_t>(pl) * plane, kC, g.T, g.Tp, g.B));
     DSX_TRY(make_map_act(&h->tm_s16[pl], h->ws.S16 + static_cast<size_t>(pl) * plane, kC, g.T, g.Tp, g.B));
@@ -1349,6 +1427,8 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
     for (int pl = 0; pl < 2; ++pl) prm.tm_y[bf][pl] = h->tm_y[bf][pl];
   prm.tm_cond[0] = h->tm_cond[0];
   prm.tm_cond[1] = h->tm_cond[1];
+  prm.tm_yh[0] = h->tm_yh[0];
+  prm.tm_yh[1] = h->tm_yh[1];
   prm.X = h->ws.X;
   prm.SKIP = h->ws.SKIP;
   prm.Y = h->ws.Y;
