@@ -35,7 +35,7 @@ int dev_alloc(dsx_handle* h, void** p, size_t bytes, bool model_owned) {
 }
 
 static void free_ws(Workspace& w) {
-  void* ptrs[] = {w.X, w.SKIP, w.CONDF, w.G1, w.Zf, w.Y, w.CONDH, w.S16, w.DTAB, w.EMB, w.TVALS, w.EPS, w.XTMP, w.XSTATE};
+  void* ptrs[] = {w.X, w.SKIP, w.CONDF, w.G1, w.Zf, w.Y, w.CONDH, w.CP, w.S16, w.DTAB, w.EMB, w.TVALS, w.EPS, w.XTMP, w.XSTATE};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   w = Workspace();
@@ -65,6 +65,7 @@ int ensure_workspace(dsx_handle* h, const Geom& g, int rows) {
     DSX_TRY(A(reinterpret_cast<void**>(&w.Y), nf * m.C * 2 * 4));
     DSX_TRY(A(reinterpret_cast<void**>(&w.CONDH), nf * m.H * 2 * 2));
     DSX_TRY(A(reinterpret_cast<void**>(&w.S16), nf * m.C * 2 * 2));
+    DSX_TRY(A(reinterpret_cast<void**>(&w.CP), static_cast<size_t>(m.L) * g.tiles * 2 * 256 * kTile * 4));
   } else {
     DSX_TRY(A(reinterpret_cast<void**>(&w.CONDF), nf * m.H * 4));
   }
@@ -144,6 +145,7 @@ static int prepare(dsx_handle* h, const float* cond, dsx_strides cs, int B, int 
   DSX_TRY(ensure_workspace(h, g, rows));
   if (h->precision != DSX_PREC_FP32_SIMT) DSX_TRY(tc_prepare_maps(h, g));
   DSX_TRY(launch_pack_cond(h, cond, cs, g, s));
+  if (h->precision != DSX_PREC_FP32_SIMT) DSX_TRY(launch_tc_condproj(h, g, s));
   return DSX_OK;
 }
 

@@ -86,6 +86,7 @@ struct Workspace {
   float* Zf = nullptr;      // [B][Tp][C]  SIMT gate output
   __half* Y = nullptr;      // [2 buffers][2 planes][B][Tp][C]
   __half* CONDH = nullptr;  // [2 planes][B][Tp][H]
+  float* CP = nullptr;      // [L][tiles][2][64][128][4] conditioner projection + bias of every layer (tcgen05 path)
   __half* S16 = nullptr;    // [2 planes][B][Tp][C] skip_sum / sqrt(L), operand of the head GEMM
   float* DTAB = nullptr;    // [rows][L][C]
   float* EMB = nullptr;     // [rows][C] scratch (mlp output)
@@ -124,7 +125,7 @@ struct dsx_handle {
   int flags_cap = 0;
   int flags_geom_b = 0, flags_geom_t = 0;   // geometry of the last stack launch
   unsigned int flag_count = 0;         // value of every counter before the next stack launch
-  bool attr_layer[3] = {false, false, false}, attr_head[2] = {false, false};
+  bool attr_layer[3] = {false, false, false}, attr_head[2] = {false, false}, attr_cond = false;
   int occ_cache[3][17] = {};
   int cluster_occ = 0;              // max co-resident utterance clusters reported by the driver (last launch)
   int stack_mode = 1;               // 1: all residual layers of an evaluation in one cluster-per-utterance launch
@@ -160,6 +161,7 @@ int launch_epilogue(dsx_handle* h, const float* x, const int64_t* mel2ph, const 
 // ---- dsx_tc.cu ---------------------------------------------------------------------------
 int tc_pack_model(dsx_handle* h, cudaStream_t s);
 int tc_prepare_maps(dsx_handle* h, const Geom& g);
+int launch_tc_condproj(dsx_handle* h, const Geom& g, cudaStream_t s);
 int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int row_per_b, cudaStream_t s);
 // Head / tail of DiffNet on tensor cores.  flags: 1 = head (skip -> eps), 2 = write eps, 4 = DDPM update of x,
 // 8 = input projection of x (after the update if any) for the evaluation that uses table row (next_row0, row_per_b).

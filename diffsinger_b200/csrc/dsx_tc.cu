@@ -1,8 +1,10 @@
 // tcgen05 / TMEM / TMA path of the dsx sampler (sm_100a): one fused kernel per residual layer
 // (usr/diff/net.py:66-78):
 //
-//   GEMM1  D1[128 frames x 512] = [y(t-d) | y(t) | y(t+d) | cond(t)] (K = 1024) . W1^T      y = x + d_l
-//   epi1   z = sigmoid(D1[:, gate] + b) * tanh(D1[:, filter] + b)  -> fp16 (hi, lo) in shared memory
+//   CP     conditioner_projection(cond) + biases, all layers: step-independent, so computed ONCE per call by
+//          k_tc_condproj (hi/lo split on both operands) and kept in HBM as fp32 in the accumulator's layout
+//   GEMM1  D1[128 frames x 512] = [y(t-d) | y(t) | y(t+d)] (K = 768) . W1^T                  y = x + d_l
+//   epi1   z = sigmoid(D1[:, gate] + CP) * tanh(D1[:, filter] + CP)  -> fp16 (hi, lo) in shared memory
 //   GEMM2  D2[128 x 512] = z (K = 256) . W2^T
 //   epi2   x <- (x + D2[:, :256] + b) / sqrt2 ;  y_next = fp16 split of (x + d_{l+1}) ;  skip += D2[:, 256:] + b
 //
@@ -49,11 +51,10 @@ constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowBytes;
 
 template <int P>
 struct TcCfg {
-  // P = number of MMA passes of the parity scheme: 1 = fp16 operands; 2 = weights hi+lo, activations fp16 except the
-  // conditioner (hi+lo); 3 = hi+lo on both operands everywhere.
+  // P = number of MMA passes of the parity scheme: 1 = fp16 operands; 2 = weights hi+lo, running activations fp16;
+  // 3 = hi+lo on both operands.  (The conditioner projection is hoisted out of the loop and always exact.)
   static constexpr bool WLO = (P >= 2);     // W_lo pass
   static constexpr bool ALO_T = (P == 3);   // A_lo pass on the conv taps (y) and on z
-  static constexpr bool ALO_C = (P >= 2);   // A_lo pass on the conditioner k-blocks
   static constexpr int Z_PLANES = ALO_T ? 2 : 1;
   // GEMM1 streams through a ring of UNITS 16 KB units.  z (the A operand of GEMM2) is [planes][4 k-blocks]
   // of 16 KB: k-blocks 0,1 (written while GEMM1 still runs) have their own buffer; k-blocks 2,3 are written
@@ -77,13 +78,12 @@ struct TcCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   // ring units consumed per k-block: GEMM1 {A_hi, W_hi [, W_lo, A_lo]}, GEMM2 {W_hi [, W_lo]}
   static constexpr int UT = 2 + (WLO ? 1 : 0) + (ALO_T ? 1 : 0);   // conv-tap k-block
-  static constexpr int UC = 2 + (WLO ? 1 : 0) + (ALO_C ? 1 : 0);   // conditioner k-block
   static constexpr int U2 = 1 + (WLO ? 1 : 0);
   static constexpr int UG = 1 + 3 * (1 + (WLO ? 1 : 0));          // SHIFT: one 64-channel block = y unit + 3 taps x {W_hi [, W_lo]}
-  // Ring slot of unit `ul` of a layer.  The first four k-blocks (the conditioner k-blocks, which do not depend on the
-  // previous layer) cycle through the non-staging slots only, so they can be loaded and multiplied while the previous
-  // layer's skip epilogue still owns the staging slots; after that the whole ring is used.
-  static constexpr int S0 = 4 * UC;
+  // Ring slot of unit `ul` of a layer.  The first S0 units cycle through the non-staging slots only, so they can be
+  // loaded and multiplied while the previous layer's skip epilogue still owns the staging slots; after that the whole
+  // ring is used.
+  static constexpr int S0 = SHIFT ? 2 * UG : 4 * UT;
   __host__ __device__ static constexpr int slot(int ul) { return ul < S0 ? ul % (UNITS - STG_UNITS) : (ul - S0) % UNITS; }
 };
 
@@ -96,7 +96,7 @@ struct TcLayerParams {
   float* SKIP;               // [B][Tp][256]
   __half* Y;                 // [2 buffers][2 planes][plane_elems]: layer l reads buffer l&1, writes buffer (l+1)&1
   size_t plane_elems;
-  const float* b1p;          // [L][2][256] (packed order)
+  const float* CP;           // [L][tiles][2 chunks][64 column groups][128 rows][4]: cond projection + bias (fp32)
   const float* b2;           // [L][512]
   const float* dtab;         // FiLM table row of this evaluation: [L][256], utterance b at + b * d_row_stride
   int d_row_stride;
@@ -120,10 +120,10 @@ __device__ __forceinline__ float tanh_acc(float x) {
 }
 __device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
-// Order in which GEMM1 consumes its 16 k-blocks (k-block = tap*4 + channel block, 12..15 = conditioner): conditioner
-// first (no dependency on the previous layer), then the centre tap (this tile's own y), the halo taps last (they
-// need the neighbour tiles' y) -- so a layer starts its MMAs while the neighbours are still publishing.
-__device__ __forceinline__ int kb_order(int ko) { return ko < 4 ? 12 + ko : (ko < 8 ? ko : (ko < 12 ? ko - 8 : ko - 4)); }
+// Order in which GEMM1 (one tile per tap, P = 3) consumes its 12 k-blocks (k-block = tap*4 + channel block): the
+// centre tap (this tile's own y) first, the halo taps (they need the neighbour tiles' y) last.
+__device__ __forceinline__ int kb_order(int ko) { return ko < 4 ? 4 + ko : (ko < 8 ? ko - 4 : ko); }
+constexpr size_t kCpChunk = 256 * kTile;   // floats of CP per (layer, tile, chunk)
 
 // publish / wait on a tile's counter in global memory (gpu scope)
 __device__ __forceinline__ void flag_publish(unsigned int* f) {
@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   const bool tile_valid = tile < p.tile_end;
   const int b = tile / p.tiles_per_utt, tr = tile % p.tiles_per_utt;
   const int bq = tile_valid ? b : p.B;            // b == B -> every TMA row is out of bounds (zeros)
+  const int cp_tile = tile_valid ? tile : 0;      // padding CTAs read (and discard) tile 0's slice of CP
   const int t0 = tile_valid ? tr * kTile : 0;
   const bool multi = (p.l1 - p.l0 > 1);
   const bool nb_lo = multi && tile_valid && tr > 0, nb_hi = multi && tile_valid && tr + 1 < p.tiles_per_utt;
@@ -207,8 +208,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
     tma_prefetch_desc(&p.tm_w);
     tma_prefetch_desc(&p.tm_y[0][0]);
     tma_prefetch_desc(&p.tm_y[1][0]);
-    tma_prefetch_desc(&p.tm_cond[0]);
-    if (Cfg::ALO_C) tma_prefetch_desc(&p.tm_cond[1]);
     if (Cfg::ALO_T) {
       tma_prefetch_desc(&p.tm_y[0][1]);
       tma_prefetch_desc(&p.tm_y[1][1]);
@@ -256,6 +255,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       const CUtensorMap* ymap = p.tm_y[l & 1];
       bool y_ok = (li == 0) || !multi || !tile_valid, e_ok = (li == 0);
       if (li > 0) ok = mbar_wait(g2done, prev, wd, 105);            // ring-2 / z units of the previous layer are free
+      {                                                             // this layer's slice of CP: HBM -> L2, ahead of epi1
+        const char* cpl = reinterpret_cast<const char*>(p.CP + (static_cast<size_t>(l) * p.tiles + cp_tile) * 2 * kCpChunk);
+        for (int i = 0; i < 16; ++i) prefetch_l2_bulk(cpl + i * 16384, 16384);
+      }
       int ul = 0;                                                   // unit index within the layer
       auto acquire = [&](int code, int bytes = kUnitBytes) -> uint8_t* {
         const int s = Cfg::slot(ul);
@@ -274,13 +277,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       bool yn_ok = y_ok;                                            // neighbours' y (halo taps)
       auto load_a = [&](int plane, int kb) {
         const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
-        if (kb < 12 && !y_ok) {                                     // centre tap: y_l of this tile
+        if (!y_ok) {                                                // centre tap: y_l of this tile
           ok = flag_wait(p.flags + tile, target, wd, 107);
           fence_proxy_async_all();
           y_ok = true;
           if (!ok) return;
         }
-        if (kb < 12 && (kb >> 2) != 1 && !yn_ok) {                  // halo taps: y_l of the neighbour tiles
+        if ((kb >> 2) != 1 && !yn_ok) {                             // halo taps: y_l of the neighbour tiles
           if (nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
           if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
           fence_proxy_async_all();
@@ -290,10 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         const int s = Cfg::slot(ul);
         uint8_t* dst = acquire(101);
         if (!dst) return;
-        if (kb < 12)
-          tma_load_3d<G>(&ymap[plane], &full[s], dst, (kb & 3) * 64, t0 + ((kb >> 2) - 1) * dil, bq, lead);
-        else
-          tma_load_3d<G>(&p.tm_cond[plane], &full[s], dst, (kb - 12) * 64, t0, bq, lead);
+        tma_load_3d<G>(&ymap[plane], &full[s], dst, (kb & 3) * 64, t0 + ((kb >> 2) - 1) * dil, bq, lead);
         ++ul;
       };
       auto load_w = [&](int tileidx) {
@@ -305,12 +305,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       };
       if constexpr (!Cfg::SHIFT) {
         for (int h = 0; h < 2 && ok; ++h)
-          for (int ko = 0; ko < 16 && ok; ++ko) {
+          for (int ko = 0; ko < 12 && ok; ++ko) {
             const int kb = kb_order(ko);
             load_a(0, kb);
             if (ok) load_w((0 * 2 + h) * 16 + kb);
             if (Cfg::WLO && ok) load_w((1 * 2 + h) * 16 + kb);
-            if ((kb >= 12 ? Cfg::ALO_C : Cfg::ALO_T) && ok) load_a(1, kb);
+            if (Cfg::ALO_T && ok) load_a(1, kb);
           }
       } else {
         // one activation unit per 64-channel block: [8 halo | 128 centre | 8 halo] rows, three boxes, one barrier
@@ -333,12 +333,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
           ++ul;
         };
         for (int h = 0; h < 2 && ok; ++h) {
-          for (int cb = 0; cb < 4 && ok; ++cb) {           // conditioner k-blocks first (no dependency on layer l-1)
-            load_a(0, 12 + cb);
-            if (ok) load_w((0 * 2 + h) * 16 + 12 + cb);
-            if (Cfg::WLO && ok) load_w((1 * 2 + h) * 16 + 12 + cb);
-            if (Cfg::ALO_C && ok) load_a(1, 12 + cb);
-          }
           for (int cb = 0; cb < 4 && ok; ++cb) {
             load_y(cb);
             for (int tj = 0; tj < 3 && ok; ++tj) {         // tap order: centre, left, right
@@ -404,9 +398,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         tc_fence_after();
         const uint32_t d = tmem_base + buf * 256;
         uint32_t acc = 0;
-        for (int ko = 0; ko < (Cfg::SHIFT ? 4 : 16) && ok; ++ko) {
-          const bool alo = (ko < 4) ? Cfg::ALO_C : Cfg::ALO_T;    // k-blocks 0..3 of the order are the conditioner
-          const int nu = 2 + (Cfg::WLO ? 1 : 0) + (alo ? 1 : 0);
+        for (int ko = 0; ko < (Cfg::SHIFT ? 0 : 12) && ok; ++ko) {
+          constexpr bool alo = Cfg::ALO_T;
+          constexpr int nu = Cfg::UT;
           const uint64_t a_hi = wait_unit(ul, 202);
           const uint64_t w_hi = wait_unit(ul + 1, 202);
           if (!ok) break;
@@ -520,6 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       if (lane == 0) okv = mbar_wait(bar, parity, wd, code) ? 1 : 0;
       return __shfl_sync(0xffffffffu, okv, 0) != 0;
     };
+    const uint64_t cp_policy = l2_policy_evict_first();
     uint8_t* stg = staging + (warp - 4) * 4096;
     const int lrow = lane >> 4;                               // epi2 reader: half-warp = one row
     const int lc2 = lane & 15;                                // column pair within the 32-column group
@@ -530,46 +525,54 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
     const uint8_t* stg_rd = stg + lrow * 128 + (lc2 & 1) * 8;
 
     for (int l = p.l0; l < p.l1 && ok; ++l) {
-      const float* b1p = p.b1p + static_cast<size_t>(l) * 512;
       const float* b2 = p.b2 + static_cast<size_t>(l) * 512;
       const bool skip_init = (l == 0);
       __half* const s16 = (l == p.L - 1) ? p.s16 : nullptr;
       __half* const yout = p.Y + static_cast<size_t>(((l + 1) & 1) * 2) * p.plane_elems;
       const float* dnext = (l + 1 < p.L) ? p.dtab + static_cast<size_t>(l + 1) * kC : nullptr;
-      // ---- epi1: z = sigmoid(gate) * tanh(filter); this warp produces 64 z channels = one k-block of z ----
+      // ---- epi1: z = sigmoid(gate) * tanh(filter), gate/filter = accumulator + CP (conditioner projection + bias,
+      //      streamed from HBM in the accumulator's own layout: one float4 = 4 columns of this thread's row).
+      //      Four sub-passes of 16 gate/filter column pairs per chunk; sub-passes 2*it, 2*it+1 of all 8 warps complete
+      //      z k-block 2h + it, so GEMM2 can start on k-block 2 while k-block 3 is still being gated.  CP loads run one
+      //      sub-pass ahead (the first one is issued before the accumulator wait). ----
+      const float* cpl = p.CP + (static_cast<size_t>(l) * p.tiles + cp_tile) * 2 * kCpChunk + r * 4;
       for (int h = 0; h < 2 && ok; ++h) {
+        const float* cph = cpl + h * kCpChunk;
+        float4 cg[2][4], cf[2][4];
+        auto cp_load = [&](int sp, float4* g4, float4* f4) {
+          const int gcol = (sp >> 1) * 64 + half * 32 + (sp & 1) * 16;
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            g4[v4] = ld_stream_f4(cph + ((gcol >> 2) + v4) * (kTile * 4), cp_policy);
+            f4[v4] = ld_stream_f4(cph + (((128 + gcol) >> 2) + v4) * (kTile * 4), cp_policy);
+          }
+        };
+        cp_load(0, cg[0], cf[0]);
         if (tracer) DSX_TRACE(2, h * 4 + 0);
         ok = wait_warp(&tfull[h], tf[h] & 1, 301);
         if (!ok) break;
         if (tracer) DSX_TRACE(2, h * 4 + 1);
         tf[h]++;
         tc_fence_after();
-        // two passes of 32 gate/filter column pairs: pass `it` of all 8 warps completes z k-block 2h + it, so
-        // GEMM2 can start on k-block 2 while k-block 3 is still being gated
-#pragma unroll 1
-        for (int it = 0; it < 2; ++it) {
-          const int gcol = it * 64 + half * 32;               // first gate column of this warp in this pass
-          const float* bg = b1p + h * 256 + gcol;             // gate biases; filter biases at +128
+#pragma unroll
+        for (int sp = 0; sp < 4; ++sp) {
+          const int it = sp >> 1, sub = sp & 1;
+          const int gcol = it * 64 + half * 32 + sub * 16;    // first gate column of this warp in this sub-pass
+          if (sp < 3) cp_load(sp + 1, cg[(sp + 1) & 1], cf[(sp + 1) & 1]);
           uint8_t* zrow = zaddr(0, 2 * h + it) + r * 128;
           uint8_t* zrow_lo = zaddr(1, 2 * h + it) + r * 128;
-          uint32_t g[32], f[32];
-          tmem_ld_32x32(tmem_base + tlane + h * 256 + gcol, g);
-          tmem_ld_32x32(tmem_base + tlane + h * 256 + 128 + gcol, f);
-          float4 bgq[8], bfq[8];
-#pragma unroll
-          for (int v4 = 0; v4 < 8; ++v4) {
-            bgq[v4] = __ldg(reinterpret_cast<const float4*>(bg) + v4);
-            bfq[v4] = __ldg(reinterpret_cast<const float4*>(bg + 128) + v4);
-          }
+          uint32_t g[16], f[16];
+          tmem_ld_32x16(tmem_base + tlane + h * 256 + gcol, g);
+          tmem_ld_32x16(tmem_base + tlane + h * 256 + 128 + gcol, f);
           tmem_ld_wait();
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
+          for (int c8 = 0; c8 < 2; ++c8) {
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int e = 0; e < 4; e += 2) {
               const int i = c8 * 8 + e * 2;
-              const float4 bgv = bgq[i >> 2];
-              const float4 bfv = bfq[i >> 2];
+              const float4 bgv = cg[sp & 1][i >> 2];
+              const float4 bfv = cf[sp & 1][i >> 2];
               float z4[4];
               const float vg[4] = {__uint_as_float(g[i]) + bgv.x, __uint_as_float(g[i + 1]) + bgv.y,
                                    __uint_as_float(g[i + 2]) + bgv.z, __uint_as_float(g[i + 3]) + bgv.w};
@@ -587,11 +590,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
                 lo[e + 1] = h2_bits(__floats2half2_rn(z4[2] - f23.x, z4[3] - f23.y));
               }
             }
-            const int off = ((half * 4 + c8) ^ (r & 7)) << 4;   // this warp's 32 channels = chunks 4*half .. +3
+            const int off = ((half * 4 + sub * 2 + c8) ^ (r & 7)) << 4;   // this warp's 32 channels = chunks 4*half .. +3
             *reinterpret_cast<uint4*>(zrow + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             if (Cfg::ALO_T) *reinterpret_cast<uint4*>(zrow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-          if (h == 1) {
+          if (h == 1 && sub == 1) {
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
@@ -736,6 +739,172 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   if (threadIdx.x == 64) {
     DSX_TRACE(0, 251);                                           // after TMEM free (clock64)
     if (p.trace && blockIdx.x < 2) p.trace[(blockIdx.x * 3 + 1) * 256 + 251] = static_cast<long long>(globaltimer_ns());
+  }
+}
+
+// ==========================================================================================
+// Conditioner projection of every residual layer (usr/diff/net.py:56,70: conditioner_projection(cond), plus the
+// summed dilated_conv / conditioner_projection biases), hoisted out of the sampling loop: it does not depend on the
+// diffusion step.  CP[l][tile][chunk h][column group][row][4] (fp32) is laid out exactly as the layer kernel's epi1
+// reads its accumulator: thread = row, one float4 = 4 consecutive accumulator columns.
+//   D[128 x 256] = cond_tile (K = 256, hi+lo) . Wc(l, h)^T (hi+lo), 3 passes, fp32 accumulate; + b1p
+// cta_group::1, one CTA per (tile, slice of the 2L (layer, chunk) jobs): the conditioner tile stays resident in shared
+// memory (8 x 16 KB), the weight tiles (256 rows x 64, 32 KB) stream through a 3-deep ring, two TMEM accumulators.
+// ==========================================================================================
+struct TcCondParams {
+  CUtensorMap tm_w;        // packed weights, box 64 x 128 rows
+  CUtensorMap tm_cond[2];  // conditioner planes hi / lo
+  float* CP;
+  const float* b1p;        // [L][2][256] biases in accumulator column order
+  int T, Tp, tiles_per_utt, tiles, B, L;
+  int* status;
+  unsigned long long budget_ns;
+};
+constexpr int kCondStages = 3;
+constexpr int kCondSmem = 1024 + 8 * kUnitBytes + kCondStages * 2 * kUnitBytes + 256;
+
+__global__ void __launch_bounds__(kThreads, 1) k_tc_condproj(const __grid_constant__ TcCondParams p) {
+  constexpr int NS = kCondStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* abuf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = abuf + 8 * kUnitBytes;                      // NS stages of one 256-row weight tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NS * 2 * kUnitBytes);
+  uint64_t* full = bars;            // [NS]
+  uint64_t* empty = full + NS;      // [NS]
+  uint64_t* tfull = empty + NS;     // [2]
+  uint64_t* tempty = tfull + 2;     // [2]
+  uint64_t* afull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int b = tile / p.tiles_per_utt;
+  const int t0 = (tile % p.tiles_per_utt) * kTile;
+  const int njobs = 2 * p.L;
+  const int j0 = static_cast<int>(static_cast<long long>(njobs) * blockIdx.y / gridDim.y);
+  const int j1 = static_cast<int>(static_cast<long long>(njobs) * (blockIdx.y + 1) / gridDim.y);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_w);
+    tma_prefetch_desc(&p.tm_cond[0]);
+    tma_prefetch_desc(&p.tm_cond[1]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], kEpiWarps);
+    }
+    mbar_init(afull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  Watchdog wd{p.status, globaltimer_ns() + p.budget_ns};
+
+  if (warp == 0 && lane == 0) {
+    // ---- TMA producer ----
+    mbar_arrive_expect_tx(afull, 8 * kUnitBytes);
+    for (int pl = 0; pl < 2; ++pl)
+      for (int kb = 0; kb < 4; ++kb) tma_load_3d<1>(&p.tm_cond[pl], afull, abuf + (pl * 4 + kb) * kUnitBytes, kb * 64, t0, b);
+    uint32_t u = 0;
+    bool ok = true;
+    for (int j = j0; j < j1 && ok; ++j) {
+      const int l = j >> 1, h = j & 1;
+      for (int kb = 0; kb < 4 && ok; ++kb)
+        for (int pl = 0; pl < 2 && ok; ++pl, ++u) {
+          const int s = u % NS;
+          ok = mbar_wait(&empty[s], ((u / NS) & 1) ^ 1, wd, 121);
+          if (!ok) break;
+          mbar_arrive_expect_tx(&full[s], 2 * kUnitBytes);
+          const int row = l * kRowsPerLayer + ((pl * 2 + h) * 16 + 12 + kb) * 256;
+          tma_load_2d<1>(&p.tm_w, &full[s], ring + s * 2 * kUnitBytes, 0, row);
+          tma_load_2d<1>(&p.tm_w, &full[s], ring + s * 2 * kUnitBytes + kUnitBytes, 0, row + 128);
+        }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer ----
+    constexpr uint32_t idesc = umma_idesc_f16(128, 256);
+    auto mma4 = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t& acc) {
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        umma_f16<1>(d, ad + 2 * k4, bd + 2 * k4, idesc, acc);
+        acc = 1;
+      }
+    };
+    bool ok = mbar_wait(afull, 0, wd, 221);
+    tc_fence_after();
+    uint32_t u = 0;
+    for (int j = j0; j < j1 && ok; ++j) {
+      const int jj = j - j0, buf = jj & 1;
+      ok = mbar_wait(&tempty[buf], ((jj >> 1) & 1) ^ 1, wd, 222);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t d = tmem_base + buf * 256;
+      uint32_t acc = 0;
+      for (int kb = 0; kb < 4 && ok; ++kb) {
+        const uint64_t a_hi = umma_desc_sw128(smem_u32(abuf + kb * kUnitBytes));
+        const uint64_t a_lo = umma_desc_sw128(smem_u32(abuf + (4 + kb) * kUnitBytes));
+        for (int pl = 0; pl < 2 && ok; ++pl, ++u) {
+          const int s = u % NS;
+          ok = mbar_wait(&full[s], (u / NS) & 1, wd, 223);
+          if (!ok) break;
+          tc_fence_after();
+          const uint64_t w = umma_desc_sw128(smem_u32(ring + s * 2 * kUnitBytes));
+          mma4(d, a_hi, w, acc);                      // A_hi.W_hi, A_hi.W_lo
+          if (pl == 0) mma4(d, a_lo, w, acc);         // A_lo.W_hi
+          umma_commit<1>(&empty[s]);
+        }
+      }
+      if (ok) umma_commit<1>(&tfull[buf]);
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue: accumulator + bias -> CP ----
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t tlane = static_cast<uint32_t>(quad * 32) << 16;
+    bool ok = true;
+    for (int j = j0; j < j1 && ok; ++j) {
+      const int l = j >> 1, h = j & 1, jj = j - j0, buf = jj & 1;
+      int okv = 1;
+      if (lane == 0) okv = mbar_wait(&tfull[buf], (jj >> 1) & 1, wd, 321) ? 1 : 0;
+      ok = __shfl_sync(0xffffffffu, okv, 0) != 0;
+      if (!ok) break;
+      tc_fence_after();
+      float* dst = p.CP + ((static_cast<size_t>(l) * p.tiles + tile) * 2 + h) * kCpChunk + r * 4;
+      const float* bias = p.b1p + (static_cast<size_t>(l) * 2 + h) * 256;
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + tlane + buf * 256 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + c4);
+          float4 o;
+          o.x = __uint_as_float(v[c4 * 4]) + bb.x;
+          o.y = __uint_as_float(v[c4 * 4 + 1]) + bb.y;
+          o.z = __uint_as_float(v[c4 * 4 + 2]) + bb.z;
+          o.w = __uint_as_float(v[c4 * 4 + 3]) + bb.w;
+          *reinterpret_cast<float4*>(dst + ((c0 >> 2) + c4) * (kTile * 4)) = o;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
   }
 }
 
@@ -1433,7 +1602,7 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
   prm.SKIP = h->ws.SKIP;
   prm.Y = h->ws.Y;
   prm.plane_elems = g.frames_padded() * kC;
-  prm.b1p = m.b1p;
+  prm.CP = h->ws.CP;
   prm.b2 = m.b2f;
   prm.dtab = h->ws.DTAB + static_cast<size_t>(row0) * m.L * kC;
   prm.d_row_stride = row_per_b * m.L * kC;
@@ -1484,6 +1653,32 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
     prm.l0 = l; prm.l1 = l + 1;
     DSX_TRY(launch(grid));
   }
+  return DSX_OK;
+}
+
+// CP for the conditioner currently packed in ws.CONDH (called once per API call, after launch_pack_cond).
+int launch_tc_condproj(dsx_handle* h, const Geom& g, cudaStream_t s) {
+  if (!h->attr_cond) {
+    DSX_CUDA(cudaFuncSetAttribute(k_tc_condproj, cudaFuncAttributeMaxDynamicSharedMemorySize, kCondSmem));
+    h->attr_cond = true;
+  }
+  TcCondParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.tm_w = h->tm_w;
+  prm.tm_cond[0] = h->tm_cond[0];
+  prm.tm_cond[1] = h->tm_cond[1];
+  prm.CP = h->ws.CP;
+  prm.b1p = h->m.b1p;
+  prm.T = g.T; prm.Tp = g.Tp; prm.tiles_per_utt = g.tiles_per_utt; prm.tiles = g.tiles; prm.B = g.B;
+  prm.L = h->m.L;
+  prm.status = h->status_dev;
+  prm.budget_ns = 2000000000ull;
+  // few tiles: split the 2L (layer, chunk) jobs of a tile over several CTAs so the whole machine works
+  const int split = std::max(1, std::min(2 * h->m.L, h->sm_count / std::max(g.tiles, 1)));
+  dim3 grid(static_cast<unsigned>(g.tiles), static_cast<unsigned>(split));
+  k_tc_condproj<<<grid, kThreads, kCondSmem, s>>>(prm);
+  h->launches++;
+  DSX_CUDA(cudaGetLastError());
   return DSX_OK;
 }
 
