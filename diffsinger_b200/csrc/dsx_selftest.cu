@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -323,6 +324,130 @@ static int run_shift_experiment(std::string& report) {
   return DSX_OK;
 }
 
+
+// ---- experiment 3: how fast can ONE SM pull L2-resident operand tiles into shared memory? --------------------
+// `nthr` threads (one per warp) each stream loads through their own ring of `nslot` slots (wait for the slot's previous
+// load, re-issue).  kind 0: 2D tensor map (64 x rows box, SWIZZLE_128B) -- what the layer kernel does; kind 1: 1D bulk
+// copy (cp.async.bulk, no tensor map); kind 2: 3D tensor map box 64 x 128 x 2 (two 16 KB tiles per instruction).
+struct IngestParams {
+  CUtensorMap tm[4];       // box rows 16, 32, 64, 128
+  CUtensorMap tm3;         // 3D [64][128][tiles], box 64 x 128 x 2
+  const uint8_t* src;
+  long long* cycles;
+  int kind, rows, nslot, nthr, nloads, src_tiles;
+};
+__global__ void __launch_bounds__(128, 1) k_ingest(const __grid_constant__ IngestParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NSLOT = 12;                                   // x 16 KB, shared by the issuing threads
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + NSLOT * 16384);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSLOT; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0 && w < p.nthr) {
+    const uint32_t bytes = (p.kind == 2) ? 32768u : static_cast<uint32_t>(p.rows) * 128u;
+    const int per = p.nslot / p.nthr;                         // slots of this thread: [w*per, (w+1)*per)
+    const int stride = (p.kind == 2) ? 2 : 1;                 // 16 KB cells per slot
+    const CUtensorMap* tm = &p.tm[p.rows == 16 ? 0 : (p.rows == 32 ? 1 : (p.rows == 64 ? 2 : 3))];
+    const long long t0 = clock64();
+    const int n = p.nloads / p.nthr;
+    for (int i = 0; i < n; ++i) {
+      const int sl = i % per, use = i / per, s = (w * per + sl) * stride;
+      if (use > 0)
+        for (uint32_t sp = 0; sp < (1u << 22) && !mbar_try_wait(&bars[s], (use - 1) & 1); ++sp) {}
+      mbar_arrive_expect_tx(&bars[s], bytes);
+      const int tile = (i * 7 + blockIdx.x * 3 + w * 11) % (p.src_tiles - 1);
+      uint8_t* dst = base + s * 16384;
+      if (p.kind == 0) tma_load_2d<1>(tm, &bars[s], dst, 0, tile * 128);
+      else if (p.kind == 2) tma_load_3d<1>(&p.tm3, &bars[s], dst, 0, 0, tile);
+      else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst)), "l"(p.src + static_cast<size_t>(tile) * 16384), "r"(bytes), "r"(smem_u32(&bars[s]))
+                     : "memory");
+    }
+    for (int i = max(n - per, 0); i < n; ++i) {
+      const int sl = i % per, use = i / per, s = (w * per + sl) * stride;
+      for (uint32_t sp = 0; sp < (1u << 22) && !mbar_try_wait(&bars[s], use & 1); ++sp) {}
+    }
+    p.cycles[blockIdx.x * 4 + w] = clock64() - t0;
+  }
+}
+
+static int run_ingest_experiment(std::string& report) {
+  const int src_tiles = 256;                                  // 4 MB source: L2 resident
+  uint8_t* dsrc = nullptr;
+  long long* dcyc = nullptr;
+  DSX_CUDA(cudaMalloc(&dsrc, static_cast<size_t>(src_tiles) * 16384));
+  DSX_CUDA(cudaMemset(dsrc, 0, static_cast<size_t>(src_tiles) * 16384));
+  DSX_CUDA(cudaMalloc(&dcyc, 1024 * sizeof(long long)));
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  DSX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
+  DSX_CHECK(fp && q == cudaDriverEntryPointSuccess, DSX_E_CUDA, "no cuTensorMapEncodeTiled");
+  auto enc = reinterpret_cast<CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill)>(fp);
+  IngestParams prm;
+  memset(&prm, 0, sizeof(prm));
+  cuuint64_t d2[2] = {64, static_cast<cuuint64_t>(src_tiles) * 128};
+  cuuint64_t s2[1] = {128};
+  cuuint32_t e3[3] = {1, 1, 1};
+  const int rows_opt[4] = {16, 32, 64, 128};
+  for (int i = 0; i < 4; ++i) {
+    cuuint32_t bx[2] = {64, static_cast<cuuint32_t>(rows_opt[i])};
+    CUresult r = enc(&prm.tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dsrc, d2, s2, bx, e3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSX_CHECK(r == CUDA_SUCCESS, DSX_E_CUDA, "ingest: map %d failed %d", i, static_cast<int>(r));
+  }
+  {
+    cuuint64_t d3[3] = {64, 128, static_cast<cuuint64_t>(src_tiles)};
+    cuuint64_t s3[2] = {128, 16384};
+    cuuint32_t b3[3] = {64, 128, 2};
+    CUresult r = enc(&prm.tm3, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, dsrc, d3, s3, b3, e3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSX_CHECK(r == CUDA_SUCCESS, DSX_E_CUDA, "ingest: 3D map failed %d", static_cast<int>(r));
+  }
+  prm.src = dsrc;
+  prm.cycles = dcyc;
+  prm.src_tiles = src_tiles;
+  prm.nloads = 768;
+  const int smem = 1024 + 12 * 16384 + 128;
+  DSX_CUDA(cudaFuncSetAttribute(k_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  struct Case { int kind, rows, nslot, nthr, grid; };
+  const Case cases[] = {
+      {0, 128, 12, 1, 1}, {0, 128, 12, 1, 128}, {0, 128, 6, 1, 1}, {0, 128, 3, 1, 1}, {0, 128, 1, 1, 1},
+      {0, 64, 12, 1, 1},  {0, 64, 6, 1, 1},     {0, 64, 3, 1, 1},  {0, 64, 1, 1, 1},
+      {0, 32, 12, 1, 1},  {0, 32, 1, 1, 1},     {0, 16, 12, 1, 1}, {0, 16, 1, 1, 1},
+      {0, 128, 12, 2, 1}, {0, 128, 12, 4, 1},   {0, 128, 12, 4, 128}, {0, 32, 12, 4, 1},
+      {1, 128, 12, 1, 1}, {1, 128, 12, 4, 1},   {1, 128, 1, 1, 1},
+      {2, 128, 6, 1, 1},  {2, 128, 6, 2, 1},    {2, 128, 6, 2, 128}, {2, 128, 1, 1, 1},
+  };
+  for (const Case& c : cases) {
+    prm.kind = c.kind; prm.rows = c.rows; prm.nslot = c.nslot; prm.nthr = c.nthr;
+    long long cyc[1024];
+    for (int rep = 0; rep < 2; ++rep) {                       // first repetition warms L2
+      k_ingest<<<c.grid, 128, smem>>>(prm);
+      DSX_CUDA(cudaDeviceSynchronize());
+    }
+    DSX_CUDA(cudaMemcpy(cyc, dcyc, c.grid * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int i = 0; i < c.grid; ++i)
+      for (int w = 0; w < c.nthr; ++w) mx = std::max(mx, cyc[i * 4 + w]);
+    const double per = (c.kind == 2) ? 32768.0 : c.rows * 128.0;
+    const int n = prm.nloads / c.nthr * c.nthr;
+    char line[240];
+    snprintf(line, sizeof(line), "ingest kind %d (%s) %5.0f B/load, %2d slots, %d issuing threads, grid %3d: %6.0f cycles/load, %.1f B/cycle/SM\n",
+             c.kind, c.kind == 0 ? "tensor2d" : (c.kind == 1 ? "bulk1d" : "tensor3d x2"), per, c.nslot, c.nthr, c.grid,
+             static_cast<double>(mx) / (n / c.nthr) , per * n / static_cast<double>(mx));
+    report += line;
+  }
+  cudaFree(dsrc);
+  cudaFree(dcyc);
+  return DSX_OK;
+}
 }  // namespace dsx
 
 extern "C" int dsx_selftest(int device, int which, char* report, int report_bytes) {
@@ -341,6 +466,10 @@ extern "C" int dsx_selftest(int device, int which, char* report, int report_byte
   }
   if (which == 2) {   // informational experiment, not part of which = -1
     int r = run_shift_experiment(rep);
+    if (r != DSX_OK) rc = r;
+  }
+  if (which == 3) {   // informational experiment: per-SM TMA ingest rate
+    int r = run_ingest_experiment(rep);
     if (r != DSX_OK) rc = r;
   }
   if (report && report_bytes > 0) {

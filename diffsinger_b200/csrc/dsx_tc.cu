@@ -91,7 +91,7 @@ struct TcLayerParams {
   CUtensorMap tm_w;          // packed weights, 2D [rows][64], box 64 x 128 rows
   CUtensorMap tm_y[2][2];    // conv input, [buffer = layer parity][plane hi/lo], 3D [B][T][256]
   CUtensorMap tm_cond[2];    // conditioner, planes hi/lo
-  CUtensorMap tm_yh[2];      // conv input hi plane of buffer 0 / 1 with a box of 8 frames (halo rows of the SHIFT layout)
+  CUtensorMap tm_yh[2];      // conv input hi plane of buffer 0 / 1 with a box of 8 + 128 + 8 frames (SHIFT layout)
   float* X;                  // [B][Tp][256] residual stream (in/out)
   float* SKIP;               // [B][Tp][256]
   __half* Y;                 // [2 buffers][2 planes][plane_elems]: layer l reads buffer l&1, writes buffer (l+1)&1
@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
     tma_prefetch_desc(&p.tm_w);
     tma_prefetch_desc(&p.tm_y[0][0]);
     tma_prefetch_desc(&p.tm_y[1][0]);
+    tma_prefetch_desc(&p.tm_yh[0]);
+    tma_prefetch_desc(&p.tm_yh[1]);
     if (Cfg::ALO_T) {
       tma_prefetch_desc(&p.tm_y[0][1]);
       tma_prefetch_desc(&p.tm_y[1][1]);
@@ -243,8 +245,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   Watchdog wd{p.status, globaltimer_ns() + p.budget_ns};
   if (threadIdx.x == 0) DSX_TRACE(0, 254);
 
-  if (warp == 0 && lane == 0) {
-    // ================================ TMA producer ================================
+  // A thread gets one TMA load accepted per ~430 cycles whatever its size (dsx_selftest(3)): three producer threads
+  // (warps 0, 2, 3) take the units of the ring round-robin, each with the full slot / parity bookkeeping.
+  const int prod_id = (warp == 0) ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
+  if (prod_id >= 0 && lane == 0) {
+    // ================================ TMA producers ================================
+    constexpr int NP = 3;
     uint32_t pbits = 0, pbits2 = 0;                 // per-slot use parity of ring 1 / ring 2
     bool ok = true;
     for (int l = p.l0; l < p.l1 && ok; ++l) {
@@ -255,52 +261,51 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       const CUtensorMap* ymap = p.tm_y[l & 1];
       bool y_ok = (li == 0) || !multi || !tile_valid, e_ok = (li == 0);
       if (li > 0) ok = mbar_wait(g2done, prev, wd, 105);            // ring-2 / z units of the previous layer are free
-      {                                                             // this layer's slice of CP: HBM -> L2, ahead of epi1
-        const char* cpl = reinterpret_cast<const char*>(p.CP + (static_cast<size_t>(l) * p.tiles + cp_tile) * 2 * kCpChunk);
-        for (int i = 0; i < 16; ++i) prefetch_l2_bulk(cpl + i * 16384, 16384);
-      }
+      if (prod_id == 0 && li < 10) DSX_TRACE(0, 200 + li);
       int ul = 0;                                                   // unit index within the layer
+      // Slot of unit `ul` if it is this producer's, waited empty and armed; nullptr otherwise (check `ok`).
       auto acquire = [&](int code, int bytes = kUnitBytes) -> uint8_t* {
         const int s = Cfg::slot(ul);
+        const uint32_t par = ((pbits >> s) & 1) ^ 1;
+        pbits ^= 1u << s;
+        if (ul % NP != prod_id) return nullptr;
         if (!e_ok && s >= NU - Cfg::STG_UNITS) {                    // staging units: previous epilogue must be done
           ok = mbar_wait(edone, prev, wd, 106);
           e_ok = true;
           if (!ok) return nullptr;
         }
-        ok = mbar_wait(&empty[s], ((pbits >> s) & 1) ^ 1, wd, code);
+        ok = mbar_wait(&empty[s], par, wd, code);
         if (!ok) return nullptr;
-        pbits ^= 1u << s;
         DSX_TRACE(0, ul);
         if (prank == 0) mbar_arrive_expect_tx(&full[s], G * bytes);
         return ring + s * Cfg::SLOT;
       };
+      const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
       bool yn_ok = y_ok;                                            // neighbours' y (halo taps)
-      auto load_a = [&](int plane, int kb) {
-        const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
-        if (!y_ok) {                                                // centre tap: y_l of this tile
-          ok = flag_wait(p.flags + tile, target, wd, 107);
-          fence_proxy_async_all();
-          y_ok = true;
-          if (!ok) return;
-        }
-        if ((kb >> 2) != 1 && !yn_ok) {                             // halo taps: y_l of the neighbour tiles
-          if (nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
-          if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
-          fence_proxy_async_all();
-          yn_ok = true;
+      auto load_a = [&](int plane, int kb) {                        // P = 3: one 16 KB tile per tap and channel block
+        if (ul % NP == prod_id) {
+          if (!y_ok) {                                              // centre tap: y_l of this tile
+            ok = flag_wait(p.flags + tile, target, wd, 107);
+            fence_proxy_async_all();
+            y_ok = true;
+          }
+          if (ok && (kb >> 2) != 1 && !yn_ok) {                     // halo taps: y_l of the neighbour tiles
+            if (nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
+            if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
+            fence_proxy_async_all();
+            yn_ok = true;
+          }
           if (!ok) return;
         }
         const int s = Cfg::slot(ul);
         uint8_t* dst = acquire(101);
-        if (!dst) return;
-        tma_load_3d<G>(&ymap[plane], &full[s], dst, (kb & 3) * 64, t0 + ((kb >> 2) - 1) * dil, bq, lead);
+        if (dst) tma_load_3d<G>(&ymap[plane], &full[s], dst, (kb & 3) * 64, t0 + ((kb >> 2) - 1) * dil, bq, lead);
         ++ul;
       };
       auto load_w = [&](int tileidx) {
         const int s = Cfg::slot(ul);
         uint8_t* dst = acquire(102);
-        if (!dst) return;
-        tma_load_2d<G>(&p.tm_w, &full[s], dst, 0, w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
+        if (dst) tma_load_2d<G>(&p.tm_w, &full[s], dst, 0, w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
         ++ul;
       };
       if constexpr (!Cfg::SHIFT) {
@@ -313,23 +318,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
             if (Cfg::ALO_T && ok) load_a(1, kb);
           }
       } else {
-        // one activation unit per 64-channel block: [8 halo | 128 centre | 8 halo] rows, three boxes, one barrier
+        // one activation unit per 64-channel block: [8 halo | 128 centre | 8 halo] rows = one 144-row box
         auto load_y = [&](int cb) {
-          const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
-          if (!y_ok) {
+          if (ul % NP == prod_id && !y_ok) {
             ok = flag_wait(p.flags + tile, target, wd, 107);
             if (ok && nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
             if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
             fence_proxy_async_all();
             y_ok = true;
+            if (prod_id == 0 && li < 10) DSX_TRACE(0, 210 + li);
             if (!ok) return;
           }
           const int s = Cfg::slot(ul);
           uint8_t* dst = acquire(110, Cfg::SLOT);
-          if (!dst) return;
-          tma_load_3d<G>(&p.tm_yh[l & 1], &full[s], dst, cb * 64, t0 - 8, bq, lead);
-          tma_load_3d<G>(&ymap[0], &full[s], dst + 8 * 128, cb * 64, t0, bq, lead);
-          tma_load_3d<G>(&p.tm_yh[l & 1], &full[s], dst + (8 + kTile) * 128, cb * 64, t0 + kTile, bq, lead);
+          if (dst) tma_load_3d<G>(&p.tm_yh[l & 1], &full[s], dst, cb * 64, t0 - 8, bq, lead);
           ++ul;
         };
         for (int h = 0; h < 2 && ok; ++h) {
@@ -348,13 +350,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       int u2 = 0;
       auto load_w2 = [&](int tileidx) {
         const int s = u2 % NU2;
-        ok = mbar_wait(&empty2[s], ((pbits2 >> s) & 1) ^ 1, wd, 104);
-        if (!ok) return;
+        const uint32_t par = ((pbits2 >> s) & 1) ^ 1;
         pbits2 ^= 1u << s;
-        DSX_TRACE(0, 128 + u2);
-        if (prank == 0) mbar_arrive_expect_tx(&full2[s], G * kUnitBytes);
-        tma_load_2d<G>(&p.tm_w, &full2[s], ring + s * Cfg::SLOT, 0,
-                       w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
+        if (u2 % NP == prod_id) {
+          ok = mbar_wait(&empty2[s], par, wd, 104);
+          if (!ok) return;
+          DSX_TRACE(0, 128 + u2);
+          if (prank == 0) mbar_arrive_expect_tx(&full2[s], G * kUnitBytes);
+          tma_load_2d<G>(&p.tm_w, &full2[s], ring + s * Cfg::SLOT, 0,
+                         w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
+        }
         ++u2;
       };
       for (int q = 0; q < 2 && ok; ++q)
@@ -398,6 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         tc_fence_after();
         const uint32_t d = tmem_base + buf * 256;
         uint32_t acc = 0;
+        if (h == 0 && li < 10) DSX_TRACE(1, 210 + li);              // TMEM buffer 0 free: GEMM1 of this layer may start
         for (int ko = 0; ko < (Cfg::SHIFT ? 0 : 12) && ok; ++ko) {
           constexpr bool alo = Cfg::ALO_T;
           constexpr int nu = Cfg::UT;
@@ -428,6 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
             const uint64_t y = wait_unit(ul, 206);              // [8 halo | 128 centre | 8 halo] rows of 64 channels
             if (!ok) break;
             DSX_TRACE(1, 4 + cb + 16 * h);
+            if (h == 0 && cb == 0 && li < 10) DSX_TRACE(1, 230 + li);
             int uu = ul + 1;
             for (int tj = 0; tj < 3 && ok; ++tj) {
               const int tap = tj == 0 ? 1 : (tj == 1 ? 0 : 2);
@@ -495,6 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         if (ok) umma_commit<G>(&tfull[buf], pair_mask);
       }
       if (ok) umma_commit<G>(g2done, pair_mask);
+      if (li < 10) DSX_TRACE(1, 220 + li);
     }
   } else if (warp >= 4) {
     // ================================ epilogue (8 warps) ================================
@@ -717,6 +725,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
           __syncwarp();
           if (lane == 0) flag_publish(p.flags + tile);
         }
+        if (tracer && l - p.l0 < 10) DSX_TRACE(2, 100 + q * 10 + (l - p.l0));
       }
       if (ok && multi && l + 1 < p.l1) {
         __syncwarp();
@@ -1509,7 +1518,7 @@ int tc_prepare_maps(dsx_handle* h, const Geom& g) {
   for (int buf = 0; buf < 2; ++buf) {
     for (int pl = 0; pl < 2; ++pl)
       DSX_TRY(make_map_act(&h->tm_y[buf][pl], h->ws.Y + (static_cast<size_t>(buf) * 2 + pl) * plane, kC, g.T, g.Tp, g.B));
-    DSX_TRY(make_map_act(&h->tm_yh[buf], h->ws.Y + static_cast<size_t>(buf) * 2 * plane, kC, g.T, g.Tp, g.B, 8));
+    DSX_TRY(make_map_act(&h->tm_yh[buf], h->ws.Y + static_cast<size_t>(buf) * 2 * plane, kC, g.T, g.Tp, g.B, kTile + 16));
   }
   for (int pl = 0; pl < 2; ++pl) {
     DSX_TRY(make_map_act(&h->tm_cond[pl], h->ws.CONDH + static_cast<size_t>(pl) * plane, kC, g.T, g.Tp, g.B));

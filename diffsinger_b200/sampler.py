@@ -254,6 +254,6 @@ class DsxSampler:
 
 
 def selftest(device=0, which=-1):
-    buf = ctypes.create_string_buffer(4096)
-    rc = lib.dsx_selftest(device, which, buf, 4096)
+    buf = ctypes.create_string_buffer(16384)
+    rc = lib.dsx_selftest(device, which, buf, 16384)
     return rc, buf.value.decode(errors="replace")

@@ -172,7 +172,7 @@ enum {
 int dsx_set_option(dsx_handle* h, int what, int64_t value);
 enum {
   DSX_OPT_TC_CTA_GROUP = 0, /* 2 (the layer kernel pairs CTAs; kept for forward compatibility) */
-  DSX_OPT_RESERVED_1 = 1,   /* (unused: with the persistent layer stack a step is 2 launches, graphs bring nothing) */
+  DSX_OPT_RESERVED_1 = 1,   /* (unused) */
   DSX_OPT_PROFILE = 2,      /* 1: bracket the residual-layer kernel(s) of every evaluation with CUDA events; setting it
                                resets the sums */
   DSX_OPT_STACK_MODE = 3    /* 1 (default): all residual layers of an evaluation in ONE persistent launch whenever every

@@ -39,3 +39,11 @@ for cta in (0, 1):
     e = [rel(v) for v in tr[cta, 2, :13]]
     print("epilogue: [c0 wait-start, wait-done, done] [c1 ...] res wait-start, wait-done, skip wait-start, wait-done, end:")
     print("  ", e[0:3], e[4:7], e[8:13])
+    if cta == 0:
+        print("per layer (li = 0..5): producer past g2done", [rel(v) for v in tr[0, 0, 200:206]])
+        print("                       producer flags seen  ", [rel(v) for v in tr[0, 0, 210:216]])
+        print("                       mma TMEM buf0 free   ", [rel(v) for v in tr[0, 1, 210:216]])
+        print("                       mma GEMM1 first MMA  ", [rel(v) for v in tr[0, 1, 230:236]])
+        print("                       mma GEMM2 issued     ", [rel(v) for v in tr[0, 1, 220:226]])
+        print("                       epi2 residual done   ", [rel(v) for v in tr[0, 2, 100:106]])
+        print("                       epi2 skip done       ", [rel(v) for v in tr[0, 2, 110:116]])
