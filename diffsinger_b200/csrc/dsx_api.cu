@@ -508,7 +508,7 @@ int dsx_set_option(dsx_handle* h, int what, int64_t value) {
       DSX_CHECK(h->tc_group != 0, DSX_E_INVALID, "no tcgen05 on this device");
       h->tc_group = static_cast<int>(value);
       break;
-    case DSX_OPT_RESERVED_1: break;
+    case DSX_OPT_CP_PREFETCH: h->cp_prefetch = static_cast<int>(value); break;
     case DSX_OPT_STACK_MODE: h->stack_mode = static_cast<int>(value); break;
     case DSX_OPT_PROFILE:
       h->profile = value ? 1 : 0;

@@ -128,6 +128,7 @@ struct dsx_handle {
   bool attr_layer[3] = {false, false, false}, attr_head[2] = {false, false}, attr_cond = false;
   int occ_cache[3][17] = {};
   int cluster_occ = 0;              // max co-resident utterance clusters reported by the driver (last launch)
+  int cp_prefetch = 1;              // tuning knob (DSX_OPT_CP_PREFETCH)
   int stack_mode = 1;               // 1: all residual layers of an evaluation in one cluster-per-utterance launch
   long long* trace_dev = nullptr;   // debug timeline buffer (dsx_debug_trace)
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop), prof_used of them recorded

@@ -97,13 +97,11 @@ int simt_pack_model(dsx_handle* h, const dsx_diffnet_params* p, cudaStream_t s) 
 // cos as separate fp32 ops); here each transcendental is evaluated in double and rounded once,
 // which is within 1 ulp of any conforming fp32 libm.
 // ------------------------------------------------------------------------------------------
-__global__ void k_embed_table(ModelDev m, const int64_t* __restrict__ tvals, float* __restrict__ dtab,
-                              float* __restrict__ emb_out) {
+__global__ void k_embed_table(ModelDev m, const int64_t* __restrict__ tvals, float* __restrict__ emb_out) {
   extern __shared__ float sm[];
-  const int C = m.C, L = m.L;
+  const int C = m.C;
   float* e0 = sm;           // [C]  sinusoid
   float* h1 = sm + C;       // [4C] hidden
-  float* e2 = h1 + 4 * C;   // [C]  mlp out
   const int row = blockIdx.x;
   const float t = static_cast<float>(tvals[row]);
   const int half = C / 2;
@@ -135,21 +133,35 @@ __global__ void k_embed_table(ModelDev m, const int64_t* __restrict__ tvals, flo
   __syncthreads();
   for (int j = warp; j < C; j += nwarps) {
     float acc = dot(m.mlp2_w + static_cast<size_t>(j) * 4 * C, h1, 4 * C) + m.mlp2_b[j];
-    if (lane == 0) {
-      e2[j] = acc;
-      if (emb_out) emb_out[static_cast<size_t>(row) * C + j] = acc;
-    }
+    if (lane == 0) emb_out[static_cast<size_t>(row) * C + j] = acc;
   }
-  __syncthreads();
-  for (int idx = warp; idx < L * C; idx += nwarps) {
-    float acc = dot(m.dif_w + static_cast<size_t>(idx) * C, e2, C) + m.dif_b[idx];
-    if (lane == 0) dtab[static_cast<size_t>(row) * L * C + idx] = acc;
+}
+
+// per-layer FiLM vectors d_l(t) = diffusion_projection_l(emb(t)) (net.py:62,67) for every row of the table: one warp
+// per output channel keeps its weight row in registers and walks over the rows
+__global__ void k_embed_proj(ModelDev m, const float* __restrict__ emb, float* __restrict__ dtab, int rows) {
+  const int C = m.C, L = m.L;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (idx >= L * C) return;
+  const float* w = m.dif_w + static_cast<size_t>(idx) * C;
+  const float bias = m.dif_b[idx];
+  for (int row = 0; row < rows; ++row) {
+    const float* v = emb + static_cast<size_t>(row) * C;
+    float acc = 0.f;
+    for (int k = lane; k < C; k += 32) acc = fmaf(w[k], v[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) dtab[static_cast<size_t>(row) * L * C + idx] = acc + bias;
   }
 }
 
 int launch_embed_table(dsx_handle* h, const int64_t* t_dev, int rows, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(6) * h->m.C * sizeof(float);
-  k_embed_table<<<rows, 512, smem, s>>>(h->m, t_dev, h->ws.DTAB, h->ws.EMB);
+  const size_t smem = static_cast<size_t>(5) * h->m.C * sizeof(float);
+  k_embed_table<<<rows, 512, smem, s>>>(h->m, t_dev, h->ws.EMB);
+  h->launches++;
+  DSX_CUDA(cudaGetLastError());
+  k_embed_proj<<<(h->m.L * h->m.C + 15) / 16, 512, 0, s>>>(h->m, h->ws.EMB, h->ws.DTAB, rows);
   h->launches++;
   DSX_CUDA(cudaGetLastError());
   return DSX_OK;

@@ -56,46 +56,51 @@ struct TcCfg {
   static constexpr bool WLO = (P >= 2);     // W_lo pass
   static constexpr bool ALO_T = (P == 3);   // A_lo pass on the conv taps (y) and on z
   static constexpr int Z_PLANES = ALO_T ? 2 : 1;
-  // GEMM1 streams through a ring of UNITS 16 KB units.  z (the A operand of GEMM2) is [planes][4 k-blocks]
-  // of 16 KB: k-blocks 0,1 (written while GEMM1 still runs) have their own buffer; k-blocks 2,3 are written
-  // after GEMM1 has finished and alias the last Z23_UNITS ring units, so GEMM2's weight ring is the first
-  // UNITS2 units only.
-  // Epilogue 2 transposes the accumulator through STG_UNITS more ring units (free once GEMM1 is done).
-  // SHIFT (P <= 2): the three dilated taps of a 64-channel block share ONE shared-memory copy of the activations:
-  // a slot holds [8 halo rows | 128 centre rows | 8 halo rows] (18 KB) and tap j's UMMA descriptor simply starts
-  // (8 + (j-1)*d) rows in (SWIZZLE_128B is a function of the absolute address; verified by dsx_selftest(2)).  That cuts
-  // the bytes TMA must push into each SM -- the measured limiter of GEMM1 (~35-40 B/cycle/SM) -- by 14-21 %.
-  // P == 3 has no shared memory left for 18 KB slots and keeps one 16 KB tile per tap.
+  // z (the A operand of GEMM2) is [planes][4 k-blocks] of 16 KB: k-blocks 0,1 (written while GEMM1 still runs) have
+  // their own buffer z01; k-blocks 2,3 are written after GEMM1 has finished and alias operand buffers of GEMM1.
+  // Epilogue 2 transposes the accumulator through a 32 KB staging area (8 warps x 32 rows x 128 B).
+  //
+  // SHIFT (P <= 2): the three dilated taps of a 64-channel block share ONE shared-memory copy of the activations: a y
+  // slot holds [8 halo rows | 128 centre rows | 8 halo rows] (18 KB, one TMA box) and tap j's UMMA descriptor simply
+  // starts (8 + (j-1)*d) rows in (SWIZZLE_128B is a function of the absolute address; verified by dsx_selftest(2)).
+  // Shared memory: [W ring: WSLOTS x 16 KB | 2 y slots x 18 KB (z k-blocks 2,3 alias them) | staging 32 KB | z01].
+  // All weight tiles of GEMM1 and GEMM2, layer after layer, flow through the ONE W ring in a fixed global order, so
+  // the weight producers run ahead of every dependency (flags, epilogues, layer boundaries); the y slots double-buffer
+  // the activation blocks.
+  // (Splitting chunk 1 into two N = 128 sub-chunks to hide half of its gate epilogue was tried: a cta_group::2 MMA with
+  // N = 128 takes as long as one with N = 256 here, so it lost.)
+  // P == 3 has no shared memory for that and keeps one 16 KB tile per tap in a ring of UNITS units:
+  // [ring2 (GEMM2 weights) | z23 | staging] alias the ring once GEMM1 is done.
   static constexpr bool SHIFT = (P <= 2);
-  static constexpr int SLOT = SHIFT ? (kTile + 16) * 128 : kUnitBytes;
+  static constexpr int SLOT = SHIFT ? (kTile + 16) * 128 : kUnitBytes;   // y slot (SHIFT) / ring unit
+  static constexpr int WSLOTS = 7;
   static constexpr int UNITS = 10;
   static constexpr int Z23_UNITS = 2 * Z_PLANES;
-  static constexpr int STG_UNITS = 2;                           // 8 warps x 32 rows x 128 B
-  static constexpr int UNITS2 = UNITS - Z23_UNITS - STG_UNITS;   // ring layout: [ring2 | z23 | staging]
+  static constexpr int STG_UNITS = 2;
+  static constexpr int UNITS2 = UNITS - Z23_UNITS - STG_UNITS;
   static constexpr int Z01_BYTES = Z_PLANES * 2 * kUnitBytes;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = 1024 + UNITS * SLOT + Z01_BYTES + BAR_BYTES;
+  static constexpr int OPER_BYTES = SHIFT ? WSLOTS * kUnitBytes + 2 * SLOT + STG_UNITS * kUnitBytes : UNITS * kUnitBytes;
+  static constexpr int SMEM_BYTES = 1024 + OPER_BYTES + Z01_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  // ring units consumed per k-block: GEMM1 {A_hi, W_hi [, W_lo, A_lo]}, GEMM2 {W_hi [, W_lo]}
-  static constexpr int UT = 2 + (WLO ? 1 : 0) + (ALO_T ? 1 : 0);   // conv-tap k-block
+  // P == 3 ring units consumed per k-block: GEMM1 {A_hi, W_hi, W_lo, A_lo}, GEMM2 {W_hi, W_lo}
+  static constexpr int UT = 2 + (WLO ? 1 : 0) + (ALO_T ? 1 : 0);
   static constexpr int U2 = 1 + (WLO ? 1 : 0);
-  static constexpr int UG = 1 + 3 * (1 + (WLO ? 1 : 0));          // SHIFT: one 64-channel block = y unit + 3 taps x {W_hi [, W_lo]}
-  // Ring slot of unit `ul` of a layer.  The first S0 units cycle through the non-staging slots only, so they can be
-  // loaded and multiplied while the previous layer's skip epilogue still owns the staging slots; after that the whole
-  // ring is used.
-  static constexpr int S0 = SHIFT ? 2 * UG : 4 * UT;
+  // P == 3 ring slot of unit `ul` of a layer: the first S0 units cycle through the non-staging slots only, so they can
+  // be loaded and multiplied while the previous layer's skip epilogue still owns the staging slots.
+  static constexpr int S0 = 4 * UT;
   __host__ __device__ static constexpr int slot(int ul) { return ul < S0 ? ul % (UNITS - STG_UNITS) : (ul - S0) % UNITS; }
 };
 
 struct TcLayerParams {
   CUtensorMap tm_w;          // packed weights, 2D [rows][64], box 64 x 128 rows
   CUtensorMap tm_y[2][2];    // conv input, [buffer = layer parity][plane hi/lo], 3D [B][T][256]
-  CUtensorMap tm_cond[2];    // conditioner, planes hi/lo
   CUtensorMap tm_yh[2];      // conv input hi plane of buffer 0 / 1 with a box of 8 + 128 + 8 frames (SHIFT layout)
   float* X;                  // [B][Tp][256] residual stream (in/out)
   float* SKIP;               // [B][Tp][256]
   __half* Y;                 // [2 buffers][2 planes][plane_elems]: layer l reads buffer l&1, writes buffer (l+1)&1
   size_t plane_elems;
+  int cp_prefetch;           // SHIFT: the activation producer streams CP into L2 half a layer ahead (tuning knob)
   const float* CP;           // [L][tiles][2 chunks][64 column groups][128 rows][4]: cond projection + bias (fp32)
   const float* b2;           // [L][512]
   const float* dtab;         // FiLM table row of this evaluation: [L][256], utterance b at + b * d_row_stride
@@ -113,10 +118,12 @@ struct TcLayerParams {
 };
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
-__device__ __forceinline__ float sigmoid_acc(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float tanh_acc(float x) {
-  // 2*sigmoid(2x) - 1, absolute error ~2e-7
-  return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * x)), -1.f);
+// sigmoid(g) * tanh(f) = (1 - E2) / ((1 + E1)(1 + E2)), E1 = e^-g, E2 = e^-2f: three MUFU operations instead of four
+// (the gate epilogue is MUFU-bound); absolute error ~2e-7.  f is clamped at -15 (tanh = -1 to 2e-13) so E2 stays finite.
+__device__ __forceinline__ float gate_acc(float g, float f) {
+  const float e1 = ex2_approx(-1.4426950408889634f * g);
+  const float e2 = ex2_approx(-2.8853900817779268f * fmaxf(f, -15.f));
+  return (1.f - e2) * rcp_approx((1.f + e1) * (1.f + e2));
 }
 __device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
@@ -166,23 +173,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   constexpr int NU2 = Cfg::UNITS2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* z01 = ring + NU * Cfg::SLOT;
-  uint8_t* staging = ring + (NU - Cfg::STG_UNITS) * Cfg::SLOT;   // last ring units: epilogue-2 transpose
+  // SHIFT: ring = W ring (WSLOTS x 16 KB), then the two y slots, then staging; otherwise the 10-unit ring whose last
+  // units double as z23 / staging
+  uint8_t* yslots = ring + Cfg::WSLOTS * kUnitBytes;                                     // SHIFT only
+  uint8_t* staging = Cfg::SHIFT ? yslots + 2 * Cfg::SLOT : ring + (NU - Cfg::STG_UNITS) * kUnitBytes;
+  uint8_t* z01 = ring + Cfg::OPER_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(z01 + Cfg::Z01_BYTES);
-  uint64_t* full = bars;             // [NU]   GEMM1 ring
+  uint64_t* full = bars;             // [NU]   P == 3: GEMM1 ring; SHIFT: W ring (first WSLOTS)
   uint64_t* empty = full + NU;       // [NU]
-  uint64_t* full2 = empty + NU;      // [NU2]  GEMM2 weight ring (aliases ring units 0..NU2-1)
+  uint64_t* full2 = empty + NU;      // [NU2]  P == 3: GEMM2 weight ring (aliases ring units 0..NU2-1)
   uint64_t* empty2 = full2 + NU2;    // [NU2]
   uint64_t* tfull = empty2 + NU2;    // [2]
   uint64_t* tempty = tfull + 2;      // [2]
   uint64_t* zf = tempty + 2;         // [2] z k-block 2 / 3 written (both CTAs of the pair); k-blocks 0,1 ride on tempty[0]
-  uint64_t* g1done = zf + 2;         // all GEMM1 MMAs of the layer complete
-  uint64_t* g2done = g1done + 1;     // all GEMM2 MMAs of the layer complete (ring2 / z units reusable)
-  uint64_t* edone = g2done + 1;      // this CTA's epilogue has left the staging units
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(edone + 1);
-  // z k-block address: plane 0 = hi, 1 = lo.  k-blocks 2,3 alias ring units [NU2, NU2 + Z23_UNITS)
+  uint64_t* g1done = zf + 2;         // P == 3: all GEMM1 MMAs of the layer complete
+  uint64_t* g2done = g1done + 1;     // all GEMM2 MMAs of the layer complete (z units reusable)
+  uint64_t* edone = g2done + 1;      // P == 3: this CTA's epilogue has left the staging units
+  uint64_t* yfull = edone + 1;       // [2] SHIFT: y slots
+  uint64_t* yempty = yfull + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty + 2);
+  static_assert((2 * Cfg::UNITS + 2 * Cfg::UNITS2 + 13) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
+  // z k-block address: plane 0 = hi, 1 = lo.  k-blocks 2,3 alias the y slots (SHIFT) / ring units [NU2, NU2 + Z23_UNITS)
   auto zaddr = [&](int plane, int kb) -> uint8_t* {
-    return kb < 2 ? z01 + (plane * 2 + kb) * kUnitBytes : ring + (NU2 + plane * 2 + (kb - 2)) * Cfg::SLOT;
+    if (kb < 2) return z01 + (plane * 2 + kb) * kUnitBytes;
+    return Cfg::SHIFT ? yslots + (kb - 2) * Cfg::SLOT : ring + (NU2 + plane * 2 + (kb - 2)) * kUnitBytes;
   };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -233,6 +247,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
     }
     mbar_init(&zf[0], kEpiWarps * G);
     mbar_init(&zf[1], kEpiWarps * G);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&yfull[i], 1);
+      mbar_init(&yempty[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<G>(tmem_slot, 512);
@@ -245,133 +263,176 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   Watchdog wd{p.status, globaltimer_ns() + p.budget_ns};
   if (threadIdx.x == 0) DSX_TRACE(0, 254);
 
-  // A thread gets one TMA load accepted per ~430 cycles whatever its size (dsx_selftest(3)): three producer threads
-  // (warps 0, 2, 3) take the units of the ring round-robin, each with the full slot / parity bookkeeping.
+  // A thread gets one TMA load accepted per ~430 cycles whatever its size (dsx_selftest(3)), so three threads (lane 0
+  // of warps 0, 2, 3) produce.  SHIFT: producer 0 owns the activation blocks (and their dependencies), producers 1, 2
+  // alternate over the weight tiles.  P == 3: the three take the ring units round-robin.
   const int prod_id = (warp == 0) ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
   if (prod_id >= 0 && lane == 0) {
-    // ================================ TMA producers ================================
-    constexpr int NP = 3;
-    uint32_t pbits = 0, pbits2 = 0;                 // per-slot use parity of ring 1 / ring 2
     bool ok = true;
-    for (int l = p.l0; l < p.l1 && ok; ++l) {
-      const int li = l - p.l0;
-      const uint32_t prev = (li - 1) & 1;
-      const int dil = 1 << (l % p.cycle);
-      const int w_row0 = l * kRowsPerLayer;
-      const CUtensorMap* ymap = p.tm_y[l & 1];
-      bool y_ok = (li == 0) || !multi || !tile_valid, e_ok = (li == 0);
-      if (li > 0) ok = mbar_wait(g2done, prev, wd, 105);            // ring-2 / z units of the previous layer are free
-      if (prod_id == 0 && li < 10) DSX_TRACE(0, 200 + li);
-      int ul = 0;                                                   // unit index within the layer
-      // Slot of unit `ul` if it is this producer's, waited empty and armed; nullptr otherwise (check `ok`).
-      auto acquire = [&](int code, int bytes = kUnitBytes) -> uint8_t* {
-        const int s = Cfg::slot(ul);
-        const uint32_t par = ((pbits >> s) & 1) ^ 1;
-        pbits ^= 1u << s;
-        if (ul % NP != prod_id) return nullptr;
-        if (!e_ok && s >= NU - Cfg::STG_UNITS) {                    // staging units: previous epilogue must be done
-          ok = mbar_wait(edone, prev, wd, 106);
-          e_ok = true;
+    if constexpr (Cfg::SHIFT) {
+      if (prod_id == 0) {
+        // ================================ activation producer ================================
+        uint32_t yi = 0;                                            // running block index: slot yi & 1
+        for (int l = p.l0; l < p.l1 && ok; ++l) {
+          const int li = l - p.l0;
+          if (li > 0) {
+            ok = mbar_wait(g2done, (li - 1) & 1, wd, 105);          // z k-blocks 2,3 (in the y slots) consumed
+            if (li < 10) DSX_TRACE(0, 200 + li);
+            if (ok && multi && tile_valid) {                        // y_l of this tile and its neighbours published
+              const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
+              ok = flag_wait(p.flags + tile, target, wd, 107);
+              if (ok && nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
+              if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
+              fence_proxy_async_all();
+            }
+            if (li < 10) DSX_TRACE(0, 210 + li);
+          }
+          for (int hc = 0; hc < 8 && ok; ++hc, ++yi) {              // (chunk h, channel block cb) = (hc >> 2, hc & 3)
+            const int s = yi & 1;
+            ok = mbar_wait(&yempty[s], ((yi >> 1) & 1) ^ 1, wd, 110);
+            if (!ok) break;
+            DSX_TRACE(0, hc);
+            if (prank == 0) mbar_arrive_expect_tx(&yfull[s], G * Cfg::SLOT);
+            tma_load_3d<G>(&p.tm_yh[l & 1], &yfull[s], yslots + s * Cfg::SLOT, (hc & 3) * 64, t0 - 8, bq, lead);
+            if (p.cp_prefetch) {
+              // stream the conditioner projection HBM -> L2 half a layer ahead of the gate epilogue that reads it:
+              // during chunk 0's blocks chunk 1 of this layer, during chunk 1's blocks chunk 0 of the next layer
+              const int pl = (hc < 4) ? l : l + 1, ph = (hc < 4) ? 1 : 0;
+              if (pl < p.l1) {
+                const char* src = reinterpret_cast<const char*>(p.CP + ((static_cast<size_t>(pl) * p.tiles + cp_tile) * 2 + ph) * kCpChunk);
+                prefetch_l2_bulk(src + (hc & 3) * 32768, 16384);
+                prefetch_l2_bulk(src + (hc & 3) * 32768 + 16384, 16384);
+              }
+            }
+          }
+        }
+      } else {
+        // ================================ weight producers ================================
+        const uint32_t wid = prod_id - 1;
+        uint32_t wi = 0;                                            // running W tile index: slot wi % WSLOTS
+        for (int l = p.l0; l < p.l1 && ok; ++l) {
+          const int w_row0 = l * kRowsPerLayer;
+          auto load_w = [&](int tileidx) {
+            if ((wi & 1) == wid) {
+              const uint32_t s = wi % Cfg::WSLOTS;
+              ok = mbar_wait(&empty[s], ((wi / Cfg::WSLOTS) & 1) ^ 1, wd, 102);
+              if (ok) {
+                if (prank == 0) mbar_arrive_expect_tx(&full[s], G * kUnitBytes);
+                tma_load_2d<G>(&p.tm_w, &full[s], ring + s * kUnitBytes, 0,
+                               w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
+              }
+            }
+            ++wi;
+          };
+          for (int h = 0; h < 2 && ok; ++h)
+            for (int cb = 0; cb < 4 && ok; ++cb)
+              for (int tj = 0; tj < 3 && ok; ++tj) {                // tap order: centre, left, right
+                const int tap = tj == 0 ? 1 : (tj == 1 ? 0 : 2);
+                load_w((0 * 2 + h) * 16 + tap * 4 + cb);
+                if (Cfg::WLO && ok) load_w((1 * 2 + h) * 16 + tap * 4 + cb);
+              }
+          for (int q = 0; q < 2 && ok; ++q)
+            for (int kb = 0; kb < 4 && ok; ++kb) {
+              load_w(64 + (0 * 2 + q) * 4 + kb);
+              if (Cfg::WLO && ok) load_w(64 + (1 * 2 + q) * 4 + kb);
+            }
+        }
+      }
+    } else {
+      // ================================ ring producers (P == 3) ================================
+      constexpr int NP = 3;
+      uint32_t pbits = 0, pbits2 = 0;                 // per-slot use parity of ring 1 / ring 2
+      for (int l = p.l0; l < p.l1 && ok; ++l) {
+        const int li = l - p.l0;
+        const uint32_t prev = (li - 1) & 1;
+        const int dil = 1 << (l % p.cycle);
+        const int w_row0 = l * kRowsPerLayer;
+        const CUtensorMap* ymap = p.tm_y[l & 1];
+        bool y_ok = (li == 0) || !multi || !tile_valid, e_ok = (li == 0);
+        if (li > 0) ok = mbar_wait(g2done, prev, wd, 105);            // ring-2 / z units of the previous layer are free
+        if (prod_id == 0 && li < 10) DSX_TRACE(0, 200 + li);
+        int ul = 0;                                                   // unit index within the layer
+        // Slot of unit `ul` if it is this producer's, waited empty and armed; nullptr otherwise (check `ok`).
+        auto acquire = [&](int code) -> uint8_t* {
+          const int s = Cfg::slot(ul);
+          const uint32_t par = ((pbits >> s) & 1) ^ 1;
+          pbits ^= 1u << s;
+          if (ul % NP != prod_id) return nullptr;
+          if (!e_ok && s >= NU - Cfg::STG_UNITS) {                    // staging units: previous epilogue must be done
+            ok = mbar_wait(edone, prev, wd, 106);
+            e_ok = true;
+            if (!ok) return nullptr;
+          }
+          ok = mbar_wait(&empty[s], par, wd, code);
           if (!ok) return nullptr;
-        }
-        ok = mbar_wait(&empty[s], par, wd, code);
-        if (!ok) return nullptr;
-        DSX_TRACE(0, ul);
-        if (prank == 0) mbar_arrive_expect_tx(&full[s], G * bytes);
-        return ring + s * Cfg::SLOT;
-      };
-      const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
-      bool yn_ok = y_ok;                                            // neighbours' y (halo taps)
-      auto load_a = [&](int plane, int kb) {                        // P = 3: one 16 KB tile per tap and channel block
-        if (ul % NP == prod_id) {
-          if (!y_ok) {                                              // centre tap: y_l of this tile
-            ok = flag_wait(p.flags + tile, target, wd, 107);
-            fence_proxy_async_all();
-            y_ok = true;
+          DSX_TRACE(0, ul);
+          if (prank == 0) mbar_arrive_expect_tx(&full[s], G * kUnitBytes);
+          return ring + s * kUnitBytes;
+        };
+        const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
+        bool yn_ok = y_ok;                                            // neighbours' y (halo taps)
+        auto load_a = [&](int plane, int kb) {
+          if (ul % NP == prod_id) {
+            if (!y_ok) {                                              // centre tap: y_l of this tile
+              ok = flag_wait(p.flags + tile, target, wd, 107);
+              fence_proxy_async_all();
+              y_ok = true;
+            }
+            if (ok && (kb >> 2) != 1 && !yn_ok) {                     // halo taps: y_l of the neighbour tiles
+              if (nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
+              if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
+              fence_proxy_async_all();
+              yn_ok = true;
+            }
+            if (!ok) return;
           }
-          if (ok && (kb >> 2) != 1 && !yn_ok) {                     // halo taps: y_l of the neighbour tiles
-            if (nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
-            if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
-            fence_proxy_async_all();
-            yn_ok = true;
-          }
-          if (!ok) return;
-        }
-        const int s = Cfg::slot(ul);
-        uint8_t* dst = acquire(101);
-        if (dst) tma_load_3d<G>(&ymap[plane], &full[s], dst, (kb & 3) * 64, t0 + ((kb >> 2) - 1) * dil, bq, lead);
-        ++ul;
-      };
-      auto load_w = [&](int tileidx) {
-        const int s = Cfg::slot(ul);
-        uint8_t* dst = acquire(102);
-        if (dst) tma_load_2d<G>(&p.tm_w, &full[s], dst, 0, w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
-        ++ul;
-      };
-      if constexpr (!Cfg::SHIFT) {
+          const int s = Cfg::slot(ul);
+          uint8_t* dst = acquire(101);
+          if (dst) tma_load_3d<G>(&ymap[plane], &full[s], dst, (kb & 3) * 64, t0 + ((kb >> 2) - 1) * dil, bq, lead);
+          ++ul;
+        };
+        auto load_w = [&](int tileidx) {
+          const int s = Cfg::slot(ul);
+          uint8_t* dst = acquire(102);
+          if (dst) tma_load_2d<G>(&p.tm_w, &full[s], dst, 0, w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
+          ++ul;
+        };
         for (int h = 0; h < 2 && ok; ++h)
           for (int ko = 0; ko < 12 && ok; ++ko) {
             const int kb = kb_order(ko);
             load_a(0, kb);
             if (ok) load_w((0 * 2 + h) * 16 + kb);
-            if (Cfg::WLO && ok) load_w((1 * 2 + h) * 16 + kb);
-            if (Cfg::ALO_T && ok) load_a(1, kb);
+            if (ok) load_w((1 * 2 + h) * 16 + kb);
+            if (ok) load_a(1, kb);
           }
-      } else {
-        // one activation unit per 64-channel block: [8 halo | 128 centre | 8 halo] rows = one 144-row box
-        auto load_y = [&](int cb) {
-          if (ul % NP == prod_id && !y_ok) {
-            ok = flag_wait(p.flags + tile, target, wd, 107);
-            if (ok && nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
-            if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
-            fence_proxy_async_all();
-            y_ok = true;
-            if (prod_id == 0 && li < 10) DSX_TRACE(0, 210 + li);
+        // GEMM2 weights: second ring over units 0..NU2-1, usable once every GEMM1 MMA has completed
+        if (ok) ok = mbar_wait(g1done, li & 1, wd, 103);
+        int u2 = 0;
+        auto load_w2 = [&](int tileidx) {
+          const int s = u2 % NU2;
+          const uint32_t par = ((pbits2 >> s) & 1) ^ 1;
+          pbits2 ^= 1u << s;
+          if (u2 % NP == prod_id) {
+            ok = mbar_wait(&empty2[s], par, wd, 104);
             if (!ok) return;
+            DSX_TRACE(0, 128 + u2);
+            if (prank == 0) mbar_arrive_expect_tx(&full2[s], G * kUnitBytes);
+            tma_load_2d<G>(&p.tm_w, &full2[s], ring + s * kUnitBytes, 0,
+                           w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
           }
-          const int s = Cfg::slot(ul);
-          uint8_t* dst = acquire(110, Cfg::SLOT);
-          if (dst) tma_load_3d<G>(&p.tm_yh[l & 1], &full[s], dst, cb * 64, t0 - 8, bq, lead);
-          ++ul;
+          ++u2;
         };
-        for (int h = 0; h < 2 && ok; ++h) {
-          for (int cb = 0; cb < 4 && ok; ++cb) {
-            load_y(cb);
-            for (int tj = 0; tj < 3 && ok; ++tj) {         // tap order: centre, left, right
-              const int tap = tj == 0 ? 1 : (tj == 1 ? 0 : 2);
-              load_w((0 * 2 + h) * 16 + tap * 4 + cb);
-              if (Cfg::WLO && ok) load_w((1 * 2 + h) * 16 + tap * 4 + cb);
-            }
+        for (int q = 0; q < 2 && ok; ++q)
+          for (int kb = 0; kb < 4 && ok; ++kb) {
+            load_w2(64 + (0 * 2 + q) * 4 + kb);
+            if (ok) load_w2(64 + (1 * 2 + q) * 4 + kb);
           }
-        }
       }
-      // GEMM2 weights: second ring over units 0..NU2-1, usable once every GEMM1 MMA has completed
-      if (ok) ok = mbar_wait(g1done, li & 1, wd, 103);
-      int u2 = 0;
-      auto load_w2 = [&](int tileidx) {
-        const int s = u2 % NU2;
-        const uint32_t par = ((pbits2 >> s) & 1) ^ 1;
-        pbits2 ^= 1u << s;
-        if (u2 % NP == prod_id) {
-          ok = mbar_wait(&empty2[s], par, wd, 104);
-          if (!ok) return;
-          DSX_TRACE(0, 128 + u2);
-          if (prank == 0) mbar_arrive_expect_tx(&full2[s], G * kUnitBytes);
-          tma_load_2d<G>(&p.tm_w, &full2[s], ring + s * Cfg::SLOT, 0,
-                         w_row0 + tileidx * 256 + static_cast<int>(prank) * 128, lead);
-        }
-        ++u2;
-      };
-      for (int q = 0; q < 2 && ok; ++q)
-        for (int kb = 0; kb < 4 && ok; ++kb) {
-          load_w2(64 + (0 * 2 + q) * 4 + kb);
-          if (Cfg::WLO && ok) load_w2(64 + (1 * 2 + q) * 4 + kb);
-        }
     }
   } else if (warp == 1 && lane == 0 && prank == 0) {
     // ================================ MMA issuer (pair leader) ================================
     constexpr uint32_t idesc = umma_idesc_f16(128 * G, 256);
-    uint32_t mbits = 0, mbits2 = 0, tuse[2] = {0, 0};
+    uint32_t tuse[2] = {0, 0};
     bool ok = true;
     auto mma4 = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t& acc) {
 #pragma unroll
@@ -380,129 +441,150 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         acc = 1;
       }
     };
-    for (int l = p.l0; l < p.l1 && ok; ++l) {
-      const int li = l - p.l0;
-      int ul = 0, u2 = 0;
-      auto wait_unit = [&](int uu, int code) -> uint64_t {
-        const int s = Cfg::slot(uu);
-        ok = ok && mbar_wait(&full[s], (mbits >> s) & 1, wd, code);
-        mbits ^= 1u << s;
-        return umma_desc_sw128(smem_u32(ring + s * Cfg::SLOT));
-      };
-      auto wait_unit2 = [&](int uu, int code) -> uint64_t {
-        const int s = uu % NU2;
-        ok = ok && mbar_wait(&full2[s], (mbits2 >> s) & 1, wd, code);
-        mbits2 ^= 1u << s;
-        return umma_desc_sw128(smem_u32(ring + s * Cfg::SLOT));
-      };
-      for (int h = 0; h < 2 && ok; ++h) {
-        const int buf = h;
-        ok = mbar_wait(&tempty[buf], (tuse[buf] & 1) ^ 1, wd, 201);
-        if (!ok) break;
-        tuse[buf]++;
-        tc_fence_after();
-        const uint32_t d = tmem_base + buf * 256;
-        uint32_t acc = 0;
-        if (h == 0 && li < 10) DSX_TRACE(1, 210 + li);              // TMEM buffer 0 free: GEMM1 of this layer may start
-        for (int ko = 0; ko < (Cfg::SHIFT ? 0 : 12) && ok; ++ko) {
-          constexpr bool alo = Cfg::ALO_T;
-          constexpr int nu = Cfg::UT;
-          const uint64_t a_hi = wait_unit(ul, 202);
-          const uint64_t w_hi = wait_unit(ul + 1, 202);
-          if (!ok) break;
-          DSX_TRACE(1, ko + 16 * h);
-          tc_fence_after();
-          mma4(d, a_hi, w_hi, acc);
-          if (Cfg::WLO) {
-            const uint64_t w_lo = wait_unit(ul + 2, 202);
-            if (!ok) break;
-            tc_fence_after();
-            mma4(d, a_hi, w_lo, acc);
-          }
-          if (alo) {
-            const uint64_t a_lo = wait_unit(ul + 3, 202);
-            if (!ok) break;
-            tc_fence_after();
-            mma4(d, a_lo, w_hi, acc);
-          }
-          for (int i = 0; i < nu; ++i) umma_commit<G>(&empty[Cfg::slot(ul + i)], pair_mask);
-          ul += nu;
-        }
-        if constexpr (Cfg::SHIFT) {
-          const int dil = 1 << (l % p.cycle);
-          for (int cb = 0; cb < 4 && ok; ++cb) {
-            const uint64_t y = wait_unit(ul, 206);              // [8 halo | 128 centre | 8 halo] rows of 64 channels
-            if (!ok) break;
-            DSX_TRACE(1, 4 + cb + 16 * h);
-            if (h == 0 && cb == 0 && li < 10) DSX_TRACE(1, 230 + li);
-            int uu = ul + 1;
-            for (int tj = 0; tj < 3 && ok; ++tj) {
-              const int tap = tj == 0 ? 1 : (tj == 1 ? 0 : 2);
-              const uint64_t a = y + static_cast<uint64_t>(((8 + (tap - 1) * dil) * 128) >> 4);   // row-shifted start
-              const uint64_t w_hi = wait_unit(uu, 207);
-              if (!ok) break;
-              tc_fence_after();
-              mma4(d, a, w_hi, acc);
-              umma_commit<G>(&empty[Cfg::slot(uu)], pair_mask);
-              ++uu;
-              if (Cfg::WLO) {
-                const uint64_t w_lo = wait_unit(uu, 207);
-                if (!ok) break;
-                tc_fence_after();
-                mma4(d, a, w_lo, acc);
-                umma_commit<G>(&empty[Cfg::slot(uu)], pair_mask);
-                ++uu;
-              }
-            }
-            umma_commit<G>(&empty[Cfg::slot(ul)], pair_mask);   // the y unit, after its last tap
-            ul = uu;
-          }
-        }
-        if (ok) umma_commit<G>(&tfull[buf], pair_mask);
-      }
-      if (ok) umma_commit<G>(g1done, pair_mask);
-      DSX_TRACE(1, 200);
-      // GEMM2 reads z k-blocks 0,1 as soon as its TMEM buffer is free (tempty[0] is released after epi1 of chunk 0,
-      // which also made z01 visible), then k-blocks 2 and 3 as the chunk-1 epilogue delivers them.
+    // GEMM2 of one layer given a functor that multiplies z k-block kb (accumulator d) by the next weight tile(s)
+    auto gemm2 = [&](int li, auto&& kblock) {
       for (int q = 0; q < 2 && ok; ++q) {
-        const int buf = q;
-        ok = mbar_wait(&tempty[buf], (tuse[buf] & 1) ^ 1, wd, 204);
+        ok = mbar_wait(&tempty[q], (tuse[q] & 1) ^ 1, wd, 204);
         if (!ok) break;
+        tuse[q]++;
         DSX_TRACE(1, 202 + q);
-        tuse[buf]++;
         tc_fence_after();
-        const uint32_t d = tmem_base + buf * 256;
+        const uint32_t d = tmem_base + q * 256;
         uint32_t acc = 0;
         for (int kb = 0; kb < 4 && ok; ++kb) {
-          if (q == 0 && kb >= 2) {
+          if (q == 0 && kb >= 2) {                     // z k-blocks 2, 3 arrive from the chunk-1 gate epilogue
             ok = mbar_wait(&zf[kb - 2], li & 1, wd, 203);
             if (kb == 3) DSX_TRACE(1, 201);
             if (!ok) break;
             tc_fence_after();
           }
-          const uint64_t z_hi = umma_desc_sw128(smem_u32(zaddr(0, kb)));
-          const uint64_t w_hi = wait_unit2(u2, 205);
-          if (!ok) break;
-          DSX_TRACE(1, 128 + u2);
-          tc_fence_after();
-          mma4(d, z_hi, w_hi, acc);
-          if (Cfg::WLO) {
-            const uint64_t w_lo = wait_unit2(u2 + 1, 205);
-            if (!ok) break;
-            tc_fence_after();
-            mma4(d, z_hi, w_lo, acc);
-          }
-          if (Cfg::ALO_T) {
-            const uint64_t z_lo = umma_desc_sw128(smem_u32(zaddr(1, kb)));
-            mma4(d, z_lo, w_hi, acc);
-          }
-          for (int i = 0; i < Cfg::U2; ++i) umma_commit<G>(&empty2[(u2 + i) % NU2], pair_mask);
-          u2 += Cfg::U2;
+          kblock(d, q, kb, acc);
         }
-        if (ok) umma_commit<G>(&tfull[buf], pair_mask);
+        if (ok) umma_commit<G>(&tfull[q], pair_mask);
       }
       if (ok) umma_commit<G>(g2done, pair_mask);
       if (li < 10) DSX_TRACE(1, 220 + li);
+    };
+    if constexpr (Cfg::SHIFT) {
+      uint32_t wi = 0, yi = 0;
+      auto wait_w = [&](int code) -> uint64_t {        // next weight tile of the global order
+        const uint32_t s = wi % Cfg::WSLOTS;
+        ok = ok && mbar_wait(&full[s], (wi / Cfg::WSLOTS) & 1, wd, code);
+        return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
+      };
+      auto done_w = [&]() {
+        umma_commit<G>(&empty[wi % Cfg::WSLOTS], pair_mask);
+        ++wi;
+      };
+      for (int l = p.l0; l < p.l1 && ok; ++l) {
+        const int li = l - p.l0;
+        const int dil = 1 << (l % p.cycle);
+        for (int h = 0; h < 2 && ok; ++h) {
+          ok = mbar_wait(&tempty[h], (tuse[h] & 1) ^ 1, wd, 201);
+          if (!ok) break;
+          tuse[h]++;
+          tc_fence_after();
+          const uint32_t d = tmem_base + h * 256;
+          uint32_t acc = 0;
+          if (h == 0 && li < 10) DSX_TRACE(1, 210 + li);            // TMEM buffer 0 free: GEMM1 of this layer may start
+          for (int cb = 0; cb < 4 && ok; ++cb, ++yi) {
+            const int ys = yi & 1;
+            ok = mbar_wait(&yfull[ys], (yi >> 1) & 1, wd, 206);     // [8 halo | 128 centre | 8 halo] rows of 64 channels
+            if (!ok) break;
+            const uint64_t y = umma_desc_sw128(smem_u32(yslots + ys * Cfg::SLOT));
+            DSX_TRACE(1, 4 + cb + 16 * h);
+            if (h == 0 && cb == 0 && li < 10) DSX_TRACE(1, 230 + li);
+            for (int tj = 0; tj < 3 && ok; ++tj) {
+              const int tap = tj == 0 ? 1 : (tj == 1 ? 0 : 2);
+              const uint64_t a = y + static_cast<uint64_t>(((8 + (tap - 1) * dil) * 128) >> 4);   // row-shifted start
+              for (int pl = 0; pl < (Cfg::WLO ? 2 : 1) && ok; ++pl) {
+                const uint64_t w = wait_w(207);
+                if (!ok) break;
+                tc_fence_after();
+                mma4(d, a, w, acc);
+                done_w();
+              }
+            }
+            umma_commit<G>(&yempty[ys], pair_mask);                 // the y slot, after its last tap
+          }
+          if (ok) umma_commit<G>(&tfull[h], pair_mask);
+        }
+        DSX_TRACE(1, 200);
+        gemm2(li, [&](uint32_t d, int, int kb, uint32_t& acc) {
+          const uint64_t z_hi = umma_desc_sw128(smem_u32(zaddr(0, kb)));
+          for (int pl = 0; pl < (Cfg::WLO ? 2 : 1) && ok; ++pl) {
+            const uint64_t w = wait_w(205);
+            if (!ok) break;
+            tc_fence_after();
+            mma4(d, z_hi, w, acc);
+            done_w();
+          }
+        });
+      }
+    } else {
+      uint32_t mbits = 0, mbits2 = 0;
+      for (int l = p.l0; l < p.l1 && ok; ++l) {
+        const int li = l - p.l0;
+        int ul = 0, u2 = 0;
+        auto wait_unit = [&](int uu, int code) -> uint64_t {
+          const int s = Cfg::slot(uu);
+          ok = ok && mbar_wait(&full[s], (mbits >> s) & 1, wd, code);
+          mbits ^= 1u << s;
+          return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
+        };
+        auto wait_unit2 = [&](int uu, int code) -> uint64_t {
+          const int s = uu % NU2;
+          ok = ok && mbar_wait(&full2[s], (mbits2 >> s) & 1, wd, code);
+          mbits2 ^= 1u << s;
+          return umma_desc_sw128(smem_u32(ring + s * kUnitBytes));
+        };
+        for (int h = 0; h < 2 && ok; ++h) {
+          ok = mbar_wait(&tempty[h], (tuse[h] & 1) ^ 1, wd, 201);
+          if (!ok) break;
+          tuse[h]++;
+          tc_fence_after();
+          const uint32_t d = tmem_base + h * 256;
+          uint32_t acc = 0;
+          if (h == 0 && li < 10) DSX_TRACE(1, 210 + li);
+          for (int ko = 0; ko < 12 && ok; ++ko) {
+            const uint64_t a_hi = wait_unit(ul, 202);
+            const uint64_t w_hi = wait_unit(ul + 1, 202);
+            if (!ok) break;
+            DSX_TRACE(1, ko + 16 * h);
+            if (h == 0 && ko == 0 && li < 10) DSX_TRACE(1, 230 + li);
+            tc_fence_after();
+            mma4(d, a_hi, w_hi, acc);
+            const uint64_t w_lo = wait_unit(ul + 2, 202);
+            if (!ok) break;
+            tc_fence_after();
+            mma4(d, a_hi, w_lo, acc);
+            const uint64_t a_lo = wait_unit(ul + 3, 202);
+            if (!ok) break;
+            tc_fence_after();
+            mma4(d, a_lo, w_hi, acc);
+            for (int i = 0; i < Cfg::UT; ++i) umma_commit<G>(&empty[Cfg::slot(ul + i)], pair_mask);
+            ul += Cfg::UT;
+          }
+          if (ok) umma_commit<G>(&tfull[h], pair_mask);
+        }
+        if (ok) umma_commit<G>(g1done, pair_mask);
+        DSX_TRACE(1, 200);
+        gemm2(li, [&](uint32_t d, int, int kb, uint32_t& acc) {
+          const uint64_t z_hi = umma_desc_sw128(smem_u32(zaddr(0, kb)));
+          const uint64_t w_hi = wait_unit2(u2, 205);
+          if (!ok) return;
+          DSX_TRACE(1, 128 + u2);
+          tc_fence_after();
+          mma4(d, z_hi, w_hi, acc);
+          const uint64_t w_lo = wait_unit2(u2 + 1, 205);
+          if (!ok) return;
+          tc_fence_after();
+          mma4(d, z_hi, w_lo, acc);
+          mma4(d, umma_desc_sw128(smem_u32(zaddr(1, kb))), w_hi, acc);
+          for (int i = 0; i < Cfg::U2; ++i) umma_commit<G>(&empty2[(u2 + i) % NU2], pair_mask);
+          u2 += Cfg::U2;
+        });
+      }
     }
   } else if (warp >= 4) {
     // ================================ epilogue (8 warps) ================================
@@ -524,13 +606,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
     };
     const uint64_t cp_policy = l2_policy_evict_first();
     uint8_t* stg = staging + (warp - 4) * 4096;
-    const int lrow = lane >> 4;                               // epi2 reader: half-warp = one row
-    const int lc2 = lane & 15;                                // column pair within the 32-column group
+    const int lrow = lane >> 3;                               // epi2 reader: 8 lanes = one row of 32 columns (4 rows per access)
+    const int lc4 = lane & 7;                                 // 4-column chunk within the 32-column group
     const int urow0 = tile_valid ? t0 + quad * 32 : p.T;      // first frame of this warp's 32 rows
     const int nrows = min(max(p.T - urow0, 0), 32);           // valid rows of this warp (warp-uniform)
     const size_t rbase = (static_cast<size_t>(tile_valid ? b : 0) * p.Tp + (tile_valid ? t0 + quad * 32 : 0) + lrow) * kC +
-                         half * 128 + lc2 * 2;
-    const uint8_t* stg_rd = stg + lrow * 128 + (lc2 & 1) * 8;
+                         half * 128 + lc4 * 4;
+    const uint8_t* stg_rd = stg + lrow * 128;
 
     for (int l = p.l0; l < p.l1 && ok; ++l) {
       const float* b2 = p.b2 + static_cast<size_t>(l) * 512;
@@ -539,39 +621,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       __half* const yout = p.Y + static_cast<size_t>(((l + 1) & 1) * 2) * p.plane_elems;
       const float* dnext = (l + 1 < p.L) ? p.dtab + static_cast<size_t>(l + 1) * kC : nullptr;
       // ---- epi1: z = sigmoid(gate) * tanh(filter), gate/filter = accumulator + CP (conditioner projection + bias,
-      //      streamed from HBM in the accumulator's own layout: one float4 = 4 columns of this thread's row).
-      //      Four sub-passes of 16 gate/filter column pairs per chunk; sub-passes 2*it, 2*it+1 of all 8 warps complete
-      //      z k-block 2h + it, so GEMM2 can start on k-block 2 while k-block 3 is still being gated.  CP loads run one
-      //      sub-pass ahead (the first one is issued before the accumulator wait). ----
+      //      streamed in the accumulator's own layout: one float4 = 4 columns of this thread's row).  A phase drains one
+      //      accumulator in sub-passes of 16 gate/filter column pairs per warp; CP loads run one sub-pass ahead (the
+      //      first is issued before the accumulator wait).
+      //      Sub-passes 2*it, 2*it+1 of all 8 warps complete z k-block 2h + it, so GEMM2 can start on k-block 2 while
+      //      k-block 3 is still being gated. ----
       const float* cpl = p.CP + (static_cast<size_t>(l) * p.tiles + cp_tile) * 2 * kCpChunk + r * 4;
-      for (int h = 0; h < 2 && ok; ++h) {
-        const float* cph = cpl + h * kCpChunk;
+      struct SubPass { int tg, tf, cpg, zkb, zchunk, zsig; };   // TMEM gate / filter column, CP gate column (filter + 128),
+                                                                 // z k-block, first 16-byte chunk, zf barrier to signal or -1
+      auto epi1_phase = [&](auto nsp_tag, int bar, const float* cph, auto geom, int trace0) -> bool {
+        constexpr int NSP = decltype(nsp_tag)::value;
         float4 cg[2][4], cf[2][4];
         auto cp_load = [&](int sp, float4* g4, float4* f4) {
-          const int gcol = (sp >> 1) * 64 + half * 32 + (sp & 1) * 16;
+          const int cpg = geom(sp).cpg;
 #pragma unroll
           for (int v4 = 0; v4 < 4; ++v4) {
-            g4[v4] = ld_stream_f4(cph + ((gcol >> 2) + v4) * (kTile * 4), cp_policy);
-            f4[v4] = ld_stream_f4(cph + (((128 + gcol) >> 2) + v4) * (kTile * 4), cp_policy);
+            g4[v4] = ld_stream_f4(cph + ((cpg >> 2) + v4) * (kTile * 4), cp_policy);
+            f4[v4] = ld_stream_f4(cph + (((128 + cpg) >> 2) + v4) * (kTile * 4), cp_policy);
           }
         };
         cp_load(0, cg[0], cf[0]);
-        if (tracer) DSX_TRACE(2, h * 4 + 0);
-        ok = wait_warp(&tfull[h], tf[h] & 1, 301);
-        if (!ok) break;
-        if (tracer) DSX_TRACE(2, h * 4 + 1);
-        tf[h]++;
+        if (tracer) DSX_TRACE(2, trace0);
+        if (!wait_warp(&tfull[bar], tf[bar] & 1, 301)) return false;
+        if (tracer) DSX_TRACE(2, trace0 + 1);
+        tf[bar]++;
         tc_fence_after();
 #pragma unroll
-        for (int sp = 0; sp < 4; ++sp) {
-          const int it = sp >> 1, sub = sp & 1;
-          const int gcol = it * 64 + half * 32 + sub * 16;    // first gate column of this warp in this sub-pass
-          if (sp < 3) cp_load(sp + 1, cg[(sp + 1) & 1], cf[(sp + 1) & 1]);
-          uint8_t* zrow = zaddr(0, 2 * h + it) + r * 128;
-          uint8_t* zrow_lo = zaddr(1, 2 * h + it) + r * 128;
+        for (int sp = 0; sp < NSP; ++sp) {
+          const SubPass sg = geom(sp);
+          if (sp + 1 < NSP) cp_load(sp + 1, cg[(sp + 1) & 1], cf[(sp + 1) & 1]);
+          uint8_t* zrow = zaddr(0, sg.zkb) + r * 128;
+          uint8_t* zrow_lo = zaddr(1, sg.zkb) + r * 128;
           uint32_t g[16], f[16];
-          tmem_ld_32x16(tmem_base + tlane + h * 256 + gcol, g);
-          tmem_ld_32x16(tmem_base + tlane + h * 256 + 128 + gcol, f);
+          tmem_ld_32x16(tmem_base + tlane + sg.tg, g);
+          tmem_ld_32x16(tmem_base + tlane + sg.tf, f);
           tmem_ld_wait();
 #pragma unroll
           for (int c8 = 0; c8 < 2; ++c8) {
@@ -588,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
                                    __uint_as_float(f[i + 2]) + bfv.z, __uint_as_float(f[i + 3]) + bfv.w};
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4)
-                z4[q4] = (P == 1) ? sigmoid_fast(vg[q4]) * tanh_approx(vf[q4]) : sigmoid_acc(vg[q4]) * tanh_acc(vf[q4]);
+                z4[q4] = (P == 1) ? sigmoid_fast(vg[q4]) * tanh_approx(vf[q4]) : gate_acc(vg[q4], vf[q4]);
               const __half2 h01 = __floats2half2_rn(z4[0], z4[1]), h23 = __floats2half2_rn(z4[2], z4[3]);
               hi[e] = h2_bits(h01);
               hi[e + 1] = h2_bits(h23);
@@ -598,27 +681,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
                 lo[e + 1] = h2_bits(__floats2half2_rn(z4[2] - f23.x, z4[3] - f23.y));
               }
             }
-            const int off = ((half * 4 + sub * 2 + c8) ^ (r & 7)) << 4;   // this warp's 32 channels = chunks 4*half .. +3
+            const int off = ((sg.zchunk + c8) ^ (r & 7)) << 4;
             *reinterpret_cast<uint4*>(zrow + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             if (Cfg::ALO_T) *reinterpret_cast<uint4*>(zrow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-          if (h == 1 && sub == 1) {
+          if (sg.zsig >= 0) {
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
-            release(&zf[it]);
+            release(&zf[sg.zsig]);
           }
         }
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (tracer) DSX_TRACE(2, h * 4 + 2);
-        release(&tempty[h]);
-      }
+        if (tracer) DSX_TRACE(2, trace0 + 2);
+        release(&tempty[bar]);
+        return true;
+      };
+      auto wide = [&](int h) {
+        return [=](int sp) {
+          const int it = sp >> 1, sub = sp & 1, c = it * 64 + half * 32 + sub * 16;
+          return SubPass{h * 256 + c, h * 256 + 128 + c, c, 2 * h + it, half * 4 + sub * 2, (h == 1 && sub == 1) ? it : -1};
+        };
+      };
+      ok = epi1_phase(std::integral_constant<int, 4>{}, 0, cpl, wide(0), 0);
+      if (ok) ok = epi1_phase(std::integral_constant<int, 4>{}, 1, cpl + kCpChunk, wide(1), 4);
+      if (!ok) break;
       // ---- epi2: each warp moves its 32 rows x 32 columns through a swizzled shared-memory tile so that every
-      //      global access instruction covers whole 128-byte row segments (2 rows x 32 columns of fp32).  All
-      //      addresses are one base pointer per thread plus compile-time offsets; the row-validity test is hoisted
-      //      (only the last tile of an utterance takes the predicated path). ----
+      //      global access instruction covers whole 128-byte row segments (4 rows x 32 columns of fp32, 16 bytes per
+      //      lane: the LSU instruction queue is what throttles this phase).  All addresses are one base pointer per
+      //      thread plus compile-time offsets; the row-validity test is hoisted (only the last tile of an utterance
+      //      takes the predicated path). ----
       auto epi2_half = [&](auto full_tag, int q) {
         constexpr bool FULL = decltype(full_tag)::value;
         float* const gp = ((q == 0) ? p.X : p.SKIP) + rbase;
@@ -626,22 +720,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         __half* const sp = s16 ? s16 + rbase : nullptr;
         const int mode = (q == 0) ? 0 : (skip_init ? 1 : (s16 ? 2 : 3));   // 0 residual, 1 store, 2 load+add (+s16), 3 red.add
         const bool do_load = (mode == 0 || mode == 2);
-        const float* dn = (q == 0 && dnext) ? dnext + static_cast<size_t>(tile_valid ? b : 0) * p.d_row_stride + half * 128 + lc2 * 2 : nullptr;
-        const float* bp = b2 + q * 256 + half * 128 + lc2 * 2;
+        const float* dn = (q == 0 && dnext) ? dnext + static_cast<size_t>(tile_valid ? b : 0) * p.d_row_stride + half * 128 + lc4 * 4 : nullptr;
+        const float* bp = b2 + q * 256 + half * 128 + lc4 * 4;
         // per-column vectors of the four 32-column groups: requested before the accumulator wait (these come
         // from L2: the proxy / gpu fences of the hand-over invalidate L1)
-        float2 biasv[4], dnvv[4];
+        float4 biasv[4], dnvv[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          biasv[jj] = __ldg(reinterpret_cast<const float2*>(bp + jj * 32));
-          dnvv[jj] = dn ? __ldg(reinterpret_cast<const float2*>(dn + jj * 32)) : make_float2(0.f, 0.f);
+          biasv[jj] = __ldg(reinterpret_cast<const float4*>(bp + jj * 32));
+          dnvv[jj] = dn ? __ldg(reinterpret_cast<const float4*>(dn + jj * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float2 pre[16];
+        float4 pre[8];
         auto prefetch = [&](int j) {
 #pragma unroll
-          for (int it = 0; it < 16; ++it) {
-            pre[it] = make_float2(0.f, 0.f);
-            if (do_load && (FULL || it * 2 + lrow < nrows)) pre[it] = *reinterpret_cast<const float2*>(gp + it * 2 * kC + j);
+          for (int it = 0; it < 8; ++it) {
+            pre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (do_load && (FULL || it * 4 + lrow < nrows)) pre[it] = *reinterpret_cast<const float4*>(gp + it * 4 * kC + j);
           }
         };
         prefetch(0);
@@ -662,49 +756,56 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
             *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
                 make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
           __syncwarp();
-          const float2 bias = biasv[jj], dnv = dnvv[jj];
-          float2 res[16];
+          const float4 bias = biasv[jj], dnv = dnvv[jj];
+          float4 res[8];
 #pragma unroll
-          for (int it = 0; it < 16; ++it) {
-            // row rr = 2*it + lrow; its 16-byte chunk (lc2 >> 1) sits at position chunk ^ (rr & 7)
-            const float2 d = *reinterpret_cast<const float2*>(stg_rd + it * 256 + ((((lc2 >> 1) ^ ((it * 2) & 7)) ^ lrow) << 4));
-            float2 v = pre[it];
+          for (int it = 0; it < 8; ++it) {
+            // row rr = 4*it + lrow; its 16-byte chunk lc4 sits at position lc4 ^ (rr & 7)
+            const float4 d = *reinterpret_cast<const float4*>(stg_rd + it * 512 + ((lc4 ^ ((it * 4 + lrow) & 7)) << 4));
+            float4 v = pre[it];
             if (mode == 0) {
               v.x = (v.x + (d.x + bias.x)) * 0.70710678118654752440f;
               v.y = (v.y + (d.y + bias.y)) * 0.70710678118654752440f;
+              v.z = (v.z + (d.z + bias.z)) * 0.70710678118654752440f;
+              v.w = (v.w + (d.w + bias.w)) * 0.70710678118654752440f;
             } else {
               v.x += d.x + bias.x;
               v.y += d.y + bias.y;
+              v.z += d.z + bias.z;
+              v.w += d.w + bias.w;
             }
             res[it] = v;
           }
           if (j + 32 < 128) prefetch(j + 32);                   // next group's loads fly while this one is stored
 #pragma unroll
-          for (int it = 0; it < 16; ++it) {
-            if (FULL || it * 2 + lrow < nrows) {
-              const float2 v = res[it];
-              float* g = gp + it * 2 * kC + j;
+          for (int it = 0; it < 8; ++it) {
+            if (FULL || it * 4 + lrow < nrows) {
+              const float4 v = res[it];
+              float* g = gp + it * 4 * kC + j;
               if (mode != 3) {
-                *reinterpret_cast<float2*>(g) = v;
+                *reinterpret_cast<float4*>(g) = v;
               } else {
-                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(g), "f"(v.x), "f"(v.y) : "memory");
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                             : "memory");
               }
               if (mode == 2) {
-                const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l;
-                const __half2 hh = __floats2half2_rn(sa, sb);
-                *reinterpret_cast<__half2*>(sp + it * 2 * kC + j) = hh;
+                const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l, sc = v.z * p.inv_sqrt_l, sd = v.w * p.inv_sqrt_l;
+                const __half2 h0 = __floats2half2_rn(sa, sb), h1 = __floats2half2_rn(sc, sd);
+                *reinterpret_cast<uint2*>(sp + it * 4 * kC + j) = make_uint2(h2_bits(h0), h2_bits(h1));
                 if (P >= 2) {
-                  const float2 hf = __half22float2(hh);
-                  *reinterpret_cast<__half2*>(sp + p.plane_elems + it * 2 * kC + j) = __floats2half2_rn(sa - hf.x, sb - hf.y);
+                  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                  *reinterpret_cast<uint2*>(sp + p.plane_elems + it * 4 * kC + j) =
+                      make_uint2(h2_bits(__floats2half2_rn(sa - f0.x, sb - f0.y)), h2_bits(__floats2half2_rn(sc - f1.x, sd - f1.y)));
                 }
               }
               if (dn) {
-                const float ya = v.x + dnv.x, yb = v.y + dnv.y;
-                const __half2 hh = __floats2half2_rn(ya, yb);
-                *reinterpret_cast<__half2*>(yp + it * 2 * kC + j) = hh;
+                const float ya = v.x + dnv.x, yb = v.y + dnv.y, yc = v.z + dnv.z, yd = v.w + dnv.w;
+                const __half2 h0 = __floats2half2_rn(ya, yb), h1 = __floats2half2_rn(yc, yd);
+                *reinterpret_cast<uint2*>(yp + it * 4 * kC + j) = make_uint2(h2_bits(h0), h2_bits(h1));
                 if (Cfg::ALO_T) {
-                  const float2 hf = __half22float2(hh);
-                  *reinterpret_cast<__half2*>(yp + p.plane_elems + it * 2 * kC + j) = __floats2half2_rn(ya - hf.x, yb - hf.y);
+                  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                  *reinterpret_cast<uint2*>(yp + p.plane_elems + it * 4 * kC + j) =
+                      make_uint2(h2_bits(__floats2half2_rn(ya - f0.x, yb - f0.y)), h2_bits(__floats2half2_rn(yc - f1.x, yd - f1.y)));
                 }
               }
             }
@@ -727,7 +828,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         }
         if (tracer && l - p.l0 < 10) DSX_TRACE(2, 100 + q * 10 + (l - p.l0));
       }
-      if (ok && multi && l + 1 < p.l1) {
+      if (!Cfg::SHIFT && ok && multi && l + 1 < p.l1) {           // P == 3: the staging units go back to the ring
         __syncwarp();
         if (lane == 0) mbar_arrive(edone);
       }
@@ -817,17 +918,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_condproj(const __grid_consta
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   Watchdog wd{p.status, globaltimer_ns() + p.budget_ns};
 
-  if (warp == 0 && lane == 0) {
-    // ---- TMA producer ----
-    mbar_arrive_expect_tx(afull, 8 * kUnitBytes);
-    for (int pl = 0; pl < 2; ++pl)
-      for (int kb = 0; kb < 4; ++kb) tma_load_3d<1>(&p.tm_cond[pl], afull, abuf + (pl * 4 + kb) * kUnitBytes, kb * 64, t0, b);
+  const int prod_id = (warp == 0) ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
+  if (prod_id >= 0 && lane == 0) {
+    // ---- TMA producers: thread 0 brings the conditioner tile, all three take the weight tiles round-robin ----
+    if (prod_id == 0) {
+      mbar_arrive_expect_tx(afull, 8 * kUnitBytes);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int kb = 0; kb < 4; ++kb) tma_load_3d<1>(&p.tm_cond[pl], afull, abuf + (pl * 4 + kb) * kUnitBytes, kb * 64, t0, b);
+    }
     uint32_t u = 0;
     bool ok = true;
     for (int j = j0; j < j1 && ok; ++j) {
       const int l = j >> 1, h = j & 1;
       for (int kb = 0; kb < 4 && ok; ++kb)
         for (int pl = 0; pl < 2 && ok; ++pl, ++u) {
+          if (u % 3 != static_cast<uint32_t>(prod_id)) continue;
           const int s = u % NS;
           ok = mbar_wait(&empty[s], ((u / NS) & 1) ^ 1, wd, 121);
           if (!ok) break;
@@ -1016,79 +1121,76 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   Watchdog wd{p.status, globaltimer_ns() + p.budget_ns};
 
-  if (warp == 0 && lane == 0) {
-    // ================================ TMA producer ================================
+  const int prod_id = (warp == 0) ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
+  if (prod_id >= 0 && lane == 0) {
+    // ================================ TMA producers ================================
+    // three threads take the units round-robin (one thread gets one load accepted per ~430 cycles: dsx_selftest(3))
+    constexpr uint32_t NP = 3;
     uint32_t u = 0;
     bool ok = true;
-    auto acquire = [&](int code) -> uint8_t* {
-      const int s = u % NU;
-      ok = mbar_wait(&empty[s], ((u / NU) & 1) ^ 1, wd, code);
+    // slot of unit `u` if it is this producer's (waited empty and armed), else nullptr; always advances u
+    auto acquire = [&](int code, uint64_t*& bar) -> uint8_t* {
+      const uint32_t uu = u++;
+      if (uu % NP != static_cast<uint32_t>(prod_id) || !ok) return nullptr;
+      const int s = uu % NU;
+      ok = mbar_wait(&empty[s], ((uu / NU) & 1) ^ 1, wd, code);
       if (!ok) return nullptr;
       mbar_arrive_expect_tx(&full[s], kUnitBytes);
+      bar = &full[s];
       return ring + s * kUnitBytes;
     };
-    auto load_a = [&](int plane, int kb) {
-      const int s = u % NU;
-      uint8_t* dst = acquire(111);
-      if (!dst) return;
-      tma_load_3d<1>(&p.tm_s16[plane], &full[s], dst, kb * 64, t0, b);
-      ++u;
-    };
     auto load_w = [&](int tileidx) {
-      const int s = u % NU;
-      uint8_t* dst = acquire(112);
-      if (!dst) return;
-      tma_load_2d<1>(&p.tm_wh, &full[s], dst, 0, tileidx * 128);
-      ++u;
+      uint64_t* bar = nullptr;
+      uint8_t* dst = acquire(112, bar);
+      if (dst) tma_load_2d<1>(&p.tm_wh, bar, dst, 0, tileidx * 128);
     };
     if (do_head) {
       // H1 streams through ring A = ring + h buffer (h is only written after H1's accumulator is complete)
       uint32_t ua = 0;
-      auto acquireA = [&]() -> uint8_t* {
-        const int s = ua % NA;
-        ok = mbar_wait(&emptyA[s], ((ua / NA) & 1) ^ 1, wd, 113);
+      auto acquireA = [&](uint64_t*& bar) -> uint8_t* {
+        const uint32_t uu = ua++;
+        if (uu % NP != static_cast<uint32_t>(prod_id) || !ok) return nullptr;
+        const int s = uu % NA;
+        ok = mbar_wait(&emptyA[s], ((uu / NA) & 1) ^ 1, wd, 113);
         if (!ok) return nullptr;
         mbar_arrive_expect_tx(&fullA[s], kUnitBytes);
+        bar = &fullA[s];
         return ring + s * kUnitBytes;
       };
       auto loadA_a = [&](int plane, int kb) {
-        const int s = ua % NA;
-        uint8_t* dst = acquireA();
-        if (!dst) return;
-        tma_load_3d<1>(&p.tm_s16[plane], &fullA[s], dst, kb * 64, t0, b);
-        ++ua;
+        uint64_t* bar = nullptr;
+        uint8_t* dst = acquireA(bar);
+        if (dst) tma_load_3d<1>(&p.tm_s16[plane], bar, dst, kb * 64, t0, b);
       };
       auto loadA_w = [&](int tileidx) {
-        const int s = ua % NA;
-        uint8_t* dst = acquireA();
-        if (!dst) return;
-        tma_load_2d<1>(&p.tm_wh, &fullA[s], dst, 0, tileidx * 128);
-        ++ua;
+        uint64_t* bar = nullptr;
+        uint8_t* dst = acquireA(bar);
+        if (dst) tma_load_2d<1>(&p.tm_wh, bar, dst, 0, tileidx * 128);
       };
       for (int kb = 0; kb < 4 && ok; ++kb) {
         loadA_a(0, kb);
-        if (ok) loadA_w((0 * 2 + 0) * 4 + kb);
-        if (ok) loadA_w((0 * 2 + 1) * 4 + kb);
+        loadA_w((0 * 2 + 0) * 4 + kb);
+        loadA_w((0 * 2 + 1) * 4 + kb);
         if (P == 3) {
-          if (ok) loadA_w((1 * 2 + 0) * 4 + kb);
-          if (ok) loadA_w((1 * 2 + 1) * 4 + kb);
-          if (ok) loadA_a(1, kb);
+          loadA_w((1 * 2 + 0) * 4 + kb);
+          loadA_w((1 * 2 + 1) * 4 + kb);
+          loadA_a(1, kb);
         }
       }
       // the H2 / I weights use the small ring, whose units alias ring A: wait for H1's MMAs
       if (ok) ok = mbar_wait(&tf[0], 0, wd, 114);
       for (int kb = 0; kb < 4 && ok; ++kb) {
         load_w(16 + 0 * 4 + kb);
-        if (P == 3 && ok) load_w(16 + 1 * 4 + kb);
+        if (P == 3) load_w(16 + 1 * 4 + kb);
       }
     }
     if (do_in) {
       for (int kb = 0; kb < 2 && ok; ++kb) {
         load_w(24 + (0 * 2 + 0) * 2 + kb);
-        if (ok) load_w(24 + (0 * 2 + 1) * 2 + kb);
+        load_w(24 + (0 * 2 + 1) * 2 + kb);
         if (P == 3) {
-          if (ok) load_w(24 + (1 * 2 + 0) * 2 + kb);
-          if (ok) load_w(24 + (1 * 2 + 1) * 2 + kb);
+          load_w(24 + (1 * 2 + 0) * 2 + kb);
+          load_w(24 + (1 * 2 + 1) * 2 + kb);
         }
       }
     }
@@ -1429,7 +1531,7 @@ __global__ void k_pack_wtc(const float* __restrict__ w1f, const float* __restric
     const int q = (u / 4) & 1, kb = u & 3;
     src = w2f + (static_cast<size_t>(l) * 2 * kC + q * 256 + n) * kC + kb * 64;
   }
-  __half* dst = wpack + ((static_cast<size_t>(l) * 80 + tileidx) * 256 + n) * 64;
+  __half* dst = wpack + (static_cast<size_t>(l) * kRowsPerLayer + static_cast<size_t>(tileidx) * 256 + n) * 64;
   for (int kk = 0; kk < 64; ++kk) {
     const float v = src[kk];
     const __half hi = __float2half_rn(v);
@@ -1447,7 +1549,7 @@ int tc_pack_model(dsx_handle* h, cudaStream_t s) {
   const size_t rows = static_cast<size_t>(h->m.L) * kRowsPerLayer;
   DSX_TRY(dev_alloc(h, reinterpret_cast<void**>(&wpack), rows * 64 * sizeof(__half), true));
   DSX_TRY(dev_alloc(h, reinterpret_cast<void**>(&b1p), static_cast<size_t>(h->m.L) * 512 * sizeof(float), true));
-  dim3 grid(80, h->m.L);
+  dim3 grid(kRowsPerLayer / 256, h->m.L);
   k_pack_wtc<<<grid, 256, 0, s>>>(h->m.w1f, h->m.w2f, h->m.b1f, wpack, b1p);
   h->launches++;
   DSX_CUDA(cudaGetLastError());
@@ -1603,8 +1705,6 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
   prm.tm_w = h->tm_w;
   for (int bf = 0; bf < 2; ++bf)
     for (int pl = 0; pl < 2; ++pl) prm.tm_y[bf][pl] = h->tm_y[bf][pl];
-  prm.tm_cond[0] = h->tm_cond[0];
-  prm.tm_cond[1] = h->tm_cond[1];
   prm.tm_yh[0] = h->tm_yh[0];
   prm.tm_yh[1] = h->tm_yh[1];
   prm.X = h->ws.X;
@@ -1612,6 +1712,7 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
   prm.Y = h->ws.Y;
   prm.plane_elems = g.frames_padded() * kC;
   prm.CP = h->ws.CP;
+  prm.cp_prefetch = h->cp_prefetch;
   prm.b2 = m.b2f;
   prm.dtab = h->ws.DTAB + static_cast<size_t>(row0) * m.L * kC;
   prm.d_row_stride = row_per_b * m.L * kC;

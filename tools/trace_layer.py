@@ -36,7 +36,7 @@ for cta in (0, 1):
     print("mma k-block start (GEMM1, chunk 0 then chunk 1, order cond|centre|halo):", [rel(v) for v in tr[cta, 1, 0:32]])
     print("mma k-block start (GEMM2):", [rel(v) for v in tr[cta, 1, 128:128 + 8 * U2:U2]])
     print("mma: before zfull wait, after zfull, tempty q0, q1:", [rel(v) for v in tr[cta, 1, 200:204]])
-    e = [rel(v) for v in tr[cta, 2, :13]]
+    e = [rel(v) for v in tr[cta, 2, :16]]
     print("epilogue: [c0 wait-start, wait-done, done] [c1 ...] res wait-start, wait-done, skip wait-start, wait-done, end:")
     print("  ", e[0:3], e[4:7], e[8:13])
     if cta == 0:
