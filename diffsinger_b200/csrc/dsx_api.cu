@@ -97,7 +97,7 @@ int check_status(dsx_handle* h, cudaStream_t s, const char* what) {
 static int run_layers(dsx_handle* h, const Geom& g, int row0, int row_per_b, int nl, cudaStream_t s) {
   const bool tc = h->precision != DSX_PREC_FP32_SIMT;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (h->profile) {
+  if (h->profile == 1) {
     while (h->prof_events.size() < h->prof_used + 2) {
       cudaEvent_t e;
       DSX_CUDA(cudaEventCreate(&e));
@@ -113,7 +113,7 @@ static int run_layers(dsx_handle* h, const Geom& g, int row0, int row_per_b, int
   } else {
     for (int l = 0; l < nl; ++l) DSX_TRY(launch_simt_layer(h, l, g, row0, row_per_b, s));
   }
-  if (h->profile) DSX_CUDA(cudaEventRecord(e1, s));
+  if (h->profile == 1) DSX_CUDA(cudaEventRecord(e1, s));
   return DSX_OK;
 }
 
@@ -182,7 +182,20 @@ static int sample_ddpm_impl(dsx_handle* h, float* x, const Geom& g, int t_start,
       // 20 fused residual-layer kernels, then ONE kernel: head GEMMs + p_sample update + next step's input projection
       DSX_TRY(run_layers(h, g, j, 0, h->m.L, s));
       const int flags = TC_HEAD | TC_UPDATE | (j + 1 < n_steps ? TC_INPROJ : 0);
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (h->profile == 2) {                       // DSX_OPT_PROFILE = 2: bracket the head kernel instead of the layer stack
+        while (h->prof_events.size() < h->prof_used + 2) {
+          cudaEvent_t e;
+          DSX_CUDA(cudaEventCreate(&e));
+          h->prof_events.push_back(e);
+        }
+        e0 = h->prof_events[h->prof_used];
+        e1 = h->prof_events[h->prof_used + 1];
+        h->prof_used += 2;
+        DSX_CUDA(cudaEventRecord(e0, s));
+      }
       DSX_TRY(launch_tc_head(h, g, flags, x, xs, nullptr, nz, seed, static_cast<uint64_t>(j), c, j + 1, 0, s));
+      if (e1) DSX_CUDA(cudaEventRecord(e1, s));
     } else {
       DSX_TRY(launch_ddpm_update(h, x, h->ws.EPS, nz, seed, static_cast<uint64_t>(j), c, mel, g.T, s));
     }
@@ -511,7 +524,7 @@ int dsx_set_option(dsx_handle* h, int what, int64_t value) {
     case DSX_OPT_CP_PREFETCH: h->cp_prefetch = static_cast<int>(value); break;
     case DSX_OPT_STACK_MODE: h->stack_mode = static_cast<int>(value); break;
     case DSX_OPT_PROFILE:
-      h->profile = value ? 1 : 0;
+      h->profile = static_cast<int>(value);
       h->prof_used = 0;
       break;
     default: set_error("unknown option %d", what); return DSX_E_INVALID;

@@ -130,6 +130,7 @@ struct dsx_handle {
   int cluster_occ = 0;              // max co-resident utterance clusters reported by the driver (last launch)
   int cp_prefetch = 1;              // tuning knob (DSX_OPT_CP_PREFETCH)
   int stack_mode = 1;               // 1: all residual layers of an evaluation in one cluster-per-utterance launch
+  int trace_seq = 0;                // debug: running index of traced launches
   long long* trace_dev = nullptr;   // debug timeline buffer (dsx_debug_trace)
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop), prof_used of them recorded
   size_t prof_used = 0;

@@ -115,6 +115,7 @@ struct TcLayerParams {
   int* status;
   unsigned long long budget_ns;
   long long* trace;          // debug: [2 CTAs][3 roles][256] clock64 stamps, or nullptr
+  int seq;                   // debug: launch sequence number (slot of the entry / exit wall-clock stamps)
 };
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   if (threadIdx.x == 0) {
     DSX_TRACE(0, 250);                                           // kernel entry (clock64)
     if (p.trace && blockIdx.x < 2) p.trace[(blockIdx.x * 3 + 1) * 256 + 250] = static_cast<long long>(globaltimer_ns());
+    if (p.trace && blockIdx.x == 0) p.trace[220 + (p.seq % 8) * 2] = static_cast<long long>(globaltimer_ns());
   }
   // tile -> (utterance, 128-frame tile in the utterance); the grid is padded to an even number of CTAs
   const int tile = p.tile0 + blockIdx.x;
@@ -849,6 +851,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
   if (threadIdx.x == 64) {
     DSX_TRACE(0, 251);                                           // after TMEM free (clock64)
     if (p.trace && blockIdx.x < 2) p.trace[(blockIdx.x * 3 + 1) * 256 + 251] = static_cast<long long>(globaltimer_ns());
+    if (p.trace && blockIdx.x == 0) p.trace[221 + (p.seq % 8) * 2] = static_cast<long long>(globaltimer_ns());
   }
 }
 
@@ -1053,6 +1056,7 @@ struct TcHeadParams {
   int* status;
   unsigned long long budget_ns;
   long long* trace;        // debug: CTA 0 writes clock64 stamps at [2*256 + 100 ...]
+  int seq;                 // debug: launch sequence number
 };
 
 #define DSX_HTRACE(slot)                                                        \
@@ -1095,6 +1099,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
   const int b = tile / p.tiles_per_utt;
   const int t0 = (tile % p.tiles_per_utt) * kTile;
   const bool do_head = p.flags & TC_HEAD, do_in = p.flags & TC_INPROJ;
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {        // wall-clock entry stamp (tools/trace_gaps.py)
+    p.trace[5 * 256 + 220 + (p.seq % 8) * 2] = static_cast<long long>(globaltimer_ns());
+    p.trace[2 * 256 + 98] = clock64();
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_wh);
@@ -1473,6 +1481,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    p.trace[5 * 256 + 221 + (p.seq % 8) * 2] = static_cast<long long>(globaltimer_ns());
+    p.trace[2 * 256 + 99] = clock64();
+  }
 }
 
 // whead tile order (128 rows x 64 k each): skip_projection [plane][row half][kb 0..3] (16 tiles),
@@ -1723,6 +1735,7 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
   prm.status = h->status_dev;
   prm.budget_ns = 4000000000ull;
   prm.trace = h->trace_dev;
+  prm.seq = h->trace_seq++;
   const int P = h->precision;   // DSX_PREC_FP16 = 1, FP16X2 = 2, FP16X3 = 3 == MMA passes
   auto launch = [&](int grid) -> int {
     return P == 1 ? launch_tc_layer_t<1>(h, prm, grid, kG, s)
@@ -1835,6 +1848,7 @@ int launch_tc_head(dsx_handle* h, const Geom& g, int flags, float* x_state, dsx_
   prm.status = h->status_dev;
   prm.budget_ns = 2000000000ull;
   prm.trace = h->trace_dev;
+  prm.seq = h->trace_seq++;
   return (h->precision == DSX_PREC_FP16) ? launch_tc_head_t<1>(h, prm, g.tiles, s) : launch_tc_head_t<3>(h, prm, g.tiles, s);
 }
 

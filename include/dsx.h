@@ -174,8 +174,8 @@ enum {
   DSX_OPT_TC_CTA_GROUP = 0, /* 2 (the layer kernel pairs CTAs; kept for forward compatibility) */
   DSX_OPT_CP_PREFETCH = 1,  /* tuning knob, results do not depend on it: 1 = the layer kernel's activation producer streams the
                                hoisted conditioner projection HBM -> L2 half a layer ahead of the gate epilogue */
-  DSX_OPT_PROFILE = 2,      /* 1: bracket the residual-layer kernel(s) of every evaluation with CUDA events; setting it
-                               resets the sums */
+  DSX_OPT_PROFILE = 2,      /* 1: bracket the residual-layer kernel(s) of every evaluation with CUDA events; 2: bracket the
+                               head / update kernel of every DDPM step instead; 0: off.  Setting it resets the sums */
   DSX_OPT_STACK_MODE = 3    /* 1 (default): all residual layers of an evaluation in ONE persistent launch whenever every
                                128-frame tile can own an SM at once (tiles <= co-resident CTAs); 0: one launch per layer */
 };

@@ -210,6 +210,24 @@ def test_stack_mode_matches_per_layer_launches(dsx, prec):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("prec", ["fp16x2", "fp16x3"])
+def test_tuning_knobs_do_not_change_results(dsx, prec):
+    """The L2 prefetch of the hoisted conditioner projection is a scheduling knob only: a DDPM loop is bit-identical with
+    it on or off."""
+    from diffsinger_b200 import _capi
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    s, dev = make_sampler(dsx, 4, prec, S)
+    B, T, K = 3, 333, 12
+    cond, xT = rs_normal(13, (B, 256, T)).to(dev), rs_normal(14, (B, 1, 80, T)).to(dev)
+    outs = []
+    for pre in (1, 0):
+        s.set_option(_capi.OPT_CP_PREFETCH, pre)
+        outs.append(s.sample_ddpm(xT, cond, 100, K, seed=5).cpu())
+    s.close()
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
+
+
 def test_shard_equivalence_and_determinism(dsx):
     """Utterances are independent: sampling B=4 equals sampling two halves, bit for bit (section 8e)."""
     S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
