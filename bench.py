@@ -29,6 +29,7 @@ import torch.distributed as dist
 HP = dict(hidden_size=256, residual_layers=20, residual_channels=256, dilation_cycle_length=1,
           audio_num_mel_bins=80, keep_bins=80)
 # algorithmic FLOPs per mel frame: whole DiffNet evaluation, conditioner projection hoisted
+_JSON_OUT = sys.stdout
 FLOP_PER_FRAME_EVAL = 21184512
 # one residual-layer kernel launch, per frame: 2*(3*256*512 + 256*512)  (dilated conv + output projection)
 FLOP_PER_FRAME_LAYER = 2 * (3 * 256 * 512 + 256 * 512)
@@ -180,7 +181,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def main():
@@ -199,6 +200,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
+
+    # stdout carries exactly ONE JSON line: everything libraries print there (NCCL's version banner, ...) goes to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -377,7 +384,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
             "extra": extra,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
