@@ -631,18 +631,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
       const float* cpl = p.CP + (static_cast<size_t>(l) * p.tiles + cp_tile) * 2 * kCpChunk + r * 4;
       struct SubPass { int tg, tf, cpg, zkb, zchunk, zsig; };   // TMEM gate / filter column, CP gate column (filter + 128),
                                                                  // z k-block, first 16-byte chunk, zf barrier to signal or -1
-      auto epi1_phase = [&](auto nsp_tag, int bar, const float* cph, auto geom, int trace0) -> bool {
-        constexpr int NSP = decltype(nsp_tag)::value;
-        float4 cg[2][4], cf[2][4];
-        auto cp_load = [&](int sp, float4* g4, float4* f4) {
-          const int cpg = geom(sp).cpg;
+      // CP double buffer in registers: sub-pass sp reads buffer sp & 1 while the loads of sub-pass sp + 1 fly -- also across
+      // the chunk boundary (the first loads of chunk 1 are issued during the last sub-pass of chunk 0)
+      float4 cg[2][4], cf[2][4];
+      auto cp_issue = [&](const float* cph, int cpg, float4* g4, float4* f4) {
 #pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            g4[v4] = ld_stream_f4(cph + ((cpg >> 2) + v4) * (kTile * 4), cp_policy);
-            f4[v4] = ld_stream_f4(cph + (((128 + cpg) >> 2) + v4) * (kTile * 4), cp_policy);
-          }
-        };
-        cp_load(0, cg[0], cf[0]);
+        for (int v4 = 0; v4 < 4; ++v4) {
+          g4[v4] = ld_stream_f4(cph + ((cpg >> 2) + v4) * (kTile * 4), cp_policy);
+          f4[v4] = ld_stream_f4(cph + (((128 + cpg) >> 2) + v4) * (kTile * 4), cp_policy);
+        }
+      };
+      auto epi1_phase = [&](int bar, const float* cph, auto geom, int trace0, bool preloaded, const float* next_cph,
+                            auto next_geom) -> bool {
+        constexpr int NSP = 4;
+        if (!preloaded) cp_issue(cph, geom(0).cpg, cg[0], cf[0]);
         if (tracer) DSX_TRACE(2, trace0);
         if (!wait_warp(&tfull[bar], tf[bar] & 1, 301)) return false;
         if (tracer) DSX_TRACE(2, trace0 + 1);
@@ -651,7 +653,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
 #pragma unroll
         for (int sp = 0; sp < NSP; ++sp) {
           const SubPass sg = geom(sp);
-          if (sp + 1 < NSP) cp_load(sp + 1, cg[(sp + 1) & 1], cf[(sp + 1) & 1]);
+          if (sp + 1 < NSP) cp_issue(cph, geom(sp + 1).cpg, cg[(sp + 1) & 1], cf[(sp + 1) & 1]);
+          else if (next_cph) cp_issue(next_cph, next_geom(0).cpg, cg[0], cf[0]);
           uint8_t* zrow = zaddr(0, sg.zkb) + r * 128;
           uint8_t* zrow_lo = zaddr(1, sg.zkb) + r * 128;
           uint32_t g[16], f[16];
@@ -707,8 +710,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
           return SubPass{h * 256 + c, h * 256 + 128 + c, c, 2 * h + it, half * 4 + sub * 2, (h == 1 && sub == 1) ? it : -1};
         };
       };
-      ok = epi1_phase(std::integral_constant<int, 4>{}, 0, cpl, wide(0), 0);
-      if (ok) ok = epi1_phase(std::integral_constant<int, 4>{}, 1, cpl + kCpChunk, wide(1), 4);
+      ok = epi1_phase(0, cpl, wide(0), 0, false, cpl + kCpChunk, wide(1));
+      if (ok) ok = epi1_phase(1, cpl + kCpChunk, wide(1), 4, true, nullptr, wide(1));
       if (!ok) break;
       // ---- epi2: each warp moves its 32 rows x 32 columns through a swizzled shared-memory tile so that every
       //      global access instruction covers whole 128-byte row segments (4 rows x 32 columns of fp32, 16 bytes per
