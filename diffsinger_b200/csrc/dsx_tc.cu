@@ -153,6 +153,30 @@ __device__ __forceinline__ bool flag_wait(const unsigned int* f, unsigned int ta
   }
 }
 
+// Wait until this tile's counter and its neighbours' (lo / hi may be null) have all reached `target`: the three polls
+// travel to L2 together (relaxed loads), one gpu-scope fence turns the successful observation into an acquire.
+__device__ __forceinline__ bool flag_wait3(const unsigned int* f, const unsigned int* lo, const unsigned int* hi,
+                                           unsigned int target, const Watchdog& wd, int code) {
+  uint32_t spins = 0;
+  while (true) {
+    unsigned int v0, v1 = target, v2 = target;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v0) : "l"(f) : "memory");
+    if (lo) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(lo) : "memory");
+    if (hi) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v2) : "l"(hi) : "memory");
+    if (static_cast<int>(v0 - target) >= 0 && static_cast<int>(v1 - target) >= 0 && static_cast<int>(v2 - target) >= 0) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      return true;
+    }
+    if (((++spins) & 0xff) == 0) {
+      if (*(volatile int*)wd.status != 0) return false;
+      if (globaltimer_ns() > wd.deadline_ns) {
+        atomicCAS(wd.status, 0, code);
+        return false;
+      }
+    }
+  }
+}
+
 #define DSX_TRACE(role, slot)                                                              \
   do {                                                                                     \
     if (p.trace && blockIdx.x < 2 && (slot) < 256)                                          \
@@ -282,9 +306,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
             if (li < 10) DSX_TRACE(0, 200 + li);
             if (ok && multi && tile_valid) {                        // y_l of this tile and its neighbours published
               const unsigned int target = p.flag_base + static_cast<unsigned int>(kEpiWarps * li);
-              ok = flag_wait(p.flags + tile, target, wd, 107);
-              if (ok && nb_lo) ok = flag_wait(p.flags + tile - 1, target, wd, 108);
-              if (ok && nb_hi) ok = flag_wait(p.flags + tile + 1, target, wd, 109);
+              ok = flag_wait3(p.flags + tile, nb_lo ? p.flags + tile - 1 : nullptr, nb_hi ? p.flags + tile + 1 : nullptr,
+                              target, wd, 107);
               fence_proxy_async_all();
             }
             if (li < 10) DSX_TRACE(0, 210 + li);

@@ -42,7 +42,7 @@ for name, B, T, (Ts, mb), K, interval, cycle in CFG:
         evals = (K // interval + (1 if K % interval else 0) + 1) if interval else K
         scale = (1000 / K) if "200 of 1000" in name else 1.0
         rec = {"config": name, "precision": prec, "ms_loop": ms * scale, "evals": int(evals * scale), "ms_per_eval": ms / evals,
-               "frames_per_s": B * T / (ms * scale * 1e-3), "stack_mode_active": bool(B * ((T + 127) // 128) <= 148)}
+               "frames_per_s": B * T / (ms * scale * 1e-3), "stack_launches_per_eval": -(-B // max(148 // ((T + 127) // 128), 1))}
         print(json.dumps(rec))
         out.append(rec)
         s.close()
