@@ -1,29 +1,32 @@
-// tcgen05 / TMEM / TMA path of the dsx sampler (sm_100a): one fused kernel per residual layer
-// (usr/diff/net.py:66-78):
+// tcgen05 / TMEM / TMA path of the dsx sampler (sm_100a).  Three kernels:
+//   k_tc_layer<P>   all residual layers of one DiffNet evaluation (usr/diff/net.py:58-78), persistent, one launch
+//   k_tc_head<P>    skip / output projections, the DDPM update and the next step's input projection (net.py:115-130,
+//                   shallow_diffusion_tts.py:134-166)
+//   k_tc_condproj   conditioner projection of every layer, once per call (it does not depend on the diffusion step)
 //
-//   CP     conditioner_projection(cond) + biases, all layers: step-independent, so computed ONCE per call by
-//          k_tc_condproj (hi/lo split on both operands) and kept in HBM as fp32 in the accumulator's layout
+// Per residual layer and 128-frame tile:
 //   GEMM1  D1[128 frames x 512] = [y(t-d) | y(t) | y(t+d)] (K = 768) . W1^T                  y = x + d_l
-//   epi1   z = sigmoid(D1[:, gate] + CP) * tanh(D1[:, filter] + CP)  -> fp16 (hi, lo) in shared memory
+//   epi1   z = sigmoid(D1[:, gate] + CP) * tanh(D1[:, filter] + CP)  -> fp16 (hi [, lo]) in shared memory
 //   GEMM2  D2[128 x 512] = z (K = 256) . W2^T
-//   epi2   x <- (x + D2[:, :256] + b) / sqrt2 ;  y_next = fp16 split of (x + d_{l+1}) ;  skip += D2[:, 256:] + b
+//   epi2   x <- (x + D2[:, :256] + b) / sqrt2 ;  y_next = fp16 (split) of (x + d_{l+1}) ;  skip += D2[:, 256:] + b
+// where CP = conditioner_projection_l(cond) + biases comes from HBM (fp32, accumulator layout, written by k_tc_condproj).
 //
 // Layout: activations are frames-major ([B][Tp][256], Tp = T rounded up to 128) so a 128-frame tile
 // of 64 channels is one TMA box that lands in shared memory as the canonical K-major SWIZZLE_128B
-// UMMA operand (rows of 128 B, 8-row atoms 1024 B apart).  The dilated taps are three boxes of the
-// same tensor at frame offsets -d, 0, +d; TMA zero-fills rows outside [0, T), which is exactly the
-// conv's zero padding applied after the FiLM add.  Weights are pre-packed into 256x64 fp16 tiles
-// (32 KB) in the order the K loop consumes them; the gate/filter rows of a 256-wide N chunk are
-// interleaved as [128 gate | 128 filter] so TMEM columns j and j+128 belong to the same channel.
+// UMMA operand (rows of 128 B, 8-row atoms 1024 B apart).  The dilated taps read the same tensor at
+// frame offsets -d, 0, +d; TMA zero-fills rows outside [0, T), which is exactly the conv's zero
+// padding applied after the FiLM add.  Weights are pre-packed into 256x64 fp16 tiles (32 KB) in the
+// order the K loop consumes them; the gate/filter rows of a 256-wide N chunk are interleaved as
+// [128 gate | 128 filter] so TMEM columns j and j+128 belong to the same channel.
 //
-// Precision: P = 1 uses fp16 operands (fp32 accumulate); P = 3 accumulates A_hi*W_hi + A_hi*W_lo +
-// A_lo*W_hi into the same TMEM tile (hi/lo fp16 split, ~2^-22 relative) -- the K loop is simply 3x
-// longer.
+// Precision: P = 1 fp16 operands (fp32 accumulate); P = 2 adds a W_lo pass (weights as hi+lo fp16 pairs);
+// P = 3 accumulates A_hi*W_hi + A_hi*W_lo + A_lo*W_hi into the same TMEM tile (~2^-22 relative).
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread; the leader CTA only when
-// cta_group::2), warp 2 = TMEM allocator, warps 4-7 = epilogue (thread = frame row = TMEM lane).
-// cta_group::2 (G = 2): a cluster of two CTAs, each with its own 128 frames (UMMA M = 256); every CTA
-// loads half of each weight tile, halving weight traffic from L2 and shared-memory operand reads.
+// Roles (384 threads): lane 0 of warps 0, 2, 3 = TMA producers (a thread gets one load accepted per ~430 cycles),
+// warp 1 = MMA issuer (one thread of the pair's leader CTA), warp 2 also allocates TMEM, warps 4-11 = epilogue
+// (thread = frame row = TMEM lane; two warps per lane quadrant split the columns).
+// cta_group::2: a cluster of two CTAs, each with its own 128 frames (UMMA M = 256); every CTA loads half of each
+// weight tile, halving weight traffic from L2 and shared-memory operand reads.
 #include <cuda.h>
 #include <stdio.h>
 #include <string.h>
