@@ -303,10 +303,9 @@ def main():
             pass
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         traffic = None
-        try:     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+        try:     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel, per launch
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_layer_traffic.json")))[args.precision]
-            traffic = {"bytes_per_launch": tj["dram_bytes_read"] + tj["dram_bytes_write"], "launch": "20 residual layers",
-                       "source": "profiles/r01_layer_traffic.json (ncu --set full)"}
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:
             pass
         ach = FLOP_PER_FRAME_LAYER * B * T / avg_s / 1e12
@@ -316,7 +315,11 @@ def main():
         roof = {"bound": "tensor", "kernel": "k_tc_layer (fused residual-layer stack, tcgen05; time per layer = stack time / 20)", "achieved": ach, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
-                "traffic": traffic, "avg_layer_us": avg_s * 1e6, "evaluations_profiled": n,
+                "traffic": traffic,
+                "traffic_note": "DRAM bytes per launch (= 20 residual layers) from profiles/r01_layer_traffic.json (ncu --set full); "
+                                "671 MB of it is the hoisted conditioner projection streamed once per evaluation",
+                "flops_per_launch": FLOP_PER_FRAME_LAYER * B * T * 20, "avg_launch_us": avg_s * 20e6,
+                "avg_layer_us": avg_s * 1e6, "evaluations_profiled": n,
                 "layer_kernels_share_of_step": ns * 1e-6 / ms_per_step,
                 "mma_passes": passes,
                 "executed_tflops": FLOP_PER_FRAME_LAYER * passes * B * T / avg_s / 1e12,
