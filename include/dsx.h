@@ -35,12 +35,14 @@ enum {
   DSX_E_NOMEM = -5
 };
 
-/* Arithmetic of the three contractions of each residual layer (usr/diff/net.py:66-78). */
+/* Arithmetic of the contractions of each residual layer (usr/diff/net.py:66-78).  In the tcgen05 modes the conditioner
+ * projection -- it does not depend on the diffusion step -- is computed once per call with hi+lo operands and kept in
+ * fp32; the modes differ in the dilated conv and the output projection. */
 enum {
   DSX_PREC_FP32_SIMT = 0, /* fp32 CUDA-core path, any channel count                          */
   DSX_PREC_FP16 = 1,      /* tcgen05 kind::f16, fp16 operands, fp32 accumulate (fast mode)   */
-  DSX_PREC_FP16X2 = 2,    /* tcgen05, weights and conditioner hi+lo, running activations fp16: 2 MMA passes (3 on
-                             the conditioner k-blocks); max |d| ~2e-4 after 100 steps (default parity mode)       */
+  DSX_PREC_FP16X2 = 2,    /* tcgen05, weights as hi+lo fp16 pairs, running activations fp16: 2 MMA passes;
+                             max |d| ~2e-4 after 100 steps (default parity mode)                               */
   DSX_PREC_FP16X3 = 3     /* tcgen05, hi+lo fp16 split of both operands, 3 MMAs (fp32-equivalent)*/
 };
 
@@ -194,6 +196,8 @@ int dsx_debug_set_layer_limit(dsx_handle* h, int n_layers);
 /* Hardware self-tests of the tcgen05 / TMA encodings this library relies on (one small
  * launch each, results checked on the host).  which = -1 runs all; returns 0 when every
  * selected test passes, otherwise DSX_E_KERNEL with the failing names in dsx_last_error().
+ * which = 0 / 1: UMMA + TMA round trip with cta_group::1 / ::2; informational experiments (not part of -1):
+ * 2 = row-shifted SWIZZLE_128B operand descriptors, 3 = TMA ingest rate of one SM versus issuing threads / box size.
  * report (may be NULL): host buffer receiving a text report. */
 int dsx_selftest(int device, int which, char* report, int report_bytes);
 

@@ -25,6 +25,18 @@ def test_library_exports_every_declared_symbol(lib_built):
     assert _capi.lib.dsx_version() == 100
 
 
+def test_header_enums_match_the_ctypes_constants(lib_built):
+    """Precision / info / option codes of include/dsx.h and diffsinger_b200/_capi.py must agree."""
+    from diffsinger_b200 import _capi
+    header = open(os.path.join(ROOT, "include", "dsx.h")).read()
+    enums = {k: int(v) for k, v in re.findall(r"\b(DSX_[A-Z0-9_]+)\s*=\s*(-?\d+)", header)}
+    for name, value in enums.items():
+        for prefix in ("PREC_", "INFO_", "OPT_"):
+            if name.startswith("DSX_" + prefix):
+                assert getattr(_capi, name[4:]) == value, name
+    assert {v for k, v in enums.items() if k.startswith("DSX_PREC_")} == set(_capi.PRECISIONS.values())
+
+
 def test_no_cpu_fallback_is_loud(lib_built):
     import diffsinger_b200 as dsx
     torch.manual_seed(0)
