@@ -6,12 +6,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DSX_LIB", os.path.join(_HERE, "lib", "libdsx.so"))
 
-PREC_FP32_SIMT, PREC_FP16, PREC_FP16X2, PREC_FP16X3 = 0, 1, 2, 3
+PREC_FP32_SIMT, PREC_FP16, PREC_FP16X2, PREC_FP16X3, PREC_FP16S = 0, 1, 2, 3, 4
 PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "fp16": PREC_FP16, "fp16x2": PREC_FP16X2,
-              "fp16x3": PREC_FP16X3}
+              "fp16x3": PREC_FP16X3, "fp16s": PREC_FP16S}
 (INFO_PRECISION, INFO_KERNEL_LAUNCHES, INFO_WORKSPACE_BYTES, INFO_SM_COUNT, INFO_TC_CTA_GROUP, INFO_LAYER_KERNEL_NS,
- INFO_LAYER_KERNEL_LAUNCHES, INFO_STACK_MODE, INFO_CLUSTER_OCCUPANCY) = range(9)
-OPT_TC_CTA_GROUP, OPT_CP_PREFETCH, OPT_PROFILE, OPT_STACK_MODE = 0, 1, 2, 3
+ INFO_LAYER_KERNEL_LAUNCHES, INFO_STACK_MODE, INFO_CLUSTER_OCCUPANCY, INFO_STACK_KERNEL_LAUNCHES) = range(10)
+OPT_TC_CTA_GROUP, OPT_CP_PREFETCH, OPT_PROFILE, OPT_STACK_MODE, OPT_STACK_KERNEL, OPT_SR_SETS, OPT_BATCH_OFFSET = 0, 1, 2, 3, 4, 5, 6
 SCHEDULE_BUFFERS = (
     "betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
     "sqrt_one_minus_alphas_cumprod", "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
@@ -22,7 +22,7 @@ SCHEDULE_BUFFERS = (
 SYMBOLS = (
     "dsx_version", "dsx_last_error", "dsx_create", "dsx_destroy", "dsx_load_diffnet", "dsx_set_schedule",
     "dsx_diffnet_forward", "dsx_sample_ddpm", "dsx_sample_plms", "dsx_infer", "dsx_infer_host", "dsx_get_info",
-    "dsx_set_option", "dsx_debug_read", "dsx_debug_trace", "dsx_debug_set_layer_limit", "dsx_selftest",
+    "dsx_set_option", "dsx_set_cond", "dsx_plms_update", "dsx_debug_read", "dsx_debug_trace", "dsx_debug_set_layer_limit", "dsx_selftest",
 )
 
 
@@ -64,6 +64,8 @@ lib.dsx_sample_ddpm.argtypes = [_vp, _vp, _vp, Strides, _i, _i, _i, _i, _vp, _u6
 lib.dsx_sample_plms.argtypes = [_vp, _vp, _vp, Strides, _i, _i, _i, _i, _vp]
 lib.dsx_infer.argtypes = [_vp, _vp, Strides, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]
 lib.dsx_infer_host.argtypes = [_vp, _vp, Strides, _vp, _vp, _u64, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]
+lib.dsx_set_cond.argtypes = [_vp, _vp, Strides, _i, _i, _vp]
+lib.dsx_plms_update.argtypes = [_vp, _vp, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _vp]
 lib.dsx_get_info.argtypes = [_vp, _i, ctypes.POINTER(_i64)]
 lib.dsx_set_option.argtypes = [_vp, _i, _i64]
 lib.dsx_debug_read.argtypes = [_vp, _i, _vp, _i, _i, _vp]

@@ -41,44 +41,60 @@ static void free_ws(Workspace& w) {
   w = Workspace();
 }
 
-int ensure_workspace(dsx_handle* h, const Geom& g, int rows) {
+// Grow-only workspace: every buffer keeps its byte capacity; a call with a new (B, T) that fits re-uses the allocations
+// (only the tensor maps are re-encoded, see tc_prepare_maps), so utterance lengths that change from call to call cost no
+// cudaFree / cudaMalloc (cudaFree synchronises the device).  New allocations are zeroed on the caller's stream.
+int ensure_workspace(dsx_handle* h, const Geom& g, int rows, cudaStream_t s) {
   Workspace& w = h->ws;
   const ModelDev& m = h->m;
   const bool tc = h->precision != DSX_PREC_FP32_SIMT;
-  const bool have_tc = w.Y != nullptr, have_simt = w.CONDF != nullptr;
-  if (w.X && w.g.B == g.B && w.g.T == g.T && w.rows_cap >= rows && (tc ? have_tc : have_simt)) return DSX_OK;
-  const int keep_rows = std::max(rows, w.rows_cap);
-  free_ws(w);
   const size_t nf = g.frames_padded();
-  size_t total = 0;
-  auto A = [&](void** p, size_t bytes) -> int {
-    total += bytes;
-    DSX_TRY(dev_alloc(h, p, bytes, false));
-    DSX_CUDA(cudaMemset(*p, 0, bytes));
+  bool moved = false;
+  auto need = [&](void** p, size_t& cap, size_t bytes) -> int {
+    if (cap >= bytes && *p) return DSX_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    w.bytes -= cap;
+    cap = 0;
+    const size_t grow = bytes + bytes / 8;      // headroom: slightly longer utterances next time do not reallocate
+    DSX_TRY(dev_alloc(h, p, grow, false));
+    DSX_CUDA(cudaMemsetAsync(*p, 0, grow, s));
+    cap = grow;
+    w.bytes += grow;
+    moved = true;
     return DSX_OK;
   };
-  DSX_TRY(A(reinterpret_cast<void**>(&w.X), nf * m.C * 4));
-  DSX_TRY(A(reinterpret_cast<void**>(&w.SKIP), nf * m.C * 4));
-  DSX_TRY(A(reinterpret_cast<void**>(&w.G1), nf * 2 * m.C * 4));
-  DSX_TRY(A(reinterpret_cast<void**>(&w.Zf), nf * m.C * 4));
+#define NEED(field, bytes) DSX_TRY(need(reinterpret_cast<void**>(&w.field), w.cap_##field, (bytes)))
+  NEED(X, nf * m.C * 4);
+  NEED(SKIP, nf * m.C * 4);
   if (tc) {
-    DSX_TRY(A(reinterpret_cast<void**>(&w.Y), nf * m.C * 2 * 4));
-    DSX_TRY(A(reinterpret_cast<void**>(&w.CONDH), nf * m.H * 2 * 2));
-    DSX_TRY(A(reinterpret_cast<void**>(&w.S16), nf * m.C * 2 * 2));
-    DSX_TRY(A(reinterpret_cast<void**>(&w.CP), static_cast<size_t>(m.L) * g.tiles * 2 * 256 * kTile * 4));
+    const void* cond_before[2] = {w.CONDH, w.CP};
+    NEED(Y, nf * m.C * 2 * 4);
+    NEED(CONDH, nf * m.H * 2 * 2);
+    NEED(S16, nf * m.C * 2 * 2);
+    NEED(CP, static_cast<size_t>(m.L) * g.tiles * 2 * 256 * kTile * 4);
+    if (cond_before[0] != w.CONDH || cond_before[1] != w.CP) h->cond_ready = false;
   } else {
-    DSX_TRY(A(reinterpret_cast<void**>(&w.CONDF), nf * m.H * 4));
+    const void* cond_before = w.CONDF;
+    NEED(G1, nf * 2 * m.C * 4);
+    NEED(Zf, nf * m.C * 4);
+    NEED(CONDF, nf * m.H * 4);
+    if (cond_before != w.CONDF) h->cond_ready = false;
   }
-  DSX_TRY(A(reinterpret_cast<void**>(&w.DTAB), static_cast<size_t>(keep_rows) * m.L * m.C * 4));
-  DSX_TRY(A(reinterpret_cast<void**>(&w.EMB), static_cast<size_t>(keep_rows) * m.C * 4));
-  DSX_TRY(A(reinterpret_cast<void**>(&w.TVALS), static_cast<size_t>(keep_rows) * 8));
+  if (w.rows_cap < rows) {
+    const int keep_rows = std::max(rows, w.rows_cap + w.rows_cap / 2);
+    NEED(DTAB, static_cast<size_t>(keep_rows) * m.L * m.C * 4);
+    NEED(EMB, static_cast<size_t>(keep_rows) * m.C * 4);
+    NEED(TVALS, static_cast<size_t>(keep_rows) * 8);
+    w.rows_cap = keep_rows;
+  }
   const size_t mel = static_cast<size_t>(g.B) * m.M * g.T;
-  DSX_TRY(A(reinterpret_cast<void**>(&w.EPS), 5 * mel * 4));
-  DSX_TRY(A(reinterpret_cast<void**>(&w.XTMP), mel * 4));
-  DSX_TRY(A(reinterpret_cast<void**>(&w.XSTATE), mel * 4));
+  NEED(EPS, 5 * mel * 4);
+  NEED(XTMP, mel * 4);
+  NEED(XSTATE, mel * 4);
+#undef NEED
+  if (moved) h->ws_epoch++;
   w.g = g;
-  w.rows_cap = keep_rows;
-  w.bytes = total;
   return DSX_OK;
 }
 
@@ -88,10 +104,21 @@ int check_status(dsx_handle* h, cudaStream_t s, const char* what) {
   if (*h->status_host != 0) {
     int code = *h->status_host;
     cudaMemsetAsync(h->status_dev, 0, sizeof(int), s);
+    // the tiles of the aborted launch stopped at different layers: their publish counters are no longer in lockstep.
+    // Zero them and forget the geometry so the next stack launch starts from a clean state (the handle stays usable).
+    reset_flags(h);
     set_error("%s: in-kernel watchdog tripped (code %d: 1xx producer, 2xx MMA issuer, 3xx epilogue wait)", what, code);
     return DSX_E_KERNEL;
   }
   return DSX_OK;
+}
+
+void reset_flags(dsx_handle* h) {
+  if (h->flags_dev) cudaMemset(h->flags_dev, 0, static_cast<size_t>(h->flags_cap) * sizeof(unsigned int));
+  h->flag_count = 0;
+  h->flags_geom_b = 0;
+  h->flags_geom_t = 0;
+  h->flags_kind = 0;
 }
 
 static int run_layers(dsx_handle* h, const Geom& g, int row0, int row_per_b, int nl, cudaStream_t s) {
@@ -109,7 +136,9 @@ static int run_layers(dsx_handle* h, const Geom& g, int row0, int row_per_b, int
     DSX_CUDA(cudaEventRecord(e0, s));
   }
   if (tc) {
-    DSX_TRY(launch_tc_layers(h, 0, nl, g, row0, row_per_b, s));
+    // weight set of DSX_PREC_FP16S: evaluation (= table row) j of a loop uses set j % R
+    if (tc_stack_usable(h, g)) DSX_TRY(launch_tc_stack(h, nl, g, row0, row_per_b, row0, s));
+    else DSX_TRY(launch_tc_layers(h, 0, nl, g, row0, row_per_b, s));
   } else {
     for (int l = 0; l < nl; ++l) DSX_TRY(launch_simt_layer(h, l, g, row0, row_per_b, s));
   }
@@ -137,15 +166,28 @@ static int run_eval(dsx_handle* h, const float* x, dsx_strides xs, const Geom& g
   return DSX_OK;
 }
 
+// Workspace + tensor maps for (B, T) and, when `cond` is given, the conditioner pack and its hoisted projection (the
+// step-independent part of every residual layer).  cond == NULL re-uses what the last call with a conditioner left behind
+// (dsx_set_cond or any entry point): callers that drive the sampling loop themselves, one p_sample / DiffNet.forward per
+// call, pay the pack + projection once per utterance batch instead of once per step.
 static int prepare(dsx_handle* h, const float* cond, dsx_strides cs, int B, int T, int rows, Geom& g, cudaStream_t s) {
   DSX_CHECK(h && h->loaded, DSX_E_STATE, "dsx_load_diffnet has not been called");
   DSX_CHECK(B > 0 && T > 0, DSX_E_INVALID, "B and T must be positive (got %d, %d)", B, T);
   DSX_CUDA(cudaSetDevice(h->device));
   g.set(B, T);
-  DSX_TRY(ensure_workspace(h, g, rows));
+  DSX_TRY(ensure_workspace(h, g, rows, s));
   if (h->precision != DSX_PREC_FP32_SIMT) DSX_TRY(tc_prepare_maps(h, g));
+  if (!cond) {
+    DSX_CHECK(h->cond_ready && h->cond_geom.B == B && h->cond_geom.T == T, DSX_E_STATE,
+              "cond == NULL needs a conditioner set for the same (B, T) by dsx_set_cond or an earlier call (have %s %dx%d, asked %dx%d)",
+              h->cond_ready ? "one for" : "none;", h->cond_geom.B, h->cond_geom.T, B, T);
+    return DSX_OK;
+  }
+  h->cond_ready = false;
   DSX_TRY(launch_pack_cond(h, cond, cs, g, s));
   if (h->precision != DSX_PREC_FP32_SIMT) DSX_TRY(launch_tc_condproj(h, g, s));
+  h->cond_ready = true;
+  h->cond_geom = g;
   return DSX_OK;
 }
 
@@ -335,12 +377,14 @@ int dsx_load_diffnet(dsx_handle* h, const dsx_diffnet_params* p, int M, int C, i
   DSX_CHECK(M > 0 && C > 0 && H > 0 && L > 0 && dilation_cycle > 0, DSX_E_INVALID, "bad model dimensions");
   DSX_CHECK(C % 16 == 0 && H % 16 == 0 && M % 16 == 0, DSX_E_INVALID, "M, C, H must be multiples of 16 (got %d %d %d)", M, C, H);
   DSX_CHECK(precision == DSX_PREC_FP32_SIMT || precision == DSX_PREC_FP16 || precision == DSX_PREC_FP16X2 ||
-                precision == DSX_PREC_FP16X3,
+                precision == DSX_PREC_FP16X3 || precision == DSX_PREC_FP16S,
             DSX_E_INVALID, "unknown precision %d", precision);
   DSX_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   free_model(h);
   free_ws(h->ws);
+  h->ws_epoch++;
+  h->cond_ready = false;
   h->tm_geom = Geom();
   memset(&h->m, 0, sizeof(h->m));
   h->m.M = M; h->m.C = C; h->m.H = H; h->m.L = L; h->m.cycle = dilation_cycle;
@@ -371,7 +415,7 @@ int dsx_set_schedule(dsx_handle* h, const float* const* bufs, int T) {
 int dsx_diffnet_forward(dsx_handle* h, const float* x, dsx_strides xs, const int64_t* t, const float* cond,
                         dsx_strides cs, float* eps, int B, int T, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  DSX_CHECK(x && t && cond && eps, DSX_E_INVALID, "null tensor pointer");
+  DSX_CHECK(x && t && eps, DSX_E_INVALID, "null tensor pointer");
   Geom g;
   DSX_TRY(prepare(h, cond, cs, B, T, B, g, s));
   DSX_TRY(launch_embed_table(h, t, B, s));
@@ -379,10 +423,43 @@ int dsx_diffnet_forward(dsx_handle* h, const float* x, dsx_strides xs, const int
   return check_status(h, s, "dsx_diffnet_forward");
 }
 
+int dsx_set_cond(dsx_handle* h, const float* cond, dsx_strides cs, int B, int T, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DSX_CHECK(cond, DSX_E_INVALID, "null tensor pointer");
+  Geom g;
+  DSX_TRY(prepare(h, cond, cs, B, T, 1, g, s));
+  return check_status(h, s, "dsx_set_cond");
+}
+
+int dsx_plms_update(dsx_handle* h, float* x_out, const float* x_in, const float* const* eps, int mode, int t, int interval,
+                    int B, int T, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DSX_CHECK(h && h->loaded, DSX_E_STATE, "dsx_load_diffnet has not been called");
+  DSX_CHECK(h->sched_T > 0, DSX_E_STATE, "dsx_set_schedule has not been called");
+  DSX_CHECK(x_out && x_in && eps && eps[0], DSX_E_INVALID, "null tensor pointer");
+  DSX_CHECK(mode >= 0 && mode <= 4 && interval > 0 && t >= 0 && t < h->sched_T && B > 0 && T > 0, DSX_E_INVALID,
+            "bad dsx_plms_update arguments (mode %d, t %d, interval %d)", mode, t, interval);
+  static const int n_eps[5] = {1, 2, 2, 3, 4};
+  for (int i = 0; i < n_eps[mode]; ++i) DSX_CHECK(eps[i], DSX_E_INVALID, "mode %d needs %d eps tensors", mode, n_eps[mode]);
+  DSX_CUDA(cudaSetDevice(h->device));
+  PlmsCoef c{};
+  plms_coefs(h, t, interval, c);
+  switch (mode) {
+    case 0: c.w0 = 1.f; c.denom = 1.f; break;
+    case 1: c.w0 = 1.f; c.w1 = 1.f; c.denom = 2.f; break;
+    case 2: c.w0 = 3.f; c.w1 = -1.f; c.denom = 2.f; break;
+    case 3: c.w0 = 23.f; c.w1 = -16.f; c.w2 = 5.f; c.denom = 12.f; break;
+    default: c.w0 = 55.f; c.w1 = -59.f; c.w2 = 37.f; c.w3 = -9.f; c.denom = 24.f; break;
+  }
+  const size_t mel = static_cast<size_t>(B) * h->m.M * T;
+  return launch_plms_update(h, x_out, x_in, eps[0], n_eps[mode] > 1 ? eps[1] : nullptr, n_eps[mode] > 2 ? eps[2] : nullptr,
+                            n_eps[mode] > 3 ? eps[3] : nullptr, c, mel, s);
+}
+
 int dsx_sample_ddpm(dsx_handle* h, float* x_inout, const float* cond, dsx_strides cs, int B, int T, int t_start,
                     int n_steps, const float* noise, uint64_t seed, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  DSX_CHECK(x_inout && cond, DSX_E_INVALID, "null tensor pointer");
+  DSX_CHECK(x_inout, DSX_E_INVALID, "null tensor pointer");
   DSX_CHECK(h && h->sched_T > 0, DSX_E_STATE, "dsx_set_schedule has not been called");
   DSX_CHECK(n_steps > 0 && t_start <= h->sched_T && t_start - n_steps >= 0, DSX_E_INVALID,
             "steps t_start=%d n_steps=%d outside schedule of %d", t_start, n_steps, h->sched_T);
@@ -395,7 +472,7 @@ int dsx_sample_ddpm(dsx_handle* h, float* x_inout, const float* cond, dsx_stride
 int dsx_sample_plms(dsx_handle* h, float* x_inout, const float* cond, dsx_strides cs, int B, int T, int t_start,
                     int interval, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  DSX_CHECK(x_inout && cond, DSX_E_INVALID, "null tensor pointer");
+  DSX_CHECK(x_inout, DSX_E_INVALID, "null tensor pointer");
   DSX_CHECK(h && h->sched_T > 0, DSX_E_STATE, "dsx_set_schedule has not been called");
   DSX_CHECK(interval > 0 && t_start > 0 && t_start <= h->sched_T, DSX_E_INVALID, "bad PLMS arguments");
   Geom g;
@@ -497,6 +574,7 @@ int dsx_get_info(dsx_handle* h, int what, int64_t* out) {
     case DSX_INFO_LAYER_KERNEL_LAUNCHES: *out = static_cast<int64_t>(h->prof_used / 2); break;
     case DSX_INFO_STACK_MODE: *out = h->stack_mode; break;
     case DSX_INFO_CLUSTER_OCCUPANCY: *out = h->cluster_occ; break;
+    case DSX_INFO_STACK_KERNEL_LAUNCHES: *out = h->stack_launches; break;
     case DSX_INFO_LAYER_KERNEL_NS: {
       double total_ms = 0;
       for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
@@ -523,6 +601,15 @@ int dsx_set_option(dsx_handle* h, int what, int64_t value) {
       break;
     case DSX_OPT_CP_PREFETCH: h->cp_prefetch = static_cast<int>(value); break;
     case DSX_OPT_STACK_MODE: h->stack_mode = static_cast<int>(value); break;
+    case DSX_OPT_STACK_KERNEL: h->stack_kernel = static_cast<int>(value); break;
+    case DSX_OPT_BATCH_OFFSET:
+      DSX_CHECK(value >= 0 && value < (1ll << 30), DSX_E_INVALID, "DSX_OPT_BATCH_OFFSET out of range");
+      h->batch_offset = static_cast<int>(value);
+      break;
+    case DSX_OPT_SR_SETS:
+      DSX_CHECK(value >= 1 && value <= 1024, DSX_E_INVALID, "DSX_OPT_SR_SETS must be in [1, 1024]");
+      h->sr_sets = static_cast<int>(value);
+      break;
     case DSX_OPT_PROFILE:
       h->profile = static_cast<int>(value);
       h->prof_used = 0;

@@ -35,6 +35,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 constexpr int kTile = 128;  // frames per tile (= UMMA M per CTA)
+constexpr int kStackSetRowsPerLayer = 32 * 256;   // rows (of 64 fp16) per layer of one stochastically rounded weight set
 
 // Geometry of one call: B utterances of T frames, stored frames-major with the frame axis
 // padded to a multiple of the tile so tiles never straddle utterances.
@@ -74,6 +75,9 @@ struct ModelDev {
   const __half* wpack; // [L][20480 rows][64]
   const float* b1p;    // [L][2 chunks][256]  gate(128) | filter(128) per chunk
   const __half* whead; // [32 tiles][128 rows][64]: skip_projection, output_projection, input_projection packs
+  const float* bskip;  // [L][256] prefix sums over layers of the skip-half biases of output_projection (stack kernel)
+  const __half* wsr;   // [R][L][8192 rows][64] stochastically rounded weight sets (DSX_PREC_FP16S), or nullptr
+  int wsr_sets;        // R
 };
 
 struct Workspace {
@@ -95,6 +99,9 @@ struct Workspace {
   float* XTMP = nullptr;    // [B][M][T] PLMS warm-up state
   float* XSTATE = nullptr;  // [B][M][T] mel state of dsx_infer
   size_t bytes = 0;
+  // byte capacities (grow-only)
+  size_t cap_X = 0, cap_SKIP = 0, cap_CONDF = 0, cap_G1 = 0, cap_Zf = 0, cap_Y = 0, cap_CONDH = 0, cap_CP = 0, cap_S16 = 0,
+         cap_DTAB = 0, cap_EMB = 0, cap_TVALS = 0, cap_EPS = 0, cap_XTMP = 0, cap_XSTATE = 0;
 };
 
 }  // namespace dsx
@@ -108,6 +115,7 @@ struct dsx_handle {
   int use_graph = 0;
   int layer_limit = -1;
   int64_t launches = 0;
+  int64_t stack_launches = 0;   // launches of k_tc_stack (dsx_stack.cu)
   dsx::ModelDev m{};
   std::vector<void*> owned;   // device allocations of the model
   int sched_T = 0;
@@ -115,7 +123,7 @@ struct dsx_handle {
   dsx::Workspace ws;
   int* status_dev = nullptr;   // kernel watchdog / self-check word
   int* status_host = nullptr;  // pinned mirror
-  CUtensorMap tm_w{}, tm_y[2][2]{}, tm_yh[2]{}, tm_cond[2]{}, tm_s16[2]{}, tm_whead{};
+  CUtensorMap tm_w{}, tm_y[2][2]{}, tm_yh[2]{}, tm_ye[2]{}, tm_cond[2]{}, tm_s16[2]{}, tm_whead{}, tm_wsr{};
   dsx::Geom tm_geom;           // geometry the activation maps were built for
   int tm_group = 0;
   int profile = 0;
@@ -125,6 +133,17 @@ struct dsx_handle {
   int flags_cap = 0;
   int flags_geom_b = 0, flags_geom_t = 0;   // geometry of the last stack launch
   unsigned int flag_count = 0;         // value of every counter before the next stack launch
+  int flags_kind = 0;                  // which kernel's counting convention the counters follow (1: k_tc_layer, 2: k_tc_stack)
+  int stack_kernel = 1;                // DSX_OPT_STACK_KERNEL: 1 = register-resident stack kernel (dsx_stack.cu) where it applies
+  int stack_occ[2] = {0, 0};           // co-resident CTA pairs of k_tc_stack<1>, <2> (0 unknown, -1 none)
+  bool attr_stack[2] = {false, false};
+  int sr_sets = 64;                    // DSX_OPT_SR_SETS: weight sets of DSX_PREC_FP16S (takes effect at the next dsx_load_diffnet)
+  unsigned long long sr_seed = 0x5DEECE66Dull;
+  unsigned long long ws_epoch = 0;     // bumped whenever a workspace buffer moves (tensor maps are rebuilt)
+  unsigned long long tm_epoch = ~0ull;
+  bool cond_ready = false;             // CONDH / CP (or CONDF) hold the conditioner of dsx_set_cond for geometry cond_geom
+  dsx::Geom cond_geom;
+  int batch_offset = 0;                // DSX_OPT_BATCH_OFFSET: global index of utterance 0 in the Philox noise counters
   bool attr_layer[3] = {false, false, false}, attr_head[2] = {false, false}, attr_cond = false;
   int occ_cache[3][17] = {};
   int cluster_occ = 0;              // max co-resident utterance clusters reported by the driver (last launch)
@@ -172,9 +191,17 @@ int launch_tc_head(dsx_handle* h, const Geom& g, int flags, float* x_state, dsx_
                    const float* noise, uint64_t seed, uint64_t offset, DdpmCoef c, int next_row0, int row_per_b,
                    cudaStream_t s);
 bool tc_supported(const dsx_handle* h);
+int ensure_flags(dsx_handle* h, int n);
+int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows);
+void reset_flags(dsx_handle* h);
+
+// ---- dsx_stack.cu ------------------------------------------------------------------------
+int tc_stack_pack(dsx_handle* h, cudaStream_t s);
+bool tc_stack_usable(dsx_handle* h, const Geom& g);
+int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_b, int wset, cudaStream_t s);
 
 int dev_alloc(dsx_handle* h, void** p, size_t bytes, bool model_owned);
-int ensure_workspace(dsx_handle* h, const Geom& g, int rows);
+int ensure_workspace(dsx_handle* h, const Geom& g, int rows, cudaStream_t s);
 int check_status(dsx_handle* h, cudaStream_t s, const char* what);
 
 }  // namespace dsx

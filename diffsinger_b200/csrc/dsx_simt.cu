@@ -436,7 +436,7 @@ int launch_head(dsx_handle* h, const Geom& g, float* eps, cudaStream_t s) {
 // p_sample after the network (shallow_diffusion_tts.py:134-166), same fp32 operation order
 // (no FMA contraction): x_recon = A*x - Bc*eps; clamp; mean = c1*x_recon + c2*x; + sigma*noise.
 __global__ void k_ddpm_update(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
-                              uint64_t seed, uint64_t offset, DdpmCoef c, size_t n, int M, int T) {
+                              uint64_t seed, uint64_t offset, DdpmCoef c, size_t n, int M, int T, int b_off) {
   size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   float xv = x[i];
@@ -449,7 +449,7 @@ __global__ void k_ddpm_update(float* __restrict__ x, const float* __restrict__ e
       z = noise[i];
     } else {
       const int t = static_cast<int>(i % T), m = static_cast<int>((i / T) % M), b = static_cast<int>(i / (static_cast<size_t>(T) * M));
-      const float4 z4 = philox_normal4(seed, offset, mel_noise_block(b, m, t, M, T));
+      const float4 z4 = philox_normal4(seed, offset, mel_noise_block(b + b_off, m, t, M, T));
       z = (m & 3) == 0 ? z4.x : (m & 3) == 1 ? z4.y : (m & 3) == 2 ? z4.z : z4.w;
     }
   }
@@ -458,7 +458,7 @@ __global__ void k_ddpm_update(float* __restrict__ x, const float* __restrict__ e
 
 int launch_ddpm_update(dsx_handle* h, float* x, const float* eps, const float* noise, uint64_t seed, uint64_t offset,
                        DdpmCoef c, size_t n, int T, cudaStream_t s) {
-  k_ddpm_update<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, eps, noise, seed, offset, c, n, h->m.M, T);
+  k_ddpm_update<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, eps, noise, seed, offset, c, n, h->m.M, T, h->batch_offset);
   h->launches++;
   DSX_CUDA(cudaGetLastError());
   return DSX_OK;
@@ -493,7 +493,7 @@ int launch_plms_update(dsx_handle* h, float* x_out, const float* x_in, const flo
 // [B,1,M,T], q_sample at K_step-1 (:206-211).
 __global__ void k_prologue(float* __restrict__ x, const float* __restrict__ fs2_mel, const float* __restrict__ noise,
                            uint64_t seed, const float* __restrict__ smin, const float* __restrict__ smax, float sa,
-                           float s1a, int T, int M) {
+                           float s1a, int T, int M, int b_off) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -511,7 +511,7 @@ __global__ void k_prologue(float* __restrict__ x, const float* __restrict__ fs2_
     int mm = m0 + i, t = t0 + threadIdx.x;
     if (mm < M && t < T) {
       size_t o = (static_cast<size_t>(b) * M + mm) * T + t;
-      float z = noise ? noise[o] : philox_normal(seed, 0xFFFFFFFFull, o);
+      float z = noise ? noise[o] : philox_normal(seed, 0xFFFFFFFFull, o + static_cast<size_t>(b_off) * M * T);
       x[o] = __fadd_rn(__fmul_rn(sa, tile[threadIdx.x][i]), __fmul_rn(s1a, z));
     }
   }
@@ -521,7 +521,7 @@ int launch_prologue(dsx_handle* h, float* x, const float* fs2_mel, const float* 
                     const float* spec_min, const float* spec_max, float sa, float s1a, int B, int T, int M,
                     cudaStream_t s) {
   dim3 grid((T + 31) / 32, (M + 31) / 32, B), block(32, 8);
-  k_prologue<<<grid, block, 0, s>>>(x, fs2_mel, start_noise, seed, spec_min, spec_max, sa, s1a, T, M);
+  k_prologue<<<grid, block, 0, s>>>(x, fs2_mel, start_noise, seed, spec_min, spec_max, sa, s1a, T, M, h->batch_offset);
   h->launches++;
   DSX_CUDA(cudaGetLastError());
   return DSX_OK;

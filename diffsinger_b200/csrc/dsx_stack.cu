@@ -1,0 +1,740 @@
+// k_tc_stack<WP>: all residual layers of one DiffNet evaluation (usr/diff/net.py:58-78,121-126) in one persistent launch,
+// with the residual stream in REGISTERS, the conv input y in SHARED MEMORY and the skip sum in TENSOR MEMORY for the whole
+// stack.  Per 128-frame tile (one CTA; two CTAs form a cta_group::2 pair, UMMA M = 256, N = 256) and layer l:
+//
+//   GEMM1   D1[:, chunk h] = [y(t-d) | y(t) | y(t+d)] (K = 768) . W1(h)^T      -> TMEM columns F = [0, 256), h = 0 then 1
+//   epi1    z(chunk h) = sigmoid(D1 gate + CP) * tanh(D1 filter + CP) -> fp16, swizzled K-major rows in shared memory
+//   GEMM2r  D2res = z (K = 256) . W2res^T                                        -> F
+//   GEMM2s  SKIP += z . W2skip^T                                                  -> TMEM columns S = [256, 512), accumulated
+//                                                                                  over ALL layers, read once at the end
+//   epi2    x <- (x + D2res + b) / sqrt2   (x: 128 fp32 registers per epilogue thread = one frame row x 128 channels)
+//           y_{l+1} = fp16(x + d_{l+1})    -> straight into the next layer's A-operand tiles in shared memory; only the
+//                                              8 first / last rows of the tile also go to HBM for the neighbour tiles' halos
+//
+// Compared with the round-1 layer kernel (dsx_tc.cu, k_tc_layer) this removes, per layer and tile, the fp32 read-modify-
+// write of x through L2 (256 KB), the skip red.add (128 KB), the y round trip through L2 (64 KB + 144 KB of TMA loads) and
+// the transposing staging pass; the layer hand-over inside a tile is a shared-memory barrier instead of a global flag round
+// trip (only the 8-row halos still travel through global memory + publish counters).
+//
+// Shared memory: [W ring 5 x 16 KB | y: 4 k-blocks x (8 halo + 128 + 8 halo rows) x 128 B | z: 4 k-blocks x 16 KB |
+//                 per-layer bias / FiLM vectors (1 KB per epilogue warp) | barriers]
+// TMEM: F (256 columns: D1 chunk 0, D1 chunk 1, D2res in turn) + S (256 columns, skip accumulator).
+// Roles (384 threads): warp 0 lane 0 = halo / flag / CP-prefetch producer, warps 2, 3 lane 0 = weight producers, warp 1
+// lane 0 of the pair leader = MMA issuer, warps 4-11 = epilogue (thread = frame row = TMEM lane, two warps per lane quadrant
+// split the 256 columns).  setmaxnreg moves registers from warps 0-3 to the epilogue warps (x lives there).
+//
+// Weight tiles: WP = 2 reads the hi and lo planes of the round-1 pack (fp16x2 parity mode); WP = 1 reads one plane -- either
+// the round-to-nearest hi plane (fp16 fast mode) or one of R stochastically rounded weight sets, a different one at every
+// diffusion step (fp16s mode: the rounding error of the weights then decorrelates across steps instead of accumulating).
+#include <cuda.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "dsx_internal.h"
+#include "dsx_ptx.cuh"
+#include "dsx_rng.cuh"
+#include "dsx_tc_common.cuh"
+
+namespace dsx {
+
+struct StackCfg {
+  static constexpr int WSLOTS = 5;
+  static constexpr int YSLOT = (kTile + 16) * 128;         // [8 halo | 128 centre | 8 halo] rows of 64 channels
+  static constexpr int W_BYTES = WSLOTS * kUnitBytes;
+  static constexpr int Y_BYTES = 4 * YSLOT;
+  static constexpr int Z_BYTES = 4 * kUnitBytes;
+  static constexpr int TAB_BYTES = kEpiWarps * 1024;       // per epilogue warp: [bias(128) | d_next(128)] fp32 of its column half
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 1024 + W_BYTES + Y_BYTES + Z_BYTES + TAB_BYTES + BAR_BYTES;
+  static constexpr int REGS_LOW = 56, REGS_HIGH = 224;     // setmaxnreg targets: 128 * 56 + 256 * 224 = 64512 = 384 * 168 (the launch allocation)
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(YSLOT % 1024 == 0, "y slots must keep the 1024-byte swizzle atoms aligned");
+};
+
+struct TcStackParams {
+  CUtensorMap tm_w;        // weight tiles, 2D [rows][64], box 64 x 128 rows
+  CUtensorMap tm_y0;       // Y buffer 0 (written by the input projection), box 64 ch x 144 frames: layer 0 incl. halos
+  CUtensorMap tm_ye[2];    // Y buffer 0 / 1, box 64 ch x 8 frames: halo rows published by the neighbour tiles
+  float* X;                // [B][Tp][256] residual stream: read at entry, written back at exit
+  float* SKIP;             // [B][Tp][256] skip sum (debug tap / fp32 copy), written at exit
+  __half* Y;               // [2 buffers][2 planes][plane_elems]; only the edge rows of the hi plane are written here
+  size_t plane_elems;
+  const float* CP;         // [L][tiles][2 chunks][64 column groups][128 rows][4] conditioner projection + biases
+  int cp_prefetch;
+  const float* b2;         // [L][512] output_projection bias (residual half | skip half)
+  const float* bskip;      // [L][256] prefix sums over layers of the skip-half biases
+  const float* dtab;       // FiLM rows of this evaluation: [L][256], utterance b at + b * d_row_stride
+  int d_row_stride;
+  int T, Tp, tiles_per_utt, tiles, B;
+  int tile0, tile_end;     // this launch covers tiles [tile0, tile_end) (whole utterances); CTA i -> tile tile0 + i
+  int nl, L, cycle;        // layers [0, nl); dilation of layer l = 1 << (l % cycle)
+  int w_row0;              // first row of this evaluation's weight set in tm_w
+  int w_layer_rows;        // rows per layer
+  int w_sr;                // 0: round-1 pack (80 tiles per layer, hi / lo planes); 1: single-plane set (32 tiles per layer)
+  unsigned int* flags;     // [tiles] publish counters
+  unsigned int flag_base;
+  __half* s16;             // fp16 split of skip_total / sqrt(L): plane 0 hi, plane 1 (at + plane_elems) lo
+  float inv_sqrt_l;
+  int fast_act;            // 1: tanh.approx gate (fp16 fast mode)
+  int* status;
+  unsigned long long budget_ns;
+  long long* trace;        // debug: [2 CTAs][3 roles][256] clock64 stamps, or nullptr
+};
+
+constexpr int kFlagsPerLayer = 4;      // edge warps (rows 0-31 and 96-127, two column halves) publish per layer
+
+#define DSX_STRACE(role, slot)                                                         \
+  do {                                                                                 \
+    if (p.trace && blockIdx.x < 2 && (slot) < 256)                                      \
+      p.trace[(blockIdx.x * 3 + (role)) * 256 + (slot)] = clock64();                   \
+  } while (0)
+
+// wait until the (up to two) neighbour tiles' counters have reached `target`
+__device__ __forceinline__ bool flag_wait2(const unsigned int* lo, const unsigned int* hi, unsigned int target,
+                                           const Watchdog& wd, int code) {
+  if (!lo && !hi) return true;
+  uint32_t spins = 0;
+  while (true) {
+    unsigned int v1 = target, v2 = target;
+    if (lo) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(lo) : "memory");
+    if (hi) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v2) : "l"(hi) : "memory");
+    if (static_cast<int>(v1 - target) >= 0 && static_cast<int>(v2 - target) >= 0) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      return true;
+    }
+    if (((++spins) & 0xff) == 0) {
+      if (*(volatile int*)wd.status != 0) return false;
+      if (globaltimer_ns() > wd.deadline_ns) {
+        atomicCAS(wd.status, 0, code);
+        return false;
+      }
+    }
+  }
+}
+
+template <int WP>
+__global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant__ TcStackParams p) {
+  using Cfg = StackCfg;
+  constexpr int G = kG;
+  constexpr int WS = Cfg::WSLOTS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* wring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* yslots = wring + Cfg::W_BYTES;
+  uint8_t* zbuf = yslots + Cfg::Y_BYTES;
+  float* tab = reinterpret_cast<float*>(zbuf + Cfg::Z_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tab) + Cfg::TAB_BYTES);
+  uint64_t* full = bars;            // [WS] weight tile landed (both CTAs' halves; leader's barrier)
+  uint64_t* empty = full + WS;      // [WS] weight tile consumed (tcgen05.commit, both CTAs)
+  uint64_t* tfull = empty + WS;     // accumulator F (or S at the very end) complete -> epilogue
+  uint64_t* tempty = tfull + 1;     // epilogue phase done (F drained, z / y written), 8 warps x 2 CTAs -> leader
+  uint64_t* g1done = tempty + 1;    // all GEMM1 MMAs of the layer complete: the y slots may be overwritten
+  uint64_t* yhalo = g1done + 1;     // halo rows (layer 0: whole slots) landed (leader's barrier)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yhalo + 1);
+  static_assert((2 * Cfg::WSLOTS + 4) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t prank = crank & 1;
+  const uint32_t lead = crank & ~1u;
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << lead);
+  const int tile = p.tile0 + blockIdx.x;
+  const bool tile_valid = tile < p.tile_end;
+  const int b = tile / p.tiles_per_utt, tr = tile % p.tiles_per_utt;
+  const int bq = tile_valid ? b : p.B;            // b == B: every TMA row out of bounds (zeros)
+  const int cp_tile = tile_valid ? tile : 0;      // padding CTAs read (and discard) tile 0's slice of CP
+  const int t0 = tile_valid ? tr * kTile : 0;
+  const bool nb_lo = tile_valid && tr > 0, nb_hi = tile_valid && tr + 1 < p.tiles_per_utt;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_w);
+    tma_prefetch_desc(&p.tm_y0);
+    tma_prefetch_desc(&p.tm_ye[0]);
+    tma_prefetch_desc(&p.tm_ye[1]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < WS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, kEpiWarps * G);
+    mbar_init(g1done, 1);
+    mbar_init(yhalo, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<G>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  Watchdog wd{p.status, globaltimer_ns() + p.budget_ns};
+
+  // weight tile row in tm_w: GEMM1 (chunk h, tap, channel block cb, plane) / GEMM2 (half q, k-block kb, plane)
+  auto w1_row = [&](int l, int h, int tap, int cb, int plane) -> int {
+    const int idx = p.w_sr ? (h * 12 + tap * 4 + cb) : ((plane * 2 + h) * 16 + tap * 4 + cb);
+    return p.w_row0 + l * p.w_layer_rows + idx * 256 + static_cast<int>(prank) * 128;
+  };
+  auto w2_row = [&](int l, int q, int kb, int plane) -> int {
+    const int idx = p.w_sr ? (24 + q * 4 + kb) : (64 + (plane * 2 + q) * 4 + kb);
+    return p.w_row0 + l * p.w_layer_rows + idx * 256 + static_cast<int>(prank) * 128;
+  };
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_LOW));
+    if (warp == 0 && lane == 0) {
+      // ================================ halo / flag / CP-prefetch producer ================================
+      bool ok = true;
+      auto cp_prefetch = [&](int l, int h) {
+        if (!p.cp_prefetch || l >= p.nl) return;
+        const char* src = reinterpret_cast<const char*>(p.CP + ((static_cast<size_t>(l) * p.tiles + cp_tile) * 2 + h) * kCpChunk);
+        for (int i = 0; i < 8; ++i) prefetch_l2_bulk(src + i * 16384, 16384);
+      };
+      // layer 0: the whole [8 | 128 | 8]-row slots come from Y buffer 0 (written by the input projection kernel)
+      if (prank == 0) mbar_arrive_expect_tx(yhalo, G * Cfg::Y_BYTES);
+      for (int cb = 0; cb < 4; ++cb) tma_load_3d<G>(&p.tm_y0, yhalo, yslots + cb * Cfg::YSLOT, cb * 64, t0 - 8, bq, lead);
+      cp_prefetch(0, 0);
+      cp_prefetch(0, 1);
+      cp_prefetch(1, 0);
+      for (int l = 1; l < p.nl && ok; ++l) {
+        // y_l: the centre rows are written into the slots by this tile's own epilogue; the halo rows come from the
+        // neighbour tiles through global memory once (a) GEMM1 of layer l-1 no longer reads the slots and (b) the
+        // neighbours have published their edge rows of y_l
+        ok = mbar_wait(g1done, (l - 1) & 1, wd, 105);
+        DSX_STRACE(0, l * 4);
+        if (ok)
+          ok = flag_wait2(nb_lo ? p.flags + tile - 1 : nullptr, nb_hi ? p.flags + tile + 1 : nullptr,
+                          p.flag_base + static_cast<unsigned int>(kFlagsPerLayer * l), wd, 107);
+        if (!ok) break;
+        fence_proxy_async_all();
+        DSX_STRACE(0, l * 4 + 1);
+        if (prank == 0) mbar_arrive_expect_tx(yhalo, G * 8 * 1024);
+        for (int cb = 0; cb < 4; ++cb) {
+          tma_load_3d<G>(&p.tm_ye[l & 1], yhalo, yslots + cb * Cfg::YSLOT, cb * 64, t0 - 8, bq, lead);
+          tma_load_3d<G>(&p.tm_ye[l & 1], yhalo, yslots + cb * Cfg::YSLOT + (kTile + 8) * 128, cb * 64, t0 + kTile, bq, lead);
+        }
+        DSX_STRACE(0, l * 4 + 2);
+        cp_prefetch(l, 1);
+        cp_prefetch(l + 1, 0);
+      }
+    } else if ((warp == 2 || warp == 3) && lane == 0) {
+      // ================================ weight producers ================================
+      const uint32_t wid = warp - 2;
+      uint32_t wi = 0;
+      bool ok = true;
+      auto load_w = [&](int row) {
+        if ((wi & 1) == wid) {
+          const uint32_t s = wi % WS;
+          ok = mbar_wait(&empty[s], ((wi / WS) & 1) ^ 1, wd, 102);
+          if (ok) {
+            if (prank == 0) mbar_arrive_expect_tx(&full[s], G * kUnitBytes);
+            tma_load_2d<G>(&p.tm_w, &full[s], wring + s * kUnitBytes, 0, row, lead);
+          }
+        }
+        ++wi;
+      };
+      for (int l = 0; l < p.nl && ok; ++l) {
+        for (int h = 0; h < 2 && ok; ++h) {
+          for (int cb = 0; cb < 4 && ok; ++cb)                      // centre tap first: needs no halo rows
+            for (int pl = 0; pl < WP && ok; ++pl) load_w(w1_row(l, h, 1, cb, pl));
+          for (int cb = 0; cb < 4 && ok; ++cb)
+            for (int tap = 0; tap < 3 && ok; tap += 2)
+              for (int pl = 0; pl < WP && ok; ++pl) load_w(w1_row(l, h, tap, cb, pl));
+        }
+        for (int q = 0; q < 2 && ok; ++q)
+          for (int kb = 0; kb < 4 && ok; ++kb)
+            for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, q, kb, pl));
+      }
+    } else if (warp == 1 && lane == 0 && prank == 0) {
+      // ================================ MMA issuer (pair leader) ================================
+      constexpr uint32_t idesc = umma_idesc_f16(128 * G, 256);
+      const uint32_t dF = tmem_base, dS = tmem_base + 256;
+      uint32_t wi = 0, te = 0;
+      bool ok = true;
+      auto mma_tile = [&](uint32_t d, uint64_t a, uint32_t& acc, int code) {   // one weight tile of the global order
+        const uint32_t s = wi % WS;
+        ok = ok && mbar_wait(&full[s], (wi / WS) & 1, wd, code);
+        if (!ok) return;
+        tc_fence_after();
+        const uint64_t w = umma_desc_sw128(smem_u32(wring + s * kUnitBytes));
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          umma_f16<G>(d, a + 2 * k4, w + 2 * k4, idesc, acc);
+          acc = 1;
+        }
+        umma_commit<G>(&empty[s], pair_mask);
+        ++wi;
+      };
+      auto wait_epi = [&](int code) {                   // next epilogue phase done: F drained, its z / y in shared memory
+        ok = ok && mbar_wait(tempty, te & 1, wd, code);
+        ++te;
+        tc_fence_after();
+      };
+      uint32_t acc_s = 0;
+      for (int l = 0; l < p.nl && ok; ++l) {
+        const int dil = 1 << (l % p.cycle);
+        for (int h = 0; h < 2 && ok; ++h) {
+          if (l > 0 || h > 0) wait_epi(201);            // h = 0: epi2 of layer l-1 (y_l centre rows); h = 1: epi1 chunk 0
+          if (!ok) break;
+          DSX_STRACE(1, l * 8 + h * 2);
+          uint32_t acc = 0;
+          if (h == 0 && l == 0) {                       // layer 0: the whole slots (centre rows too) arrive by TMA
+            ok = mbar_wait(yhalo, 0, wd, 206);
+            tc_fence_after();
+          }
+          for (int cb = 0; cb < 4 && ok; ++cb) {        // centre tap: rows written by this pair's own epilogue
+            const uint64_t a = umma_desc_sw128(smem_u32(yslots + cb * Cfg::YSLOT)) + static_cast<uint64_t>((8 * 128) >> 4);
+            for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dF, a, acc, 207);
+          }
+          if (h == 0 && l > 0 && ok) {                  // halo rows of this layer (from the neighbour tiles) landed
+            ok = mbar_wait(yhalo, l & 1, wd, 206);
+            tc_fence_after();
+          }
+          for (int cb = 0; cb < 4 && ok; ++cb) {
+            const uint64_t y = umma_desc_sw128(smem_u32(yslots + cb * Cfg::YSLOT));
+            for (int tap = 0; tap < 3 && ok; tap += 2) {
+              const uint64_t a = y + static_cast<uint64_t>(((8 + (tap - 1) * dil) * 128) >> 4);   // row-shifted start
+              for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dF, a, acc, 207);
+            }
+          }
+          if (ok && h == 1) umma_commit<G>(g1done, pair_mask);
+          if (ok) umma_commit<G>(tfull, pair_mask);
+          DSX_STRACE(1, l * 8 + h * 2 + 1);
+        }
+        if (!ok) break;
+        wait_epi(203);                                  // epi1 chunk 1: all four z k-blocks written, F free
+        if (!ok) break;
+        DSX_STRACE(1, l * 8 + 4);
+        {
+          uint32_t acc = 0;
+          for (int kb = 0; kb < 4 && ok; ++kb) {
+            const uint64_t z = umma_desc_sw128(smem_u32(zbuf + kb * kUnitBytes));
+            for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dF, z, acc, 205);
+          }
+          if (ok) umma_commit<G>(tfull, pair_mask);
+        }
+        DSX_STRACE(1, l * 8 + 5);
+        for (int kb = 0; kb < 4 && ok; ++kb) {
+          const uint64_t z = umma_desc_sw128(smem_u32(zbuf + kb * kUnitBytes));
+          for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dS, z, acc_s, 205);
+        }
+        DSX_STRACE(1, l * 8 + 6);
+      }
+      if (ok) {
+        wait_epi(208);                                  // epi2 of the last layer (so that tfull's phases stay in order)
+        if (ok) umma_commit<G>(tfull, pair_mask);        // every MMA (incl. the skip accumulation) complete
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_HIGH));
+    // ================================ epilogue (8 warps) ================================
+    const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;               // which half of the 256 columns
+    const int r = quad * 32 + lane;                 // frame row in the tile == TMEM lane
+    const uint32_t tlane = static_cast<uint32_t>(quad * 32) << 16;
+    const bool tracer = (warp == 4 && lane == 0);
+    const bool row_valid = tile_valid && (t0 + r < p.T);
+    const bool edge_lo = r < 8, edge_hi = r >= kTile - 8;
+    const size_t grow = (static_cast<size_t>(tile_valid ? b : 0) * p.Tp + t0 + r) * kC + half * 128;   // this thread's row
+    uint32_t tf = 0;
+    bool ok = true;
+    auto release = [&]() {                          // this warp's part of the phase is done
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty, lead);
+    };
+    auto wait_acc = [&](int code) -> bool {         // one lane polls, the warp reconverges on the shuffle
+      int okv = 1;
+      if (lane == 0) okv = mbar_wait(tfull, tf & 1, wd, code) ? 1 : 0;
+      ++tf;
+      okv = __shfl_sync(0xffffffffu, okv, 0);
+      tc_fence_after();
+      return okv != 0;
+    };
+    const uint64_t cp_policy = l2_policy_evict_first();
+
+    // residual stream of this thread's row: 128 channels, fp32, in registers for the whole stack
+    float x[128];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(p.X + grow + i * 4);
+      x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+    }
+    const float* dbase = p.dtab + static_cast<size_t>(tile_valid ? b : 0) * p.d_row_stride;
+
+    for (int l = 0; l < p.nl && ok; ++l) {
+      const bool has_next = (l + 1 < p.nl);
+      // ---- per-layer vectors of this warp's column half -> its own shared-memory table (the gpu-scope fences of the halo
+      //      hand-over invalidate L1, so reading them from global inside the epilogue would cost an L2 round trip each;
+      //      one table per warp: no cross-warp barrier) ----
+      float* tb = tab + (warp - 4) * 256;
+      __syncwarp();
+      *reinterpret_cast<float4*>(tb + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.b2 + static_cast<size_t>(l) * 512 + half * 128) + lane);
+      *reinterpret_cast<float4*>(tb + 128 + lane * 4) =
+          has_next ? __ldg(reinterpret_cast<const float4*>(dbase + static_cast<size_t>(l + 1) * kC + half * 128) + lane)
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+
+      // ---- epi1: z = sigmoid(gate) * tanh(filter), gate / filter = accumulator + CP; sub-passes of 8 column pairs, the CP
+      //      loads of the next sub-pass (and across the chunk boundary) fly while this one is computed ----
+      const float* cpl = p.CP + (static_cast<size_t>(l) * p.tiles + cp_tile) * 2 * kCpChunk + r * 4;
+      float4 cg[2][2], cf[2][2];
+      auto cp_issue = [&](const float* cph, int c, float4* g4, float4* f4) {
+#pragma unroll
+        for (int v4 = 0; v4 < 2; ++v4) {
+          g4[v4] = ld_stream_f4(cph + ((c >> 2) + v4) * (kTile * 4), cp_policy);
+          f4[v4] = ld_stream_f4(cph + (((128 + c) >> 2) + v4) * (kTile * 4), cp_policy);
+        }
+      };
+      auto gcol = [&](int sp) { return (sp >> 2) * 64 + half * 32 + (sp & 3) * 8; };   // gate column of sub-pass sp
+      cp_issue(cpl, gcol(0), cg[0], cf[0]);
+#pragma unroll 1
+      for (int h = 0; h < 2 && ok; ++h) {
+        const float* cph = cpl + h * kCpChunk;
+        if (tracer) DSX_STRACE(2, l * 12 + h * 3);
+        ok = wait_acc(301 + h);
+        if (!ok) break;
+        if (tracer) DSX_STRACE(2, l * 12 + h * 3 + 1);
+        uint32_t g[2][8], f[2][8];
+        tmem_ld_32x8(tmem_base + tlane + gcol(0), g[0]);
+        tmem_ld_32x8(tmem_base + tlane + 128 + gcol(0), f[0]);
+#pragma unroll
+        for (int sp = 0; sp < 8; ++sp) {
+          const int c = gcol(sp), cur = sp & 1, nxt = cur ^ 1;
+          tmem_ld_wait();
+          if (sp + 1 < 8) {
+            cp_issue(cph, gcol(sp + 1), cg[nxt], cf[nxt]);
+            tmem_ld_32x8(tmem_base + tlane + gcol(sp + 1), g[nxt]);
+            tmem_ld_32x8(tmem_base + tlane + 128 + gcol(sp + 1), f[nxt]);
+          } else if (h == 0) {
+            cp_issue(cph + kCpChunk, gcol(0), cg[nxt], cf[nxt]);
+          }
+          uint32_t hz[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 bg = cg[cur][e >> 1], bf = cf[cur][e >> 1];
+            const float g0 = __uint_as_float(g[cur][2 * e]) + ((e & 1) ? bg.z : bg.x);
+            const float g1 = __uint_as_float(g[cur][2 * e + 1]) + ((e & 1) ? bg.w : bg.y);
+            const float f0 = __uint_as_float(f[cur][2 * e]) + ((e & 1) ? bf.z : bf.x);
+            const float f1 = __uint_as_float(f[cur][2 * e + 1]) + ((e & 1) ? bf.w : bf.y);
+            float z0, z1;
+            if (p.fast_act) {
+              z0 = sigmoid_fast(g0) * tanh_approx(f0);
+              z1 = sigmoid_fast(g1) * tanh_approx(f1);
+            } else {
+              z0 = gate_acc(g0, f0);
+              z1 = gate_acc(g1, f1);
+            }
+            hz[e] = h2_bits(__floats2half2_rn(z0, z1));
+          }
+          // channel 128 h + c  ->  z k-block 2 h + (sp >> 2), 16-byte chunk half * 4 + (sp & 3) of row r
+          uint8_t* zrow = zbuf + (2 * h + (sp >> 2)) * kUnitBytes + r * 128;
+          *reinterpret_cast<uint4*>(zrow + (((half * 4 + (sp & 3)) ^ (r & 7)) << 4)) = make_uint4(hz[0], hz[1], hz[2], hz[3]);
+        }
+        release();
+        if (tracer) DSX_STRACE(2, l * 12 + h * 3 + 2);
+      }
+      if (!ok) break;
+
+      // ---- epi2: x <- (x + D2res + b) / sqrt2 in registers; y_{l+1} = fp16(x + d_{l+1}) -> next layer's A tiles ----
+      if (tracer) DSX_STRACE(2, l * 12 + 6);
+      ok = wait_acc(303);
+      if (!ok) break;
+      if (tracer) DSX_STRACE(2, l * 12 + 7);
+      {
+        const float4* bt = reinterpret_cast<const float4*>(tb);
+        const float4* dt = reinterpret_cast<const float4*>(tb + 128);
+        __half* const yedge = p.Y + static_cast<size_t>(((l + 1) & 1) * 2) * p.plane_elems + grow;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint32_t o[32];
+          tmem_ld_32x32(tmem_base + tlane + half * 128 + jj * 32, o);
+          tmem_ld_wait();
+          uint8_t* yrow = yslots + (half * 2 + (jj >> 1)) * Cfg::YSLOT + (8 + r) * 128;
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            uint32_t hy[4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = c8 * 8 + e * 4, col = jj * 32 + i;
+              const float4 bias = bt[col >> 2], dn = dt[col >> 2];
+              const float x0 = (x[col] + (__uint_as_float(o[i]) + bias.x)) * 0.70710678118654752440f;
+              const float x1 = (x[col + 1] + (__uint_as_float(o[i + 1]) + bias.y)) * 0.70710678118654752440f;
+              const float x2 = (x[col + 2] + (__uint_as_float(o[i + 2]) + bias.z)) * 0.70710678118654752440f;
+              const float x3 = (x[col + 3] + (__uint_as_float(o[i + 3]) + bias.w)) * 0.70710678118654752440f;
+              x[col] = x0; x[col + 1] = x1; x[col + 2] = x2; x[col + 3] = x3;
+              hy[2 * e] = row_valid ? h2_bits(__floats2half2_rn(x0 + dn.x, x1 + dn.y)) : 0u;
+              hy[2 * e + 1] = row_valid ? h2_bits(__floats2half2_rn(x2 + dn.z, x3 + dn.w)) : 0u;
+            }
+            if (has_next) {
+              const uint4 v = make_uint4(hy[0], hy[1], hy[2], hy[3]);
+              *reinterpret_cast<uint4*>(yrow + ((((jj & 1) * 4 + c8) ^ (r & 7)) << 4)) = v;
+              if ((edge_lo || edge_hi) && row_valid) *reinterpret_cast<uint4*>(yedge + jj * 32 + c8 * 8) = v;
+            }
+          }
+        }
+      }
+      release();
+      if (tracer) DSX_STRACE(2, l * 12 + 8);
+      if (has_next && tile_valid && (quad == 0 || quad == 3)) {
+        // publish the edge rows of y_{l+1}: generic-proxy global stores -> async-proxy (TMA) readers in the neighbour CTAs
+        fence_proxy_async_all();
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) flag_publish(p.flags + tile);
+      }
+    }
+
+    // ---- exit: skip sum (TMEM S, accumulated over all layers) -> SKIP (fp32) and the fp16 hi / lo operand of the head
+    //      GEMM; residual stream back to X (debug tap) ----
+    if (ok) ok = wait_acc(304);
+    if (ok) {
+      const float* bs = p.bskip + static_cast<size_t>(p.nl - 1) * kC + half * 128;
+#pragma unroll 1
+      for (int jj = 0; jj < 4; ++jj) {
+        uint32_t o[32];
+        tmem_ld_32x32(tmem_base + tlane + 256 + half * 128 + jj * 32, o);
+        tmem_ld_wait();
+        if (row_valid) {
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bs + jj * 32) + c4);
+            float4 v;
+            v.x = __uint_as_float(o[c4 * 4]) + bb.x;
+            v.y = __uint_as_float(o[c4 * 4 + 1]) + bb.y;
+            v.z = __uint_as_float(o[c4 * 4 + 2]) + bb.z;
+            v.w = __uint_as_float(o[c4 * 4 + 3]) + bb.w;
+            *reinterpret_cast<float4*>(p.SKIP + grow + jj * 32 + c4 * 4) = v;
+            if (p.nl == p.L) {
+              const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l, sc = v.z * p.inv_sqrt_l, sd = v.w * p.inv_sqrt_l;
+              const __half2 h0 = __floats2half2_rn(sa, sb), h1 = __floats2half2_rn(sc, sd);
+              const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+              __half* sp = p.s16 + grow + jj * 32 + c4 * 4;
+              *reinterpret_cast<uint2*>(sp) = make_uint2(h2_bits(h0), h2_bits(h1));
+              *reinterpret_cast<uint2*>(sp + p.plane_elems) =
+                  make_uint2(h2_bits(__floats2half2_rn(sa - f0.x, sb - f0.y)), h2_bits(__floats2half2_rn(sc - f1.x, sd - f1.y)));
+            }
+          }
+        }
+      }
+      if (row_valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          *reinterpret_cast<float4*>(p.X + grow + i * 4) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+      }
+    }
+    if (tracer) DSX_STRACE(2, 250);
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<G>(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+// prefix sums over layers of the skip-half biases of output_projection: bskip[l][c] = sum_{j <= l} b2[j][256 + c]
+__global__ void k_bskip_prefix(const float* __restrict__ b2, float* __restrict__ bskip, int L) {
+  const int c = threadIdx.x;
+  float acc = 0.f;
+  for (int l = 0; l < L; ++l) {
+    acc += b2[static_cast<size_t>(l) * 512 + 256 + c];
+    bskip[static_cast<size_t>(l) * 256 + c] = acc;
+  }
+}
+
+// R stochastically rounded fp16 copies of the GEMM1 / GEMM2 weights (fp16s mode): element v lies between two fp16
+// neighbours lo <= v <= hi and becomes hi with probability (v - lo) / (hi - lo), so E[w] = v; set r is used by diffusion
+// step j with j % R == r.  Layout [R][L][32 tiles][256 rows][64]: W1 tile = h * 12 + tap * 4 + cb, W2 tile = 24 + q * 4 + kb
+// (same row / k conventions as k_pack_wtc in dsx_tc.cu).  Philox4x32-10 keyed by (seed, set), counter = element index.
+__global__ void k_pack_wsr(const float* __restrict__ w1f, const float* __restrict__ w2f, __half* __restrict__ wsr, int L,
+                           unsigned long long seed) {
+  const int l = blockIdx.y, tileidx = blockIdx.x, set = blockIdx.z, n = threadIdx.x;
+  const float* src;
+  if (tileidx < 24) {
+    const int h = tileidx / 12, kb = tileidx % 12;
+    const int j = (n < 128) ? (128 * h + n) : (kC + 128 * h + (n - 128));
+    src = w1f + (static_cast<size_t>(l) * 2 * kC + j) * (4 * kC) + kb * 64;
+  } else {
+    const int u = tileidx - 24, q = u / 4, kb = u & 3;
+    src = w2f + (static_cast<size_t>(l) * 2 * kC + q * 256 + n) * kC + kb * 64;
+  }
+  const size_t row = ((static_cast<size_t>(set) * L + l) * 32 + tileidx) * 256 + n;
+  __half* dst = wsr + row * 64;
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed) ^ (0x9E3779B9u * static_cast<uint32_t>(set + 1)),
+                               static_cast<uint32_t>(seed >> 32) + static_cast<uint32_t>(set));
+  for (int k4 = 0; k4 < 16; ++k4) {
+    const size_t ctr = (static_cast<size_t>(l) * 32 + tileidx) * 256 * 16 + static_cast<size_t>(n) * 16 + k4;
+    const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0x5352u, 0u), key);
+    const uint32_t u4[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v = src[k4 * 4 + e];
+      const __half hn = __float2half_rn(v);
+      const float fn = __half2float(hn);
+      // the other neighbour: one fp16 ulp towards v
+      __half ho = hn;
+      if (fn != v) {
+        unsigned short bits = __half_as_ushort(hn);
+        const bool away = (fn < v) == (fn >= 0.f);     // move away from zero when v lies beyond |hn|
+        if (fn == 0.f) bits = (v > 0.f) ? 0x0001 : 0x8001;
+        else bits = static_cast<unsigned short>(away ? bits + 1 : bits - 1);
+        ho = __ushort_as_half(bits);
+      }
+      const float fo = __half2float(ho);
+      // P(take the other neighbour) = |v - fn| / |fo - fn|
+      const float pr = (fo != fn) ? fabsf(v - fn) / fabsf(fo - fn) : 0.f;
+      const float uu = static_cast<float>(u4[e] >> 8) * (1.0f / 16777216.0f);
+      dst[k4 * 4 + e] = (uu < pr) ? ho : hn;
+    }
+  }
+}
+
+int tc_stack_pack(dsx_handle* h, cudaStream_t s) {
+  float* bskip;
+  DSX_TRY(dev_alloc(h, reinterpret_cast<void**>(&bskip), static_cast<size_t>(h->m.L) * 256 * sizeof(float), true));
+  k_bskip_prefix<<<1, 256, 0, s>>>(h->m.b2f, bskip, h->m.L);
+  h->launches++;
+  DSX_CUDA(cudaGetLastError());
+  h->m.bskip = bskip;
+  h->m.wsr = nullptr;
+  h->m.wsr_sets = 0;
+  if (h->precision == DSX_PREC_FP16S) {
+    const int R = std::max(1, h->sr_sets);
+    __half* wsr;
+    const size_t rows = static_cast<size_t>(R) * h->m.L * kStackSetRowsPerLayer;
+    DSX_TRY(dev_alloc(h, reinterpret_cast<void**>(&wsr), rows * 64 * sizeof(__half), true));
+    dim3 grid(32, h->m.L, R);
+    k_pack_wsr<<<grid, 256, 0, s>>>(h->m.w1f, h->m.w2f, wsr, h->m.L, h->sr_seed);
+    h->launches++;
+    DSX_CUDA(cudaGetLastError());
+    h->m.wsr = wsr;
+    h->m.wsr_sets = R;
+  }
+  return DSX_OK;
+}
+
+template <int WP>
+static int stack_occupancy(dsx_handle* h) {
+  int& cache = h->stack_occ[WP - 1];
+  if (cache == 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kG);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = StackCfg::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaFuncSetAttribute(k_tc_stack<WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg::SMEM_BYTES);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, k_tc_stack<WP>, &cfg);
+    if (e != cudaSuccess) cudaGetLastError();
+    cache = (e == cudaSuccess && n >= 1) ? n : -1;
+  }
+  return cache;
+}
+
+// Can the register-resident stack kernel take this call?  (every tile of an utterance must be co-resident)
+bool tc_stack_usable(dsx_handle* h, const Geom& g) {
+  if (h->stack_kernel == 0 || !h->stack_mode) return false;
+  if (h->precision != DSX_PREC_FP16 && h->precision != DSX_PREC_FP16X2 && h->precision != DSX_PREC_FP16S) return false;
+  const int occ = (h->precision == DSX_PREC_FP16X2) ? stack_occupancy<2>(h) : stack_occupancy<1>(h);
+  h->cluster_occ = occ;
+  return occ > 0 && g.tiles_per_utt <= occ * kG;
+}
+
+// Layers [0, nl) of one evaluation (table row row0, weight set `wset`), one persistent launch per group of utterances.
+int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_b, int wset, cudaStream_t s) {
+  const ModelDev& m = h->m;
+  const bool x2 = (h->precision == DSX_PREC_FP16X2);
+  const bool sr = (h->precision == DSX_PREC_FP16S);
+  if (nl <= 0) return DSX_OK;
+  TcStackParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.tm_w = sr ? h->tm_wsr : h->tm_w;
+  prm.tm_y0 = h->tm_yh[0];
+  prm.tm_ye[0] = h->tm_ye[0];
+  prm.tm_ye[1] = h->tm_ye[1];
+  prm.X = h->ws.X;
+  prm.SKIP = h->ws.SKIP;
+  prm.Y = h->ws.Y;
+  prm.plane_elems = g.frames_padded() * kC;
+  prm.CP = h->ws.CP;
+  prm.cp_prefetch = h->cp_prefetch;
+  prm.b2 = m.b2f;
+  prm.bskip = m.bskip;
+  prm.dtab = h->ws.DTAB + static_cast<size_t>(row0) * m.L * kC;
+  prm.d_row_stride = row_per_b * m.L * kC;
+  prm.T = g.T; prm.Tp = g.Tp; prm.tiles_per_utt = g.tiles_per_utt; prm.tiles = g.tiles; prm.B = g.B;
+  prm.nl = nl; prm.L = m.L; prm.cycle = m.cycle;
+  prm.w_sr = sr ? 1 : 0;
+  prm.w_layer_rows = sr ? kStackSetRowsPerLayer : kRowsPerLayer;
+  prm.w_row0 = sr ? (wset % std::max(1, m.wsr_sets)) * m.L * kStackSetRowsPerLayer : 0;
+  prm.s16 = h->ws.S16;
+  prm.inv_sqrt_l = 1.0f / sqrtf(static_cast<float>(m.L));
+  prm.fast_act = (h->precision == DSX_PREC_FP16) ? 1 : 0;
+  prm.status = h->status_dev;
+  prm.budget_ns = 4000000000ull;
+  prm.trace = h->trace_dev;
+  const int occ = x2 ? stack_occupancy<2>(h) : stack_occupancy<1>(h);
+  const int cap_tiles = occ * kG;
+  const int utt_per_group = cap_tiles / g.tiles_per_utt;
+  DSX_CHECK(utt_per_group >= 1, DSX_E_INVALID, "stack kernel: an utterance of %d tiles does not fit %d co-resident CTAs",
+            g.tiles_per_utt, cap_tiles);
+  DSX_TRY(ensure_flags(h, g.tiles + 2));
+  if (h->flags_geom_b != g.B || h->flags_geom_t != g.T || h->flags_kind != 2) {   // counters are in lockstep only within one geometry
+    DSX_CUDA(cudaMemsetAsync(h->flags_dev, 0, static_cast<size_t>(h->flags_cap) * sizeof(unsigned int), s));
+    h->flag_count = 0;
+    h->flags_geom_b = g.B;
+    h->flags_geom_t = g.T;
+    h->flags_kind = 2;
+  }
+  prm.flags = h->flags_dev;
+  prm.flag_base = h->flag_count;
+  bool& attr_done = h->attr_stack[x2 ? 1 : 0];
+  if (!attr_done) {
+    if (x2) DSX_CUDA(cudaFuncSetAttribute(k_tc_stack<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg::SMEM_BYTES));
+    else DSX_CUDA(cudaFuncSetAttribute(k_tc_stack<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  for (int b0 = 0; b0 < g.B; b0 += utt_per_group) {
+    const int nb = std::min(utt_per_group, g.B - b0);
+    prm.tile0 = b0 * g.tiles_per_utt;
+    prm.tile_end = (b0 + nb) * g.tiles_per_utt;
+    const int grid = (prm.tile_end - prm.tile0 + kG - 1) / kG * kG;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = StackCfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (x2) DSX_CUDA(cudaLaunchKernelEx(&cfg, k_tc_stack<2>, prm));
+    else DSX_CUDA(cudaLaunchKernelEx(&cfg, k_tc_stack<1>, prm));
+    h->launches++;
+    h->stack_launches++;
+  }
+  h->flag_count += static_cast<unsigned int>(kFlagsPerLayer * std::max(nl - 1, 0));
+  return DSX_OK;
+}
+
+}  // namespace dsx

@@ -39,18 +39,9 @@
 #include "dsx_internal.h"
 #include "dsx_ptx.cuh"
 #include "dsx_rng.cuh"
+#include "dsx_tc_common.cuh"
 
 namespace dsx {
-
-constexpr int kC = 256;            // residual / conditioner channels supported by this path
-constexpr int kRowsPerLayer = 80 * 256;   // wpack rows (of 64 fp16) per layer: 64 W1 tiles + 16 W2 tiles
-
-constexpr int kG = 2;                      // cta_group of the layer kernel (cluster of two CTAs)
-constexpr int kUnitBytes = kTile * 128;    // ring unit: 128 rows x 64 fp16 (one A k-block tile, or one CTA's half of a W tile)
-constexpr int kEpiWarps = 8;               // epilogue warps (two per TMEM lane quadrant, split by columns)
-constexpr int kThreads = 128 + kEpiWarps * 32;
-constexpr int kStageRowBytes = 48;         // epilogue-2 transpose staging: 8 fp32 + 16 B pad per row
-constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowBytes;
 
 template <int P>
 struct TcCfg {
@@ -120,65 +111,6 @@ struct TcLayerParams {
   long long* trace;          // debug: [2 CTAs][3 roles][256] clock64 stamps, or nullptr
   int seq;                   // debug: launch sequence number (slot of the entry / exit wall-clock stamps)
 };
-
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
-// sigmoid(g) * tanh(f) = (1 - E2) / ((1 + E1)(1 + E2)), E1 = e^-g, E2 = e^-2f: three MUFU operations instead of four
-// (the gate epilogue is MUFU-bound); absolute error ~2e-7.  f is clamped at -15 (tanh = -1 to 2e-13) so E2 stays finite.
-__device__ __forceinline__ float gate_acc(float g, float f) {
-  const float e1 = ex2_approx(-1.4426950408889634f * g);
-  const float e2 = ex2_approx(-2.8853900817779268f * fmaxf(f, -15.f));
-  return (1.f - e2) * rcp_approx((1.f + e1) * (1.f + e2));
-}
-__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
-
-// Order in which GEMM1 (one tile per tap, P = 3) consumes its 12 k-blocks (k-block = tap*4 + channel block): the
-// centre tap (this tile's own y) first, the halo taps (they need the neighbour tiles' y) last.
-__device__ __forceinline__ int kb_order(int ko) { return ko < 4 ? 4 + ko : (ko < 8 ? ko - 4 : ko); }
-constexpr size_t kCpChunk = 256 * kTile;   // floats of CP per (layer, tile, chunk)
-
-// publish / wait on a tile's counter in global memory (gpu scope)
-__device__ __forceinline__ void flag_publish(unsigned int* f) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
-}
-__device__ __forceinline__ bool flag_wait(const unsigned int* f, unsigned int target, const Watchdog& wd, int code) {
-  uint32_t spins = 0;
-  while (true) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-    if (static_cast<int>(v - target) >= 0) return true;
-    if (((++spins) & 0xff) == 0) {
-      if (*(volatile int*)wd.status != 0) return false;
-      if (globaltimer_ns() > wd.deadline_ns) {
-        atomicCAS(wd.status, 0, code);
-        return false;
-      }
-    }
-  }
-}
-
-// Wait until this tile's counter and its neighbours' (lo / hi may be null) have all reached `target`: the three polls
-// travel to L2 together (relaxed loads), one gpu-scope fence turns the successful observation into an acquire.
-__device__ __forceinline__ bool flag_wait3(const unsigned int* f, const unsigned int* lo, const unsigned int* hi,
-                                           unsigned int target, const Watchdog& wd, int code) {
-  uint32_t spins = 0;
-  while (true) {
-    unsigned int v0, v1 = target, v2 = target;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v0) : "l"(f) : "memory");
-    if (lo) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(lo) : "memory");
-    if (hi) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v2) : "l"(hi) : "memory");
-    if (static_cast<int>(v0 - target) >= 0 && static_cast<int>(v1 - target) >= 0 && static_cast<int>(v2 - target) >= 0) {
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      return true;
-    }
-    if (((++spins) & 0xff) == 0) {
-      if (*(volatile int*)wd.status != 0) return false;
-      if (globaltimer_ns() > wd.deadline_ns) {
-        atomicCAS(wd.status, 0, code);
-        return false;
-      }
-    }
-  }
-}
 
 #define DSX_TRACE(role, slot)                                                              \
   do {                                                                                     \
@@ -1071,6 +1003,7 @@ struct TcHeadParams {
   float* eps;              // [B][M][T] contiguous (TC_WRITE_EPS)
   const float* noise;      // [B][M][T] for this step, or nullptr -> Philox
   unsigned long long seed, offset;
+  int b_off;               // global index of utterance 0 (Philox counters of a sharded batch)
   DdpmCoef c;
   float* X;                // [B][Tp][256]
   __half* Y;               // conv input of layer 0, plane 0; plane 1 at + plane_elems
@@ -1404,7 +1337,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
           } else {
 #pragma unroll
             for (int i4 = 0; i4 < 2; ++i4) {
-              const float4 z4 = philox_normal4(p.seed, p.offset, mel_noise_block(b, m0 + i4 * 4, t, p.M, p.T));
+              const float4 z4 = philox_normal4(p.seed, p.offset, mel_noise_block(b + p.b_off, m0 + i4 * 4, t, p.M, p.T));
               zn[i4 * 4] = z4.x; zn[i4 * 4 + 1] = z4.y; zn[i4 * 4 + 2] = z4.z; zn[i4 * 4 + 3] = z4.w;
             }
           }
@@ -1602,6 +1535,9 @@ int tc_pack_model(dsx_handle* h, cudaStream_t s) {
   h->launches++;
   DSX_CUDA(cudaGetLastError());
   h->m.whead = whead;
+  DSX_TRY(tc_stack_pack(h, s));
+  if (h->m.wsr)
+    DSX_TRY(make_map_2d(&h->tm_wsr, h->m.wsr, static_cast<uint64_t>(h->m.wsr_sets) * h->m.L * kStackSetRowsPerLayer, 128));
   return DSX_OK;
 }
 
@@ -1624,7 +1560,7 @@ static PFN_tmapEncodeTiled get_encode() {
   return fn;
 }
 
-static int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
   PFN_tmapEncodeTiled enc = get_encode();
   DSX_CHECK(enc, DSX_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {64, rows};
@@ -1654,14 +1590,13 @@ static int make_map_act(CUtensorMap* m, const void* base, int ch, int T, int Tp,
 
 int tc_prepare_maps(dsx_handle* h, const Geom& g) {
   const size_t plane = g.frames_padded() * kC;
-  if (h->tm_geom.B == g.B && h->tm_geom.T == g.T && h->tm_base_y == h->ws.Y && h->tm_base_cond == h->ws.CONDH &&
-      h->tm_group == h->tc_group)
-    return DSX_OK;
+  if (h->tm_geom.B == g.B && h->tm_geom.T == g.T && h->tm_epoch == h->ws_epoch && h->tm_group == h->tc_group) return DSX_OK;
   DSX_TRY(make_map_2d(&h->tm_w, h->m.wpack, static_cast<uint64_t>(h->m.L) * kRowsPerLayer, 128));
   for (int buf = 0; buf < 2; ++buf) {
     for (int pl = 0; pl < 2; ++pl)
       DSX_TRY(make_map_act(&h->tm_y[buf][pl], h->ws.Y + (static_cast<size_t>(buf) * 2 + pl) * plane, kC, g.T, g.Tp, g.B));
     DSX_TRY(make_map_act(&h->tm_yh[buf], h->ws.Y + static_cast<size_t>(buf) * 2 * plane, kC, g.T, g.Tp, g.B, kTile + 16));
+    DSX_TRY(make_map_act(&h->tm_ye[buf], h->ws.Y + static_cast<size_t>(buf) * 2 * plane, kC, g.T, g.Tp, g.B, 8));
   }
   for (int pl = 0; pl < 2; ++pl) {
     DSX_TRY(make_map_act(&h->tm_cond[pl], h->ws.CONDH + static_cast<size_t>(pl) * plane, kC, g.T, g.Tp, g.B));
@@ -1669,8 +1604,7 @@ int tc_prepare_maps(dsx_handle* h, const Geom& g) {
   }
   DSX_TRY(make_map_2d(&h->tm_whead, h->m.whead, 32 * 128, 128));
   h->tm_geom = g;
-  h->tm_base_y = h->ws.Y;
-  h->tm_base_cond = h->ws.CONDH;
+  h->tm_epoch = h->ws_epoch;
   h->tm_group = h->tc_group;
   return DSX_OK;
 }
@@ -1726,7 +1660,7 @@ static int cluster_occupancy(dsx_handle* h, int csize) {
   return cache[csize];
 }
 
-static int ensure_flags(dsx_handle* h, int n) {
+int ensure_flags(dsx_handle* h, int n) {
   if (h->flags_cap >= n) return DSX_OK;
   if (h->flags_dev) cudaFree(h->flags_dev);
   h->flags_dev = nullptr;
@@ -1765,7 +1699,8 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
   prm.budget_ns = 4000000000ull;
   prm.trace = h->trace_dev;
   prm.seq = h->trace_seq++;
-  const int P = h->precision;   // DSX_PREC_FP16 = 1, FP16X2 = 2, FP16X3 = 3 == MMA passes
+  const int P = (h->precision == DSX_PREC_FP16S) ? 2 : h->precision;   // DSX_PREC_FP16 = 1, FP16X2 = 2, FP16X3 = 3 == MMA passes
+                                                                        // (FP16S without the stack kernel: the fp16x2 scheme)
   auto launch = [&](int grid) -> int {
     return P == 1 ? launch_tc_layer_t<1>(h, prm, grid, kG, s)
                   : (P == 2 ? launch_tc_layer_t<2>(h, prm, grid, kG, s) : launch_tc_layer_t<3>(h, prm, grid, kG, s));
@@ -1779,11 +1714,12 @@ int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int
   const bool stack = h->stack_mode && (l1 - l0 > 1) && utt_per_group >= 1;
   if (stack) {
     DSX_TRY(ensure_flags(h, g.tiles + 2));
-    if (h->flags_geom_b != g.B || h->flags_geom_t != g.T) {   // counters are in lockstep only within one geometry
+    if (h->flags_geom_b != g.B || h->flags_geom_t != g.T || h->flags_kind != 1) {   // counters are in lockstep only within one geometry
       DSX_CUDA(cudaMemsetAsync(h->flags_dev, 0, static_cast<size_t>(h->flags_cap) * sizeof(unsigned int), s));
       h->flag_count = 0;
       h->flags_geom_b = g.B;
       h->flags_geom_t = g.T;
+      h->flags_kind = 1;
     }
     prm.l0 = l0; prm.l1 = l1;
     prm.flags = h->flags_dev;
@@ -1862,6 +1798,7 @@ int launch_tc_head(dsx_handle* h, const Geom& g, int flags, float* x_state, dsx_
   prm.eps = eps_out;
   prm.noise = noise;
   prm.seed = seed;
+  prm.b_off = h->batch_offset;
   prm.offset = offset;
   prm.c = c;
   prm.X = h->ws.X;

@@ -187,23 +187,28 @@ class DsxInferMixin:
         s.set_schedule({n: getattr(self, n) for n in _capi.SCHEDULE_BUFFERS})
         return s
 
-    def dsx_infer(self, ret, cond, mel2ph, step_noise=None, start_noise=None, seed=None):
-        """Everything after ``self.fs2`` in the infer branch (shallow_diffusion_tts.py:248-275)."""
+    def dsx_infer(self, ret, cond, mel2ph, step_noise=None, start_noise=None, seed=None, fs2_mel=None, x_start=None,
+                  K_step=None, keep_fs2_mel=True, allow_pndm=True):
+        """Everything after ``self.fs2`` in an infer branch: shallow_diffusion_tts.py:248-275 (defaults), the Offline
+        variant :306-322 (fs2_mel given, no mask, DDPM only) and the older sampler diffusion.py:313-320 (x_start given,
+        K_step = num_timesteps)."""
         hp = self._dsx_hparams()
-        _need_cuda(cond, ret['mel_out'])
+        if fs2_mel is None and x_start is None:
+            fs2_mel = ret['mel_out']
+        _need_cuda(cond, fs2_mel, x_start)
         dev = cond.device
         s = self._dsx_ready(dev)
-        ret['fs2_mel'] = ret['mel_out']
-        gaussian = hp.get('gaussian_start') is not None and hp['gaussian_start']
+        if keep_fs2_mel:
+            ret['fs2_mel'] = ret['mel_out']
+        gaussian = x_start is None and hp.get('gaussian_start') is not None and hp['gaussian_start']
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        x_start = None
         if gaussian:
             print('===> gaussion start.')
             x_start = torch.randn((cond.shape[0], 1, self.mel_bins, cond.shape[2]), device=dev)
-        interval = int(hp.get('pndm_speedup') or 0)
-        ret['mel_out'] = s.infer(cond, self.K_step, self.spec_min, self.spec_max,
-                                 fs2_mel=None if gaussian else ret['fs2_mel'], start_noise=start_noise,
+        interval = int(hp.get('pndm_speedup') or 0) if allow_pndm else 0
+        ret['mel_out'] = s.infer(cond, self.K_step if K_step is None else K_step, self.spec_min, self.spec_max,
+                                 fs2_mel=None if x_start is not None else fs2_mel, start_noise=start_noise,
                                  x_start=x_start, step_noise=step_noise, seed=seed, mel2ph=mel2ph,
                                  pndm_interval=interval)
         return ret
@@ -224,29 +229,20 @@ class DsxInferMixin:
         tt = int(t[0])
         s = self._dsx_ready(x.device)
         b = x.shape[0]
-
-        def x_pred(x, noise_t):
-            a_t = self.alphas_cumprod[tt].reshape(1, 1, 1, 1)
-            a_prev = torch.ones_like(a_t) if tt < interval else self.alphas_cumprod[max(tt - interval, 0)].reshape(1, 1, 1, 1)
-            a_t_sq, a_prev_sq = a_t.sqrt(), a_prev.sqrt()
-            x_delta = (a_prev - a_t) * ((1 / (a_t_sq * (a_t_sq + a_prev_sq))) * x - 1 / (
-                a_t_sq * (((1 - a_prev) * a_t).sqrt() + ((1 - a_t) * a_prev).sqrt())) * noise_t)
-            return x + x_delta
-
         full = lambda v: torch.full((b,), v, device=x.device, dtype=torch.long)
         nl = self.noise_list
+        # network evaluations and the multistep algebra both run in libdsx (the conditioner pack + projection are re-used
+        # from the previous step's call: DsxSampler._cond_arg)
         noise_pred = s.diffnet_forward(x, full(tt), cond)
         if len(nl) == 0:
-            noise_pred_prev = s.diffnet_forward(x_pred(x, noise_pred), full(max(tt - interval, 0)), cond)
-            prime = (noise_pred + noise_pred_prev) / 2
-        elif len(nl) == 1:
-            prime = (3 * noise_pred - nl[-1]) / 2
-        elif len(nl) == 2:
-            prime = (23 * noise_pred - 16 * nl[-1] + 5 * nl[-2]) / 12
+            x_mid = s.plms_update(x, [noise_pred], 0, tt, interval)
+            noise_pred_prev = s.diffnet_forward(x_mid, full(max(tt - interval, 0)), cond)
+            out = s.plms_update(x, [noise_pred, noise_pred_prev], 1, tt, interval)
         else:
-            prime = (55 * noise_pred - 59 * nl[-1] + 37 * nl[-2] - 9 * nl[-3]) / 24
+            hist = [noise_pred] + [nl[-1 - i] for i in range(min(len(nl), 3))]
+            out = s.plms_update(x, hist, len(hist), tt, interval)
         nl.append(noise_pred)
-        return x_pred(x, prime)
+        return out
 
 
 class GaussianDiffusion(DsxInferMixin, nn.Module):

@@ -5,6 +5,8 @@ ONE all-gather of the finished mel shards at the end (NCCL over NVLink / NVSwitc
 import torch
 import torch.distributed as dist
 
+from . import _capi
+
 
 def shard_bounds(n_items, world_size, rank):
     """Contiguous, balanced split: the first (n % world) ranks hold one extra item."""
@@ -21,14 +23,21 @@ def shard_batch(tensor, world_size=None, rank=None, dim=0):
 
 
 def all_gather_batch(local, n_items, group=None):
-    """local: this rank's [b_r, ...] shard -> [n_items, ...] on every rank (one collective)."""
+    """local: this rank's [b_r, ...] shard -> [n_items, ...] on every rank (one collective).  Equal shards (n_items % world
+    == 0, the usual case) gather straight into the result; ragged shards go through one padded staging buffer."""
     world = dist.get_world_size(group)
     cap = (n_items + world - 1) // world
-    pad = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    tail = tuple(local.shape[1:])
+    fused = hasattr(dist, "all_gather_into_tensor") and local.is_cuda
+    if n_items % world == 0:
+        out = torch.empty((n_items,) + tail, dtype=local.dtype, device=local.device)
+        src = local.contiguous()
+        dist.all_gather_into_tensor(out, src, group=group) if fused else _all_gather_list(out, src, world, group)
+        return out
+    pad = torch.zeros((cap,) + tail, dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
-    out = torch.empty((world * cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, pad, group=group) if hasattr(dist, "all_gather_into_tensor") and local.is_cuda \
-        else _all_gather_list(out, pad, world, group)
+    out = torch.empty((world * cap,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group) if fused else _all_gather_list(out, pad, world, group)
     parts = []
     for r in range(world):
         lo, hi = shard_bounds(n_items, world, r)
@@ -56,6 +65,15 @@ def sharded_infer(sampler, cond, K_step, spec_min, spec_max, group=None, **kw):
             sl[k] = v[:, lo:hi]
         else:
             sl[k] = v
-    local = sampler.infer(cond[lo:hi], K_step, spec_min, spec_max, **sl) if hi > lo else \
-        torch.zeros((0, cond.shape[2], spec_min.numel()), device=cond.device)
+    if hi > lo:
+        # in-kernel Philox noise is indexed by the GLOBAL utterance number: one seed gives every rank's utterances their own
+        # noise, and the sharded result equals the unsharded one
+        sampler.ensure_weights(cond.device)
+        sampler.set_option(_capi.OPT_BATCH_OFFSET, lo)
+        try:
+            local = sampler.infer(cond[lo:hi], K_step, spec_min, spec_max, **sl)
+        finally:
+            sampler.set_option(_capi.OPT_BATCH_OFFSET, 0)
+    else:
+        local = torch.zeros((0, cond.shape[2], spec_min.numel()), device=cond.device)
     return all_gather_batch(local, B, group)

@@ -49,6 +49,8 @@ class DsxSampler:
         self._wkey = None
         self._skey = None
         self._keep = None
+        self._cond_key = None          # conditioner currently packed in the handle (see _cond_arg)
+        self._cond_hold = None
 
     # -- lifecycle ------------------------------------------------------------------------------
     def close(self):
@@ -70,6 +72,7 @@ class DsxSampler:
             check(lib.dsx_create(device.index if device.index is not None else torch.cuda.current_device(),
                                  ctypes.byref(h)), "dsx_create")
             self._h, self._device, self._wkey, self._skey = h, device, None, None
+            self._cond_key = self._cond_hold = None
         return self._h
 
     def set_precision(self, precision):
@@ -141,6 +144,7 @@ class DsxSampler:
             check(lib.dsx_load_diffnet(h, ctypes.byref(p), M, C, H, L, self._cycle_len(), self.precision,
                                        _stream(device)), "dsx_load_diffnet")
         self._wkey = key
+        self._cond_key = self._cond_hold = None      # (re)loading frees the workspace
         return h
 
     # -- schedule -------------------------------------------------------------------------------
@@ -156,6 +160,21 @@ class DsxSampler:
         check(lib.dsx_set_schedule(self._h, ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p)), T), "dsx_set_schedule")
         self._skey = key
 
+    # -- conditioner cache ---------------------------------------------------------------------
+    def _cond_arg(self, cond, B, T):
+        """Pointer to hand to the C ABI: NULL when the handle already holds the pack + projection of this very
+        conditioner for (B, T) (same storage -- kept alive here so its address cannot be recycled -- same view, same
+        version counter), so per-step callers do not re-run them (reference loop :261-270)."""
+        st = cond.untyped_storage()
+        key = (st.data_ptr(), cond.storage_offset(), tuple(cond.shape), tuple(cond.stride()), cond._version, B, T,
+               self._wkey is not None)
+        if key == self._cond_key:
+            return ctypes.c_void_p(0), key, st
+        return _ptr(cond), key, st
+
+    def _cond_done(self, key, st):
+        self._cond_key, self._cond_hold = key, st
+
     # -- entry points ---------------------------------------------------------------------------
     def diffnet_forward(self, spec, diffusion_step, cond):
         """DiffNet.forward (usr/diff/net.py:107-130): spec [B,1,M,T], step [B] int64, cond [B,H,T]."""
@@ -167,10 +186,13 @@ class DsxSampler:
         cond = cond.float()
         t = diffusion_step.to(torch.int64).contiguous()
         eps = torch.empty((B, 1, M, T), device=dev, dtype=torch.float32)
+        cptr, ckey, chold = self._cond_arg(cond, B, T)
+        self._cond_key = None
         with torch.cuda.device(dev):
-            check(lib.dsx_diffnet_forward(h, _ptr(spec), _strides_bct(spec, (0, 2, 3)), _ptr(t), _ptr(cond),
+            check(lib.dsx_diffnet_forward(h, _ptr(spec), _strides_bct(spec, (0, 2, 3)), _ptr(t), cptr,
                                           _strides_bct(cond, (0, 1, 2)), _ptr(eps), B, T, _stream(dev)),
                   "dsx_diffnet_forward")
+        self._cond_done(ckey, chold)
         return eps
 
     def sample_ddpm(self, x, cond, t_start, n_steps=None, noise=None, seed=0):
@@ -185,9 +207,12 @@ class DsxSampler:
         if noise is not None:
             noise = noise.float().contiguous()
             assert noise.shape == (n_steps, B, 1, M, T), noise.shape
+        cptr, ckey, chold = self._cond_arg(cond, B, T)
+        self._cond_key = None
         with torch.cuda.device(dev):
-            check(lib.dsx_sample_ddpm(h, _ptr(xs), _ptr(cond), _strides_bct(cond, (0, 1, 2)), B, T, t_start, n_steps,
+            check(lib.dsx_sample_ddpm(h, _ptr(xs), cptr, _strides_bct(cond, (0, 1, 2)), B, T, t_start, n_steps,
                                       _ptr(noise), seed, _stream(dev)), "dsx_sample_ddpm")
+        self._cond_done(ckey, chold)
         return xs
 
     def sample_plms(self, x, cond, t_start, interval):
@@ -197,10 +222,27 @@ class DsxSampler:
         B, _, M, T = x.shape
         xs = x.float().contiguous().clone()
         cond = cond.float()
+        cptr, ckey, chold = self._cond_arg(cond, B, T)
+        self._cond_key = None
         with torch.cuda.device(dev):
-            check(lib.dsx_sample_plms(h, _ptr(xs), _ptr(cond), _strides_bct(cond, (0, 1, 2)), B, T, t_start, interval,
+            check(lib.dsx_sample_plms(h, _ptr(xs), cptr, _strides_bct(cond, (0, 1, 2)), B, T, t_start, interval,
                                       _stream(dev)), "dsx_sample_plms")
+        self._cond_done(ckey, chold)
         return xs
+
+    def plms_update(self, x, eps_list, mode, t, interval):
+        """One linear-multistep combination + get_x_pred (shallow_diffusion_tts.py:174-199) -> new x [B,1,M,T]."""
+        _need_cuda(x, *eps_list)
+        dev = x.device
+        B, _, M, T = x.shape
+        xi = x.float().contiguous()
+        es = [e.float().contiguous() for e in eps_list]
+        out = torch.empty_like(xi)
+        arr = (ctypes.c_void_p * 4)(*([e.data_ptr() for e in es] + [None] * (4 - len(es))))
+        with torch.cuda.device(dev):
+            check(lib.dsx_plms_update(self._h, _ptr(out), _ptr(xi), ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p)), mode,
+                                      int(t), int(interval), B, T, _stream(dev)), "dsx_plms_update")
+        return out
 
     def infer(self, cond, K_step, spec_min, spec_max, fs2_mel=None, start_noise=None, x_start=None,
               step_noise=None, seed=0, mel2ph=None, pndm_interval=0):
@@ -217,6 +259,7 @@ class DsxSampler:
         smax = spec_max.float().reshape(-1).contiguous()
         m2p = None if mel2ph is None else mel2ph.to(torch.int64).contiguous()
         out = torch.empty((B, T, M), device=dev, dtype=torch.float32)
+        self._cond_key = None
         with torch.cuda.device(dev):
             check(lib.dsx_infer(h, _ptr(cond), _strides_bct(cond, (0, 1, 2)), _ptr(fs2_mel), _ptr(start_noise),
                                 _ptr(x_start), _ptr(step_noise), seed, _ptr(m2p), _ptr(smin), _ptr(smax), B, T, K_step,
@@ -237,6 +280,7 @@ class DsxSampler:
         m2p = None if mel2ph is None else mel2ph.to(torch.int64).contiguous()
         if out is None:
             out = torch.empty((B, T, M), dtype=torch.float32).pin_memory()
+        self._cond_key = None
         with torch.cuda.device(dev):
             check(lib.dsx_infer_host(h, _ptr(cond), _strides_bct(cond, (0, 1, 2)), _ptr(fs2_mel), _ptr(x_start), seed,
                                      _ptr(m2p), _ptr(smin), _ptr(smax), B, T, K_step, pndm_interval, _ptr(out),

@@ -43,7 +43,11 @@ enum {
   DSX_PREC_FP16 = 1,      /* tcgen05 kind::f16, fp16 operands, fp32 accumulate (fast mode)   */
   DSX_PREC_FP16X2 = 2,    /* tcgen05, weights as hi+lo fp16 pairs, running activations fp16: 2 MMA passes;
                              max |d| ~2e-4 after 100 steps (default parity mode)                               */
-  DSX_PREC_FP16X3 = 3     /* tcgen05, hi+lo fp16 split of both operands, 3 MMAs (fp32-equivalent)*/
+  DSX_PREC_FP16X3 = 3,    /* tcgen05, hi+lo fp16 split of both operands, 3 MMAs (fp32-equivalent)*/
+  DSX_PREC_FP16S = 4      /* tcgen05, ONE MMA pass; the weights are rounded to fp16 stochastically into R sets
+                             (DSX_OPT_SR_SETS, default 64) and evaluation j of a sampling loop uses set j % R, so the weight
+                             rounding error is unbiased and decorrelated across diffusion steps instead of accumulating:
+                             max |d| ~3e-4 after 100 steps at half the MMA work of FP16X2 */
 };
 
 typedef struct dsx_handle dsx_handle;
@@ -122,6 +126,21 @@ int dsx_set_schedule(dsx_handle* h, const float* const* bufs, int T);
 int dsx_diffnet_forward(dsx_handle* h, const float* x, dsx_strides xs, const int64_t* t,
                         const float* cond, dsx_strides cs, float* eps, int B, int T, void* stream);
 
+/* Conditioner of the following calls: packs cond [B,H,T] (any strides) and computes the step-independent
+ * conditioner_projection of every residual layer (usr/diff/net.py:56,70) once.  Every entry point below that takes `cond`
+ * does the same when the pointer is non-NULL and accepts cond == NULL to re-use the conditioner already set for the same
+ * (B, T) -- for callers that drive the sampling loop themselves, one p_sample / p_sample_plms / DiffNet.forward per call
+ * (usr/diff/shallow_diffusion_tts.py:159-204), so that the pack + projection are paid once per batch, not once per step. */
+int dsx_set_cond(dsx_handle* h, const float* cond, dsx_strides cs, int B, int T, void* stream);
+
+/* Replaces: the linear-multistep combination + get_x_pred of ONE p_sample_plms step
+ * (usr/diff/shallow_diffusion_tts.py:174-199), fp32 in the reference's operation order, for callers that keep the eps
+ * history themselves (self.noise_list).  eps: HOST array of device pointers, most recent first; all tensors contiguous
+ * [B,1,M,T].  mode 0: x_out = phi(x_in, eps[0], t) (the warm-up prediction); 1: eps' = (eps[0] + eps[1]) / 2;
+ * 2: (3 e0 - e1) / 2; 3: (23 e0 - 16 e1 + 5 e2) / 12; 4: (55 e0 - 59 e1 + 37 e2 - 9 e3) / 24; then x_out = phi(x_in, eps', t). */
+int dsx_plms_update(dsx_handle* h, float* x_out, const float* x_in, const float* const* eps, int mode, int t,
+                    int interval, int B, int T, void* stream);
+
 /* Replaces: the DDPM loop `for i in reversed(range(0, t)): x = p_sample(x, i, cond)`
  * (usr/diff/shallow_diffusion_tts.py:159-166, 269-270): n_steps steps t_start-1 ... t_start-n_steps.
  * x_inout: contiguous [B,1,M,T], overwritten with the result.  noise: contiguous
@@ -168,7 +187,8 @@ enum {
                                    option was set (CUDA events on the launching stream; synchronises)     */
   DSX_INFO_LAYER_KERNEL_LAUNCHES = 6, /* number of (start, stop) brackets = evaluations profiled */
   DSX_INFO_STACK_MODE = 7,
-  DSX_INFO_CLUSTER_OCCUPANCY = 8 /* co-resident CTA pairs of the layer kernel reported by the driver */
+  DSX_INFO_CLUSTER_OCCUPANCY = 8, /* co-resident CTA pairs of the layer kernel reported by the driver */
+  DSX_INFO_STACK_KERNEL_LAUNCHES = 9 /* launches of the register-resident stack kernel (dsx_stack.cu) so far */
 };
 /* Tuning knobs (tests exercise every variant): */
 int dsx_set_option(dsx_handle* h, int what, int64_t value);
@@ -178,8 +198,13 @@ enum {
                                hoisted conditioner projection HBM -> L2 half a layer ahead of the gate epilogue */
   DSX_OPT_PROFILE = 2,      /* 1: bracket the residual-layer kernel(s) of every evaluation with CUDA events; 2: bracket the
                                head / update kernel of every DDPM step instead; 0: off.  Setting it resets the sums */
-  DSX_OPT_STACK_MODE = 3    /* 1 (default): all residual layers of an evaluation in ONE persistent launch whenever every
+  DSX_OPT_STACK_MODE = 3,   /* 1 (default): all residual layers of an evaluation in ONE persistent launch whenever every
                                128-frame tile can own an SM at once (tiles <= co-resident CTAs); 0: one launch per layer */
+  DSX_OPT_STACK_KERNEL = 4, /* 1 (default): the register-resident stack kernel (residual stream in registers, conv input in
+                               shared memory, skip sum in tensor memory) for FP16 / FP16X2 / FP16S; 0: the round-1 layer kernel */
+  DSX_OPT_SR_SETS = 5,      /* number of stochastically rounded weight sets of DSX_PREC_FP16S; set before dsx_load_diffnet */
+  DSX_OPT_BATCH_OFFSET = 6  /* global index of this call's utterance 0: the in-kernel Philox noise of utterance b is drawn for
+                               index (offset + b), so a batch sharded over ranks (one seed) reproduces the unsharded noise */
 };
 
 /* Debug taps for layer-by-layer parity (tests only): copies internal fp32 frames-major

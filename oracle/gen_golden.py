@@ -253,6 +253,167 @@ def main():
              spec_min=smin.numpy(), spec_max=smax.numpy(), noise_seed=44,
              noise_checksum=np.float64(noise.double().sum().item()))
 
+    # ---- 6. BASELINE config 3 class: full T = K = 1000 DDPM (beta <= 0.02), dilation cycle 4, injected noise ---
+    betas = O.linear_beta_schedule(1000, 0.02)
+    S = O.make_schedule(betas)
+    net = make_ref_net(ns, 0, 4)
+    sd = O.build_state_dict(0, dilation_cycle_length=4)
+    gd = make_ref_gd(ns, net, betas, 1000)
+    B, T, K = 1, 96, 1000
+    cond = rs_normal(51, (B, 256, T))
+    xT = rs_normal(52, (B, 1, 80, T))
+    noise = rs_normal(53, (K, B, 1, 80, T))
+    feed["i"] = 0
+
+    def fake_noise_like3(shape, device, repeat=False):
+        n = noise[feed["i"]]
+        feed["i"] += 1
+        return n
+
+    sdt.noise_like = fake_noise_like3
+    try:
+        x = xT
+        mids = {}
+        with torch.no_grad():
+            for i in reversed(range(K)):
+                x = gd.p_sample(x, torch.full((B,), i, dtype=torch.long), cond)
+                if i in (900, 500):
+                    mids[f"x_after_t{i}"] = x.numpy().copy()
+            xo = O.sample_ddpm(sd, S, xT, cond, K, noise, 4)
+        d = (x - xo).abs().max().item()
+        assert d <= 5e-5, d
+        report["ddpm1000_oracle_vs_ref"] = d
+        np.savez(os.path.join(OUT, "ddpm_T1000_cycle4.npz"), cond=cond.numpy(), xT=xT.numpy(), x0=x.numpy(), noise_seed=53,
+                 noise_checksum=np.float64(noise.double().sum().item()), **mids,
+                 weights_fingerprint=np.float64(fingerprint(net.state_dict())))
+    finally:
+        sdt.noise_like = orig_noise_like
+
+    # ---- 7. PLMS with a bounded state: shallow start K_step = 300 of the T = 1000 schedule (alpha_cumprod[299] ~ 0.4, so the
+    #         un-clamped state stays O(1) and an ABSOLUTE per-bin bound applies), intervals 40 and 10, B = 2 ---------------
+    gd = make_ref_gd(ns, net, betas, 300)
+    B, T, K = 2, 96, 300
+    cond = rs_normal(61, (B, 256, T))
+    xT = rs_normal(62, (B, 1, 80, T))
+    outs = {}
+    for interval in (40, 10):
+        ref_rows = []
+        for b in range(B):
+            gd.noise_list = deque(maxlen=4)
+            x = xT[b:b + 1]
+            with torch.no_grad():
+                for i in reversed(range(0, K, interval)):
+                    x = gd.p_sample_plms(x, torch.full((1,), i, dtype=torch.long), interval, cond[b:b + 1])
+            ref_rows.append(x)
+        ref = torch.cat(ref_rows, 0)
+        with torch.no_grad():
+            xo1 = torch.cat([O.sample_plms(sd, S, xT[b:b + 1], cond[b:b + 1], K, interval, 4) for b in range(B)], 0)
+        assert torch.equal(ref, xo1)
+        report[f"plms_bounded{interval}_absmax"] = ref.abs().max().item()
+        outs[f"x0_interval{interval}"] = ref.numpy()
+    np.savez(os.path.join(OUT, "plms_K300_cycle4.npz"), cond=cond.numpy(), xT=xT.numpy(), **outs,
+             weights_fingerprint=np.float64(fingerprint(net.state_dict())))
+
+    # ---- 8. the older sampler usr/diff/diffusion.py (usr/task.py:18): cosine schedule, gaussian start, full-T DDPM, no mask ---
+    import importlib
+    cwd = os.getcwd()
+    os.chdir(ref_bridge.REF_ROOT)
+    try:
+        dmod = importlib.import_module("usr.diff.diffusion")
+    finally:
+        os.chdir(cwd)
+    net = make_ref_net(ns, 0, 1)
+    sd = O.build_state_dict(0)
+    enc = ns.TokenTextEncoder(None, vocab_list=["a", "b", "c"], replace_oov=",")
+    gd_old = dmod.GaussianDiffusion(enc, 80, net, timesteps=100, loss_type="l1", spec_min=ns.hparams["spec_min"],
+                                    spec_max=ns.hparams["spec_max"]).eval()
+    Sc = O.make_schedule(O.cosine_beta_schedule(100))
+    for bname in O.SCHEDULE_BUFFERS:
+        assert torch.equal(getattr(gd_old, bname), Sc[bname]), bname
+    B, T, K = 2, 80, 100
+    dec_inp = rs_normal(71, (B, T, 256))
+    x_start = rs_normal(72, (B, 1, 80, T))
+    noise = rs_normal(73, (K, B, 1, 80, T))
+
+    class StubFS2Old(torch.nn.Module):
+        def forward(self, *a, **kw):
+            return {"decoder_inp": dec_inp.clone()}
+
+    class TorchProxy:           # torch, except randn(shape, device=...) -> the fixture's start noise
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+        def randn(self, *a, **kw):
+            return x_start.clone()
+
+    gd_old.fs2 = StubFS2Old()
+    feed["i"] = 0
+
+    def fake_noise_like4(shape, device, repeat=False):
+        n = noise[feed["i"]]
+        feed["i"] += 1
+        return n
+
+    orig_nl, orig_torch = dmod.noise_like, dmod.torch
+    dmod.noise_like, dmod.torch = fake_noise_like4, TorchProxy()
+    try:
+        with torch.no_grad():
+            ret = gd_old(torch.zeros(B, 5, dtype=torch.long), mel2ph=torch.ones(B, T, dtype=torch.long), infer=True)
+    finally:
+        dmod.noise_like, dmod.torch = orig_nl, orig_torch
+    with torch.no_grad():
+        mo = O.infer_loop(sd, Sc, dec_inp.transpose(1, 2), K, gd_old.spec_min, gd_old.spec_max, x_start=x_start,
+                          step_noise=noise)
+    d = (ret["mel_out"] - mo).abs().max().item()
+    assert d <= 1e-4, d
+    report["old_sampler_cosine_oracle_vs_ref"] = d
+    np.savez(os.path.join(OUT, "old_sampler_cosine_K100.npz"), decoder_inp=dec_inp.numpy(), x_start=x_start.numpy(),
+             mel_out=ret["mel_out"].numpy(), spec_min=gd_old.spec_min.numpy(), spec_max=gd_old.spec_max.numpy(), noise_seed=73,
+             noise_checksum=np.float64(noise.double().sum().item()))
+
+    # ---- 9. OfflineGaussianDiffusion.forward(infer=True) (usr/diffsinger_task.py:128): fs2 mel handed in through ref_mels[1],
+    #         shallow start, DDPM, no mel2ph mask ------------------------------------------------------------------------------
+    betas = O.linear_beta_schedule(100, 0.06)
+    S = O.make_schedule(betas)
+    K_step = 51
+    gd_off = sdt.OfflineGaussianDiffusion(enc, 80, net, timesteps=100, K_step=K_step, loss_type="l1", betas=torch.tensor(betas),
+                                          spec_min=ns.hparams["spec_min"], spec_max=ns.hparams["spec_max"]).eval()
+    dec_inp = rs_normal(81, (B, T, 256))
+    fs2_mel = rs_normal(82, (B, T, 80)) * 1.5 - 2.5
+    start_noise = rs_normal(83, (B, 1, 80, T))
+    noise = rs_normal(84, (K_step, B, 1, 80, T))
+
+    class StubFS2Off(torch.nn.Module):
+        def forward(self, *a, **kw):
+            return {"decoder_inp": dec_inp.clone()}
+
+    gd_off.fs2 = StubFS2Off()
+    feed["i"] = 0
+
+    def fake_noise_like5(shape, device, repeat=False):
+        n = noise[feed["i"]]
+        feed["i"] += 1
+        return n
+
+    sdt.noise_like = fake_noise_like5
+    sdt.torch.randn_like = lambda x: start_noise
+    try:
+        with torch.no_grad():
+            ret = gd_off(torch.zeros(B, 5, dtype=torch.long), mel2ph=torch.ones(B, T, dtype=torch.long),
+                         ref_mels=[torch.zeros(B, T, 80), fs2_mel], infer=True)
+    finally:
+        sdt.noise_like = orig_noise_like
+        sdt.torch.randn_like = orig_randn_like
+    with torch.no_grad():
+        mo = O.infer_loop(sd, S, dec_inp.transpose(1, 2), K_step, gd_off.spec_min, gd_off.spec_max, fs2_mel=fs2_mel,
+                          start_noise=start_noise, step_noise=noise)
+    d = (ret["mel_out"] - mo).abs().max().item()
+    assert d <= 1e-4, d
+    report["offline_forward_oracle_vs_ref"] = d
+    np.savez(os.path.join(OUT, "offline_forward_K51.npz"), decoder_inp=dec_inp.numpy(), fs2_mel=fs2_mel.numpy(),
+             start_noise=start_noise.numpy(), mel_out=ret["mel_out"].numpy(), spec_min=gd_off.spec_min.numpy(),
+             spec_max=gd_off.spec_max.numpy(), noise_seed=84, noise_checksum=np.float64(noise.double().sum().item()))
+
     for k, v in report.items():
         print(f"{k}: {v:.3e}")
     print("golden vectors written to", OUT)

@@ -52,7 +52,7 @@ def test_tcgen05_selftests(dsx):
 
 
 @pytest.mark.parametrize("cycle", [1, 4])
-@pytest.mark.parametrize("prec,group", [("fp32", None), ("fp16x3", 2), ("fp16x2", 2), ("fp16", 2)])
+@pytest.mark.parametrize("prec,group", [("fp32", None), ("fp16x3", 2), ("fp16x2", 2), ("fp16s", 2), ("fp16", 2)])
 def test_diffnet_forward_golden(dsx, cycle, prec, group):
     g = golden(f"diffnet_fwd_cycle{cycle}.npz")
     s, dev = make_sampler(dsx, cycle, prec, group=group)
@@ -61,7 +61,7 @@ def test_diffnet_forward_golden(dsx, cycle, prec, group):
     B, _, M, T = g["spec"].shape
     x_last = s.debug_read(0, B, T).cpu().numpy()       # [B,T,C]
     skip = s.debug_read(1, B, T).cpu().numpy()
-    tol = {"fp32": 2e-4, "fp16x3": 2e-4, "fp16x2": 1.5e-3, "fp16": 1e-2}[prec]
+    tol = {"fp32": 2e-4, "fp16x3": 2e-4, "fp16x2": 1.5e-3, "fp16s": 3e-3, "fp16": 1e-2}[prec]
     assert np.abs(eps - g["eps"]).max() < tol
     assert np.abs(x_last[1].T - g["x20_b1"]).max() < tol * 5
     assert np.abs(skip[0].T - g["skip_sum_b0"]).max() < tol * 20     # |skip_sum| ~ 10
@@ -74,7 +74,7 @@ def test_diffnet_forward_golden(dsx, cycle, prec, group):
     s.close()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "fp16x3", "fp16x2", "fp16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp16x3", "fp16x2", "fp16s", "fp16"])
 def test_ddpm_steps_and_loop_golden(dsx, prec):
     g = golden("ddpm_lj_K100.npz")
     S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
@@ -162,6 +162,102 @@ def test_infer_forward_golden(dsx, prec):
     print(f"infer forward {prec}: max {d.max():.3e}")
     assert d.max() < 3e-3          # denormalised domain: (spec_max - spec_min)/2 ~ 2.7x the normalised error
     assert np.all(mel[1, 60:] == 0)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16x3", "fp16x2", "fp16s"])
+def test_ddpm_full_T1000_golden(dsx, prec):
+    """BASELINE config 3 class: T = K = 1000 DDPM (beta <= 0.02), dilation cycle 4, injected noise: ten times more steps
+    for the coherent part of the operand rounding error to accumulate over."""
+    g = golden("ddpm_T1000_cycle4.npz")
+    S = O.make_schedule(O.linear_beta_schedule(1000, 0.02))
+    s, dev = make_sampler(dsx, 4, prec, S)
+    cond, xT = torch.from_numpy(g["cond"]).to(dev), torch.from_numpy(g["xT"]).to(dev)
+    noise = rs_normal(int(g["noise_seed"]), (1000,) + tuple(g["xT"].shape)).to(dev)
+    x100 = s.sample_ddpm(xT, cond, 1000, 100, noise=noise[:100]).cpu().numpy()       # after t = 900
+    assert np.abs(x100 - g["x_after_t900"]).max() < PARITY_TOL
+    x0 = s.sample_ddpm(xT, cond, 1000, 1000, noise=noise).cpu().numpy()
+    d = np.abs(x0 - g["x0"])
+    print(f"ddpm T=K=1000 {prec}: max {d.max():.3e} MAE {d.mean():.3e}")
+    assert d.max() < PARITY_TOL
+    s.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16x3", "fp16x2", "fp16s"])
+def test_plms_bounded_state_absolute_tolerance(dsx, prec):
+    """PNDM from a shallow start (K_step = 300 of the T = 1000 schedule): the un-clamped state stays O(1) (max |x| ~ 6),
+    so the north-star bound |d| < 1e-3 is applied as an ABSOLUTE per-bin bound, batched B = 2, intervals 40 and 10."""
+    g = golden("plms_K300_cycle4.npz")
+    S = O.make_schedule(O.linear_beta_schedule(1000, 0.02))
+    s, dev = make_sampler(dsx, 4, prec, S)
+    cond, xT = torch.from_numpy(g["cond"]).to(dev), torch.from_numpy(g["xT"]).to(dev)
+    for interval in (40, 10):
+        out = s.sample_plms(xT, cond, 300, interval).cpu().numpy()
+        d = np.abs(out - g[f"x0_interval{interval}"])
+        print(f"plms K=300 interval {interval} {prec}: max {d.max():.3e} (max |ref| {np.abs(g[f'x0_interval{interval}']).max():.2f})")
+        assert d.max() < PARITY_TOL
+    s.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16x2", "fp16s"])
+def test_old_sampler_cosine_golden(dsx, prec):
+    """usr/diff/diffusion.py:313-320 (the sampler usr/task.py builds): gaussian start, full-T DDPM on the cosine schedule,
+    denorm_spec, no mel2ph mask -- served by dsx_infer with x_start."""
+    g = golden("old_sampler_cosine_K100.npz")
+    S = O.make_schedule(O.cosine_beta_schedule(100))
+    s, dev = make_sampler(dsx, 1, prec, S)
+    B, T, _ = g["decoder_inp"].shape
+    noise = rs_normal(int(g["noise_seed"]), (100, B, 1, 80, T)).to(dev)
+    cond = torch.from_numpy(g["decoder_inp"]).to(dev).transpose(1, 2)
+    mel = s.infer(cond, 100, torch.from_numpy(g["spec_min"]).to(dev), torch.from_numpy(g["spec_max"]).to(dev),
+                  x_start=torch.from_numpy(g["x_start"]).to(dev), step_noise=noise).cpu().numpy()
+    d = np.abs(mel - g["mel_out"])
+    print(f"old sampler (cosine) {prec}: max {d.max():.3e}")
+    assert d.max() < 3e-3          # denormalised domain: (spec_max - spec_min) / 2 ~ 2.7x the normalised error
+    s.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16x2", "fp16s"])
+def test_offline_forward_golden(dsx, prec):
+    """OfflineGaussianDiffusion.forward(infer=True) (shallow_diffusion_tts.py:291-323): shallow start from the mel passed
+    in ref_mels[1], DDPM K = 51, denorm, no mask."""
+    g = golden("offline_forward_K51.npz")
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    s, dev = make_sampler(dsx, 1, prec, S)
+    B, T, _ = g["decoder_inp"].shape
+    noise = rs_normal(int(g["noise_seed"]), (51, B, 1, 80, T)).to(dev)
+    cond = torch.from_numpy(g["decoder_inp"]).to(dev).transpose(1, 2)
+    mel = s.infer(cond, 51, torch.from_numpy(g["spec_min"]).to(dev), torch.from_numpy(g["spec_max"]).to(dev),
+                  fs2_mel=torch.from_numpy(g["fs2_mel"]).to(dev), start_noise=torch.from_numpy(g["start_noise"]).to(dev),
+                  step_noise=noise).cpu().numpy()
+    d = np.abs(mel - g["mel_out"])
+    print(f"offline forward {prec}: max {d.max():.3e}")
+    assert d.max() < 3e-3
+    s.close()
+
+
+@pytest.mark.parametrize("prec", ["fp16x2", "fp16s"])
+def test_full_size_loop_against_oracle(dsx, prec):
+    """The headline shape (BASELINE config 2: B = 16, T = 1024, 128 tiles = every tile of the persistent stack co-resident):
+    K = 8 DDPM steps with injected noise, compared with the CPU oracle on two of the utterances (utterances are
+    independent, so the oracle runs on those two alone)."""
+    B, T, K = 16, 1024, 8
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    s, dev = make_sampler(dsx, 1, prec, S)
+    gen = torch.Generator().manual_seed(4321)
+    cond = torch.randn(B, T, 256, generator=gen).transpose(1, 2)
+    xT = torch.randn(B, 1, 80, T, generator=gen)
+    noise = torch.randn(K, B, 1, 80, T, generator=gen)
+    out = s.sample_ddpm(xT.to(dev), cond.to(dev), 100, K, noise=noise.to(dev)).cpu()
+    sd = O.build_state_dict(0)
+    for b in (0, 9):
+        ref = xT[b:b + 1]
+        with torch.no_grad():
+            for j, t in enumerate(reversed(range(100 - K, 100))):
+                ref = O.p_sample(sd, S, ref, t, cond[b:b + 1], noise[j, b:b + 1])
+        d = (out[b:b + 1] - ref).abs()
+        print(f"full-size loop {prec} utterance {b}: max {d.max():.3e} MAE {d.mean():.3e}")
+        assert d.max() < PARITY_TOL
+    s.close()
 
 
 def test_strided_inputs(dsx):

@@ -84,3 +84,59 @@ def test_infer_forward_shallow_start_with_mask():
                            mel2ph=torch.from_numpy(g["mel2ph"]))
     assert np.abs(mel.numpy() - g["mel_out"]).max() <= 1e-4
     assert np.all(mel.numpy()[1, 60:] == 0)           # masked frames (mel2ph == 0)
+
+
+def test_ddpm_full_T1000_loop():
+    """BASELINE config 3 class: T = K = 1000, beta <= 0.02, dilation cycle 4."""
+    g = golden("ddpm_T1000_cycle4.npz")
+    sd = O.build_state_dict(0, dilation_cycle_length=4)
+    S = O.make_schedule(O.linear_beta_schedule(1000, 0.02))
+    cond, xT = torch.from_numpy(g["cond"]), torch.from_numpy(g["xT"])
+    noise = rs_normal(int(g["noise_seed"]), (1000,) + tuple(xT.shape))
+    assert abs(float(noise.double().sum()) - float(g["noise_checksum"])) < 1e-6
+    x = xT
+    with torch.no_grad():
+        for j, t in enumerate(reversed(range(1000))):
+            x = O.p_sample(sd, S, x, t, cond, noise[j], 4)
+            if t in (900, 500):
+                assert np.abs(x.numpy() - g[f"x_after_t{t}"]).max() <= 5e-5, t
+    assert np.abs(x.numpy() - g["x0"]).max() <= 5e-5
+
+
+def test_plms_bounded_state_fixture():
+    g = golden("plms_K300_cycle4.npz")
+    sd = O.build_state_dict(0, dilation_cycle_length=4)
+    S = O.make_schedule(O.linear_beta_schedule(1000, 0.02))
+    cond, xT = torch.from_numpy(g["cond"]), torch.from_numpy(g["xT"])
+    for interval in (40, 10):
+        with torch.no_grad():
+            x0 = torch.cat([O.sample_plms(sd, S, xT[b:b + 1], cond[b:b + 1], 300, interval, 4) for b in range(2)], 0)
+        assert np.array_equal(x0.numpy(), g[f"x0_interval{interval}"])
+        assert np.abs(g[f"x0_interval{interval}"]).max() < 10       # bounded: an absolute tolerance is meaningful
+
+
+def test_old_sampler_cosine_schedule():
+    """usr/diff/diffusion.py:313-320: gaussian start, full-T DDPM on the cosine schedule, denorm, no mask."""
+    g = golden("old_sampler_cosine_K100.npz")
+    sd = O.build_state_dict(0)
+    S = O.make_schedule(O.cosine_beta_schedule(100))
+    B, T, _ = g["decoder_inp"].shape
+    noise = rs_normal(int(g["noise_seed"]), (100, B, 1, 80, T))
+    with torch.no_grad():
+        mel = O.infer_loop(sd, S, torch.from_numpy(g["decoder_inp"]).transpose(1, 2), 100, torch.from_numpy(g["spec_min"]),
+                           torch.from_numpy(g["spec_max"]), x_start=torch.from_numpy(g["x_start"]), step_noise=noise)
+    assert np.abs(mel.numpy() - g["mel_out"]).max() <= 1e-4
+
+
+def test_offline_forward():
+    """OfflineGaussianDiffusion.forward(infer=True), usr/diff/shallow_diffusion_tts.py:291-323."""
+    g = golden("offline_forward_K51.npz")
+    sd = O.build_state_dict(0)
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    B, T, _ = g["decoder_inp"].shape
+    noise = rs_normal(int(g["noise_seed"]), (51, B, 1, 80, T))
+    with torch.no_grad():
+        mel = O.infer_loop(sd, S, torch.from_numpy(g["decoder_inp"]).transpose(1, 2), 51, torch.from_numpy(g["spec_min"]),
+                           torch.from_numpy(g["spec_max"]), fs2_mel=torch.from_numpy(g["fs2_mel"]),
+                           start_noise=torch.from_numpy(g["start_noise"]), step_noise=noise)
+    assert np.abs(mel.numpy() - g["mel_out"]).max() <= 1e-4

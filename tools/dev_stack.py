@@ -1,0 +1,195 @@
+"""Development checks of the register-resident stack kernel (dsx_stack.cu) on a GPU box.
+
+    python tools/dev_stack.py parity      # golden / oracle parity of every mode, old kernel vs new kernel
+    python tools/dev_stack.py timing      # config-2 loop timings per mode and kernel
+    python tools/dev_stack.py trace       # clock64 timeline of one evaluation (CTA 0 / 1)
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import diffsinger_b200 as dsx  # noqa: E402
+from diffsinger_b200 import _capi  # noqa: E402
+from oracle import diffnet_oracle as O  # noqa: E402  (checker only)
+from conftest import HP, golden, rs_normal  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+
+
+def make(cycle, prec, stack_kernel=1, schedule=None, sets=None):
+    hp = dict(HP, dilation_cycle_length=cycle)
+    torch.manual_seed(0)
+    net = dsx.DiffNet(80, hparams=hp)
+    torch.nn.init.normal_(net.output_projection.weight, std=0.02)
+    net = net.to(DEV).eval()
+    s = dsx.DsxSampler(net, prec, cycle)
+    s._handle(DEV)
+    if sets is not None:
+        s.set_option(_capi.OPT_SR_SETS, sets)
+    s.ensure_weights(DEV)
+    s.set_option(_capi.OPT_STACK_KERNEL, stack_kernel)
+    if schedule is not None:
+        s.set_schedule(schedule)
+    return s
+
+
+def quick():
+    """first contact: one evaluation of the new kernel per mode against the golden vectors; aborts on the first failure"""
+    g = golden("diffnet_fwd_cycle4.npz")
+    spec, cond, t = (torch.from_numpy(g[k]).to(DEV) for k in ("spec", "cond", "t"))
+    B, _, M, T = g["spec"].shape
+    for prec in ("fp16x2", "fp16s", "fp16"):
+        s = make(4, prec, 1)
+        eps = s.diffnet_forward(spec, t, cond).cpu().numpy()
+        x_last = s.debug_read(0, B, T).cpu().numpy()
+        skip = s.debug_read(1, B, T).cpu().numpy()
+        print(f"quick {prec}: eps {np.abs(eps - g['eps']).max():.3e} x20 {np.abs(x_last[1].T - g['x20_b1']).max():.3e} "
+              f"skip {np.abs(skip[0].T - g['skip_sum_b0']).max():.3e} stack launches {s.info(_capi.INFO_STACK_KERNEL_LAUNCHES)}",
+              flush=True)
+        s.close()
+
+
+def parity():
+    rc, rep = dsx.selftest(0)
+    print("selftest", rc, flush=True)
+    res = {}
+    for cycle in (1, 4):
+        g = golden(f"diffnet_fwd_cycle{cycle}.npz")
+        spec, cond, t = (torch.from_numpy(g[k]).to(DEV) for k in ("spec", "cond", "t"))
+        B, _, M, T = g["spec"].shape
+        for prec, sk in (("fp16x2", 0), ("fp16x2", 1), ("fp16s", 1), ("fp16", 1), ("fp16", 0)):
+            s = make(cycle, prec, sk)
+            try:
+                eps = s.diffnet_forward(spec, t, cond).cpu().numpy()
+                x_last = s.debug_read(0, B, T).cpu().numpy()
+                skip = s.debug_read(1, B, T).cpu().numpy()
+                s.set_layer_limit(1)
+                s.diffnet_forward(spec, t, cond)
+                x1 = s.debug_read(0, B, T).cpu().numpy()
+                s.set_layer_limit(-1)
+                r = dict(eps=float(np.abs(eps - g["eps"]).max()), x20=float(np.abs(x_last[1].T - g["x20_b1"]).max()),
+                         skip=float(np.abs(skip[0].T - g["skip_sum_b0"]).max()), x1=float(np.abs(x1[0].T - g["x1_b0"]).max()),
+                         launches=s.info(1))
+            except Exception as e:  # noqa: BLE001
+                r = dict(error=str(e))
+            res[f"fwd_c{cycle}_{prec}_k{sk}"] = r
+            print(f"fwd cycle{cycle} {prec} stack_kernel={sk}: {r}", flush=True)
+            s.close()
+    # ragged shapes: new kernel vs old kernel (fp16x2: same operands, different accumulation order)
+    for B, T in ((1, 96), (3, 333), (1, 300), (2, 1000), (40, 520), (5, 128), (2, 129)):
+        outs = {}
+        for sk in (0, 1):
+            s = make(4, "fp16x2", sk)
+            x, cond = rs_normal(40 + B, (B, 1, 80, T)).to(DEV), rs_normal(50 + T, (B, 256, T)).to(DEV)
+            t = torch.full((B,), 7, dtype=torch.long, device=DEV)
+            try:
+                a = s.diffnet_forward(x, t, cond).cpu()
+                b = s.diffnet_forward(x, t + 1, cond).cpu()
+                a2 = s.diffnet_forward(x, t, cond).cpu()
+                outs[sk] = (a, b, bool(torch.equal(a, a2)))
+            except Exception as e:  # noqa: BLE001
+                outs[sk] = str(e)
+            s.close()
+        if isinstance(outs[0], tuple) and isinstance(outs[1], tuple):
+            d = max((outs[0][0] - outs[1][0]).abs().max().item(), (outs[0][1] - outs[1][1]).abs().max().item())
+            res[f"ragged_{B}x{T}"] = dict(diff=d, repeatable=outs[1][2], scale=outs[0][0].abs().max().item())
+        else:
+            res[f"ragged_{B}x{T}"] = dict(error=str(outs))
+        print(f"ragged {B}x{T}: {res[f'ragged_{B}x{T}']}", flush=True)
+    # K = 100 DDPM golden loop
+    g = golden("ddpm_lj_K100.npz")
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    cond, xT = torch.from_numpy(g["cond"]).to(DEV), torch.from_numpy(g["xT"]).to(DEV)
+    noise = rs_normal(int(g["noise_seed"]), (100,) + tuple(g["xT"].shape)).to(DEV)
+    for prec, sk, sets in (("fp16x2", 0, None), ("fp16x2", 1, None), ("fp16s", 1, 64), ("fp16s", 1, 16), ("fp16s", 1, 1),
+                           ("fp16", 1, None), ("fp16", 0, None)):
+        s = make(1, prec, sk, S, sets)
+        try:
+            x0 = s.sample_ddpm(xT, cond, 100, 100, noise=noise).cpu().numpy()
+            d = np.abs(x0 - g["x0"])
+            r = dict(max=float(d.max()), mae=float(d.mean()))
+        except Exception as e:  # noqa: BLE001
+            r = dict(error=str(e))
+        res[f"ddpm100_{prec}_k{sk}_sets{sets}"] = r
+        print(f"ddpm K=100 {prec} stack_kernel={sk} sets={sets}: {r}", flush=True)
+        s.close()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "dev_parity.json"), "w"), indent=1)
+
+
+def timing():
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    res = {}
+    for (B, T) in ((16, 1024), (1, 512), (4, 1024)):
+        gen = torch.Generator().manual_seed(1)
+        cond = torch.randn(B, T, 256, generator=gen).transpose(1, 2).to(DEV)
+        x = torch.randn(B, 1, 80, T, generator=gen).to(DEV)
+        for prec, sk in (("fp16x2", 0), ("fp16x2", 1), ("fp16s", 1), ("fp16", 1), ("fp16", 0)):
+            s = make(1, prec, sk, S)
+            K = 20
+            try:
+                s.sample_ddpm(x, cond, 100, 5, seed=1)
+                torch.cuda.synchronize()
+                s.set_option(_capi.OPT_PROFILE, 1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                s.sample_ddpm(x, cond, 100, K, seed=1)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / K
+                layer_ms = s.info(_capi.INFO_LAYER_KERNEL_NS) / 1e6 / max(s.info(_capi.INFO_LAYER_KERNEL_LAUNCHES), 1)
+                s.set_option(_capi.OPT_PROFILE, 0)
+                flops = B * T * 20 * 1048576
+                r = dict(ms_per_step=ms, stack_ms=layer_ms, frames_per_s_K100=B * T / (ms * 100 / 1e3),
+                         stack_tflops=flops / (layer_ms * 1e-3) / 1e12)
+            except Exception as e:  # noqa: BLE001
+                r = dict(error=str(e))
+            res[f"{B}x{T}_{prec}_k{sk}"] = r
+            print(f"timing {B}x{T} {prec} stack_kernel={sk}: {r}", flush=True)
+            s.close()
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "dev_timing.json"), "w"), indent=1)
+
+
+def trace():
+    import ctypes
+    B, T = 16, 1024
+    gen = torch.Generator().manual_seed(1)
+    cond = torch.randn(B, T, 256, generator=gen).transpose(1, 2).to(DEV)
+    x = torch.randn(B, 1, 80, T, generator=gen).to(DEV)
+    t = torch.full((B,), 57, dtype=torch.long, device=DEV)
+    out = {}
+    for prec in ("fp16s", "fp16x2"):
+        s = make(1, prec, 1)
+        s.diffnet_forward(x, t, cond)
+        buf = (ctypes.c_int64 * (6 * 256))()
+        _capi.check(_capi.lib.dsx_debug_trace(s._h, 1, None), "trace on")
+        s.diffnet_forward(x, t, cond)
+        s.diffnet_forward(x, t, cond)
+        _capi.check(_capi.lib.dsx_debug_trace(s._h, 1, ctypes.cast(buf, ctypes.c_void_p)), "trace read")
+        a = np.array(buf[:], dtype=np.int64).reshape(2, 3, 256)
+        out[prec] = a.tolist()
+        base = a[0, 1, 0]
+        print(f"--- {prec}: MMA thread (CTA 0) per layer: start G1c0, end G1c0, start G1c1, end G1c1, G2res start, G2res end, G2skip end")
+        for l in range(0, 6):
+            print(l, [int(a[0, 1, l * 8 + k] - base) for k in range(7)])
+        print("epilogue (warp 4): per layer e1c0 [enter, acc ready, done], e1c1 [...], e2 [enter, ready, done]")
+        for l in range(0, 6):
+            print(l, [int(a[0, 2, l * 12 + k] - base) for k in range(9)])
+        print("producer 0: per layer [g1done seen, flags seen, halo issued]")
+        for l in range(1, 6):
+            print(l, [int(a[0, 0, l * 4 + k] - base) for k in range(3)])
+        per_layer = (a[0, 1, 19 * 8] - a[0, 1, 1 * 8]) / 18.0
+        print(f"{prec}: cycles per layer (MMA thread, layers 1..19): {per_layer:.0f}")
+        s.close()
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "dev_trace.json"), "w"))
+
+
+if __name__ == "__main__":
+    {"quick": quick, "parity": parity, "timing": timing, "trace": trace}[sys.argv[1]]()
