@@ -35,7 +35,7 @@ int dev_alloc(dsx_handle* h, void** p, size_t bytes, bool model_owned) {
 }
 
 static void free_ws(Workspace& w) {
-  void* ptrs[] = {w.X, w.SKIP, w.CONDF, w.G1, w.Zf, w.Y, w.CONDH, w.CP, w.S16, w.DTAB, w.EMB, w.TVALS, w.EPS, w.XTMP, w.XSTATE};
+  void* ptrs[] = {w.X, w.SKIP, w.CONDF, w.G1, w.Zf, w.Y, w.CONDH, w.CP, w.S16, w.Z, w.DTAB, w.EMB, w.TVALS, w.EPS, w.XTMP, w.XSTATE};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   w = Workspace();
@@ -72,6 +72,7 @@ int ensure_workspace(dsx_handle* h, const Geom& g, int rows, cudaStream_t s) {
     NEED(Y, nf * m.C * 2 * 4);
     NEED(CONDH, nf * m.H * 2 * 2);
     NEED(S16, nf * m.C * 2 * 2);
+    NEED(Z, static_cast<size_t>(m.L) * nf * m.C * 2);
     NEED(CP, static_cast<size_t>(m.L) * g.tiles * 2 * 256 * kTile * 4);
     if (cond_before[0] != w.CONDH || cond_before[1] != w.CP) h->cond_ready = false;
   } else {
@@ -276,6 +277,46 @@ static int sample_plms_impl(dsx_handle* h, float* x, const Geom& g, int t_start,
   // history ring: hist[0] = most recent eps_t
   float* hist[4] = {nullptr, nullptr, nullptr, nullptr};
   int nh = 0, slot = 0;
+  const bool tc = h->precision != DSX_PREC_FP32_SIMT;
+  const DdpmCoef none{};
+  if (tc) {
+    // tcgen05 path: per evaluation the residual stack + ONE head kernel that also does the multistep combination, the
+    // get_x_pred update, the history store and the next evaluation's input projection (2 launches per PNDM step)
+    DSX_TRY(launch_tc_head(h, g, TC_INPROJ, x, xs, nullptr, nullptr, 0, 0, none, 0, 0, s));
+    for (int j = 0; j < n; ++j) {
+      const int t = steps[j];
+      float* e0 = E[slot];
+      PlmsFuse pf{};
+      plms_coefs(h, t, interval, pf.c);
+      DSX_TRY(run_layers(h, g, j, 0, h->m.L, s));
+      const int next_flags = (j + 1 < n) ? TC_INPROJ : 0;
+      if (nh == 0) {
+        // x' = phi(x, eps_t, t) -> XTMP; eps'' = net(x', max(t - interval, 0)); eps* = (eps_t + eps'') / 2; x = phi(x, eps*, t)
+        PlmsFuse p1 = pf;
+        p1.c.w0 = 1.f; p1.c.denom = 1.f;
+        p1.eps_store = e0;
+        p1.x_out = h->ws.XTMP;
+        DSX_TRY(launch_tc_head(h, g, TC_HEAD | TC_PLMS | TC_INPROJ, x, xs, nullptr, nullptr, 0, 0, none, n, 0, s, &p1));
+        DSX_TRY(run_layers(h, g, n, 0, h->m.L, s));
+        pf.c.w0 = 1.f; pf.c.w1 = 1.f; pf.c.denom = 2.f;
+        pf.h1 = e0;
+        DSX_TRY(launch_tc_head(h, g, TC_HEAD | TC_PLMS | next_flags, x, xs, nullptr, nullptr, 0, 0, none, j + 1, 0, s, &pf));
+      } else {
+        if (nh == 1) { pf.c.w0 = 3.f; pf.c.w1 = -1.f; pf.c.denom = 2.f; }
+        else if (nh == 2) { pf.c.w0 = 23.f; pf.c.w1 = -16.f; pf.c.w2 = 5.f; pf.c.denom = 12.f; }
+        else { pf.c.w0 = 55.f; pf.c.w1 = -59.f; pf.c.w2 = 37.f; pf.c.w3 = -9.f; pf.c.denom = 24.f; }
+        pf.h1 = hist[0];
+        pf.h2 = nh >= 2 ? hist[1] : nullptr;
+        pf.h3 = nh >= 3 ? hist[2] : nullptr;
+        pf.eps_store = e0;
+        DSX_TRY(launch_tc_head(h, g, TC_HEAD | TC_PLMS | next_flags, x, xs, nullptr, nullptr, 0, 0, none, j + 1, 0, s, &pf));
+      }
+      hist[3] = hist[2]; hist[2] = hist[1]; hist[1] = hist[0]; hist[0] = e0;
+      nh = std::min(nh + 1, 4);
+      slot = (slot + 1) % 4;
+    }
+    return DSX_OK;
+  }
   for (int j = 0; j < n; ++j) {
     const int t = steps[j];
     float* e0 = E[slot];
@@ -366,6 +407,7 @@ void dsx_destroy(dsx_handle* h) {
     if (p) cudaFree(p);
   if (h->trace_dev) cudaFree(h->trace_dev);
   if (h->flags_dev) cudaFree(h->flags_dev);
+  if (h->ll_dev) cudaFree(h->ll_dev);
   if (h->status_dev) cudaFree(h->status_dev);
   if (h->status_host) cudaFreeHost(h->status_host);
   delete h;
@@ -419,6 +461,7 @@ int dsx_diffnet_forward(dsx_handle* h, const float* x, dsx_strides xs, const int
   Geom g;
   DSX_TRY(prepare(h, cond, cs, B, T, B, g, s));
   DSX_TRY(launch_embed_table(h, t, B, s));
+  h->want_taps = 1;                      // dsx_debug_read may follow
   DSX_TRY(run_eval(h, x, xs, g, 0, 1, eps, s));
   return check_status(h, s, "dsx_diffnet_forward");
 }
@@ -465,6 +508,7 @@ int dsx_sample_ddpm(dsx_handle* h, float* x_inout, const float* cond, dsx_stride
             "steps t_start=%d n_steps=%d outside schedule of %d", t_start, n_steps, h->sched_T);
   Geom g;
   DSX_TRY(prepare(h, cond, cs, B, T, n_steps + 1, g, s));
+  h->want_taps = 0;
   DSX_TRY(sample_ddpm_impl(h, x_inout, g, t_start, n_steps, noise, seed, s));
   return check_status(h, s, "dsx_sample_ddpm");
 }
@@ -478,6 +522,7 @@ int dsx_sample_plms(dsx_handle* h, float* x_inout, const float* cond, dsx_stride
   Geom g;
   const int rows = (t_start + interval - 1) / interval + 2;
   DSX_TRY(prepare(h, cond, cs, B, T, rows, g, s));
+  h->want_taps = 0;
   DSX_TRY(sample_plms_impl(h, x_inout, g, t_start, interval, s));
   return check_status(h, s, "dsx_sample_plms");
 }
@@ -494,6 +539,7 @@ int dsx_infer(dsx_handle* h, const float* cond, dsx_strides cs, const float* fs2
   Geom g;
   const int rows = pndm_interval > 0 ? (K_step + pndm_interval - 1) / pndm_interval + 2 : K_step + 1;
   DSX_TRY(prepare(h, cond, cs, B, T, rows, g, s));
+  h->want_taps = 0;
   const int M = h->m.M;
   const size_t mel = static_cast<size_t>(B) * M * T;
   float* x = h->ws.XSTATE;   // x_t, [B,1,M,T]
@@ -527,6 +573,11 @@ int dsx_infer_host(dsx_handle* h, const float* cond_host, dsx_strides cs, const 
   // the host cond tensor must be dense in some permutation of [B,H,T]; copy its full extent.  Device staging
   // buffers live in the handle (grow-only) so a call costs copies, not cudaMalloc / cudaFree.
   const size_t cond_elems = static_cast<size_t>(B) * H * T;
+  DSX_CHECK(B > 0 && T > 0, DSX_E_INVALID, "B and T must be positive (got %d, %d)", B, T);
+  DSX_CHECK(cs.b > 0 && cs.c > 0 && cs.t > 0 &&
+                static_cast<size_t>((B - 1) * cs.b + (H - 1) * cs.c + (T - 1) * cs.t) + 1 == cond_elems,
+            DSX_E_INVALID, "dsx_infer_host: cond_host must be a dense permutation of a contiguous [B,H,T] block (strides %lld %lld %lld)",
+            static_cast<long long>(cs.b), static_cast<long long>(cs.c), static_cast<long long>(cs.t));
   int rc = DSX_OK;
   auto up = [&](int slot, const void* src, size_t bytes) -> void* {
     if (rc != DSX_OK || !src) return nullptr;
@@ -602,6 +653,7 @@ int dsx_set_option(dsx_handle* h, int what, int64_t value) {
     case DSX_OPT_CP_PREFETCH: h->cp_prefetch = static_cast<int>(value); break;
     case DSX_OPT_STACK_MODE: h->stack_mode = static_cast<int>(value); break;
     case DSX_OPT_STACK_KERNEL: h->stack_kernel = static_cast<int>(value); break;
+    case DSX_OPT_GATE_APPROX: h->gate_approx = static_cast<int>(value); break;
     case DSX_OPT_BATCH_OFFSET:
       DSX_CHECK(value >= 0 && value < (1ll << 30), DSX_E_INVALID, "DSX_OPT_BATCH_OFFSET out of range");
       h->batch_offset = static_cast<int>(value);

@@ -92,6 +92,7 @@ struct Workspace {
   __half* CONDH = nullptr;  // [2 planes][B][Tp][H]
   float* CP = nullptr;      // [L][tiles][2][64][128][4] conditioner projection + bias of every layer (tcgen05 path)
   __half* S16 = nullptr;    // [2 planes][B][Tp][C] skip_sum / sqrt(L), operand of the head GEMM
+  __half* Z = nullptr;      // [L][B][Tp][C] gate outputs z of every layer (stack kernel: A operand of the deferred skip GEMM)
   float* DTAB = nullptr;    // [rows][L][C]
   float* EMB = nullptr;     // [rows][C] scratch (mlp output)
   int64_t* TVALS = nullptr; // [rows]
@@ -100,7 +101,7 @@ struct Workspace {
   float* XSTATE = nullptr;  // [B][M][T] mel state of dsx_infer
   size_t bytes = 0;
   // byte capacities (grow-only)
-  size_t cap_X = 0, cap_SKIP = 0, cap_CONDF = 0, cap_G1 = 0, cap_Zf = 0, cap_Y = 0, cap_CONDH = 0, cap_CP = 0, cap_S16 = 0,
+  size_t cap_X = 0, cap_SKIP = 0, cap_CONDF = 0, cap_G1 = 0, cap_Zf = 0, cap_Y = 0, cap_CONDH = 0, cap_CP = 0, cap_S16 = 0, cap_Z = 0,
          cap_DTAB = 0, cap_EMB = 0, cap_TVALS = 0, cap_EPS = 0, cap_XTMP = 0, cap_XSTATE = 0;
 };
 
@@ -123,7 +124,7 @@ struct dsx_handle {
   dsx::Workspace ws;
   int* status_dev = nullptr;   // kernel watchdog / self-check word
   int* status_host = nullptr;  // pinned mirror
-  CUtensorMap tm_w{}, tm_y[2][2]{}, tm_yh[2]{}, tm_ye[2]{}, tm_cond[2]{}, tm_s16[2]{}, tm_whead{}, tm_wsr{};
+  CUtensorMap tm_w{}, tm_y[2][2]{}, tm_yh[2]{}, tm_ye[2]{}, tm_cond[2]{}, tm_s16[2]{}, tm_whead{}, tm_wsr{}, tm_z{};
   dsx::Geom tm_geom;           // geometry the activation maps were built for
   int tm_group = 0;
   int profile = 0;
@@ -133,6 +134,9 @@ struct dsx_handle {
   int flags_cap = 0;
   int flags_geom_b = 0, flags_geom_t = 0;   // geometry of the last stack launch
   unsigned int flag_count = 0;         // value of every counter before the next stack launch
+  void* ll_dev = nullptr;              // halo packets of the stack kernel (dsx_stack.cu)
+  size_t ll_cap = 0;
+  unsigned int ll_seq = 1;             // next sequence number (monotonic, never 0)
   int flags_kind = 0;                  // which kernel's counting convention the counters follow (1: k_tc_layer, 2: k_tc_stack)
   int stack_kernel = 1;                // DSX_OPT_STACK_KERNEL: 1 = register-resident stack kernel (dsx_stack.cu) where it applies
   int stack_occ[2] = {0, 0};           // co-resident CTA pairs of k_tc_stack<1>, <2> (0 unknown, -1 none)
@@ -143,6 +147,8 @@ struct dsx_handle {
   unsigned long long tm_epoch = ~0ull;
   bool cond_ready = false;             // CONDH / CP (or CONDF) hold the conditioner of dsx_set_cond for geometry cond_geom
   dsx::Geom cond_geom;
+  int gate_approx = -1;                // DSX_OPT_GATE_APPROX: -1 = default (tanh.approx gate), 0 / 1 forced
+  int want_taps = 1;                   // the next stack launches write X / SKIP back (dsx_diffnet_forward: yes, sampling loops: no)
   int batch_offset = 0;                // DSX_OPT_BATCH_OFFSET: global index of utterance 0 in the Philox noise counters
   bool attr_layer[3] = {false, false, false}, attr_head[2] = {false, false}, attr_cond = false;
   int occ_cache[3][17] = {};
@@ -186,10 +192,20 @@ int launch_tc_condproj(dsx_handle* h, const Geom& g, cudaStream_t s);
 int launch_tc_layers(dsx_handle* h, int l0, int l1, const Geom& g, int row0, int row_per_b, cudaStream_t s);
 // Head / tail of DiffNet on tensor cores.  flags: 1 = head (skip -> eps), 2 = write eps, 4 = DDPM update of x,
 // 8 = input projection of x (after the update if any) for the evaluation that uses table row (next_row0, row_per_b).
-enum { TC_HEAD = 1, TC_WRITE_EPS = 2, TC_UPDATE = 4, TC_INPROJ = 8 };
+enum { TC_HEAD = 1, TC_WRITE_EPS = 2, TC_UPDATE = 4, TC_INPROJ = 8, TC_PLMS = 16 };
+// PNDM update fused into the head kernel (TC_PLMS): eps' = (w0 eps_t + w1 h1 + w2 h2 + w3 h3) / denom, x_out = phi(x, eps', t)
+// (usr/diff/shallow_diffusion_tts.py:174-199); eps_t is also stored to `eps_store` (history ring) when non-null.
+struct PlmsFuse {
+  PlmsCoef c;
+  const float* h1;
+  const float* h2;
+  const float* h3;   // earlier eps, most recent first, contiguous [B][M][T] (or null)
+  float* eps_store;  // this evaluation's eps -> history ring slot (or null)
+  float* x_out;      // result; null: in place
+};
 int launch_tc_head(dsx_handle* h, const Geom& g, int flags, float* x_state, dsx_strides xs, float* eps_out,
                    const float* noise, uint64_t seed, uint64_t offset, DdpmCoef c, int next_row0, int row_per_b,
-                   cudaStream_t s);
+                   cudaStream_t s, const PlmsFuse* plms = nullptr);
 bool tc_supported(const dsx_handle* h);
 int ensure_flags(dsx_handle* h, int n);
 int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows);

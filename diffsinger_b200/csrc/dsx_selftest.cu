@@ -255,7 +255,9 @@ static int run_selftest(std::string& report) {
   return (status == 0 && bad == 0) ? DSX_OK : DSX_E_KERNEL;
 }
 
-static int run_shift_experiment(std::string& report) {
+// Row-shifted operand descriptors (what the dilated taps use: base_offset field 0): every shift must reproduce the reference.
+// `also_base_offset_variant` additionally reports the alternative encoding (informational).
+static int run_shift_experiment(std::string& report, bool also_base_offset_variant = false) {
   const int T = 300, CH = 128;
   std::vector<__half> ha(static_cast<size_t>(T) * CH), hw(512 * 64);
   auto aval = [](int t, int c) { return static_cast<float>((t * 131 + c * 71) % 61 - 30) / 64.f; };
@@ -299,7 +301,8 @@ static int run_shift_experiment(std::string& report) {
   const int smem = 1024 + 21504 + 256 * 128 + 64;
   DSX_CUDA(cudaFuncSetAttribute(k_shift_test, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int shifts[] = {0, 1, 2, 3, 4, 8, 16};
-  for (int ubo = 0; ubo < 2; ++ubo)
+  int failures = 0;
+  for (int ubo = 0; ubo < (also_base_offset_variant ? 2 : 1); ++ubo)
     for (int si = 0; si < 7; ++si) {
       prm.shift = shifts[si];
       prm.use_base_offset = ubo;
@@ -319,12 +322,14 @@ static int run_shift_experiment(std::string& report) {
       char line[160];
       snprintf(line, sizeof(line), "shifted_A_desc shift=%d base_offset_field=%d: bad=%d/32768\n", shifts[si], ubo, bad);
       report += line;
+      if (ubo == 0 && bad) failures++;
     }
   cudaFree(da); cudaFree(dw); cudaFree(dout); cudaFree(dstatus);
-  return DSX_OK;
+  return failures ? DSX_E_KERNEL : DSX_OK;
 }
 
 
+#ifdef DSX_EXPERIMENTS   // informational micro-benchmark, not part of the product library (build with -DDSX_EXPERIMENTS)
 // ---- experiment 3: how fast can ONE SM pull L2-resident operand tiles into shared memory? --------------------
 // `nthr` threads (one per warp) each stream loads through their own ring of `nslot` slots (wait for the slot's previous
 // load, re-issue).  kind 0: 2D tensor map (64 x rows box, SWIZZLE_128B) -- what the layer kernel does; kind 1: 1D bulk
@@ -448,6 +453,7 @@ static int run_ingest_experiment(std::string& report) {
   cudaFree(dcyc);
   return DSX_OK;
 }
+#endif  // DSX_EXPERIMENTS
 }  // namespace dsx
 
 extern "C" int dsx_selftest(int device, int which, char* report, int report_bytes) {
@@ -464,13 +470,17 @@ extern "C" int dsx_selftest(int device, int which, char* report, int report_byte
     int r = run_selftest<2>(rep);
     if (r != DSX_OK) { rc = DSX_E_KERNEL; failed += " umma_cta_group2"; }
   }
-  if (which == 2) {   // informational experiment, not part of which = -1
-    int r = run_shift_experiment(rep);
-    if (r != DSX_OK) rc = r;
+  if (which < 0 || which == 2) {   // row-shifted SWIZZLE_128B operand descriptors: the dilated taps of both layer kernels rely on them
+    int r = run_shift_experiment(rep, which == 2);
+    if (r != DSX_OK) { rc = DSX_E_KERNEL; failed += " shifted_descriptors"; }
   }
-  if (which == 3) {   // informational experiment: per-SM TMA ingest rate
+  if (which == 3) {   // informational experiment: per-SM TMA ingest rate (only in -DDSX_EXPERIMENTS builds)
+#ifdef DSX_EXPERIMENTS
     int r = run_ingest_experiment(rep);
     if (r != DSX_OK) rc = r;
+#else
+    rep += "ingest micro-benchmark not compiled in (build with -DDSX_EXPERIMENTS)\n";
+#endif
   }
   if (report && report_bytes > 0) {
     strncpy(report, rep.c_str(), static_cast<size_t>(report_bytes) - 1);

@@ -1,27 +1,38 @@
 // k_tc_stack<WP>: all residual layers of one DiffNet evaluation (usr/diff/net.py:58-78,121-126) in one persistent launch,
-// with the residual stream in REGISTERS, the conv input y in SHARED MEMORY and the skip sum in TENSOR MEMORY for the whole
-// stack.  Per 128-frame tile (one CTA; two CTAs form a cta_group::2 pair, UMMA M = 256, N = 256) and layer l:
+// with the residual stream in REGISTERS and the conv input y in SHARED MEMORY for the whole stack.  Per 128-frame tile
+// (one CTA; two CTAs form a cta_group::2 pair, UMMA M = 256, N = 256) and layer l:
 //
-//   GEMM1   D1[:, chunk h] = [y(t-d) | y(t) | y(t+d)] (K = 768) . W1(h)^T      -> TMEM columns F = [0, 256), h = 0 then 1
+//   GEMM1   D1[:, chunk h] = [y(t-d) | y(t) | y(t+d)] (K = 768) . W1(h)^T      -> TMEM F0 (h = 0), F1 (h = 1); the centre
+//                                                                                  taps of both chunks first, the halo taps last
 //   epi1    z(chunk h) = sigmoid(D1 gate + CP) * tanh(D1 filter + CP) -> fp16, swizzled K-major rows in shared memory
-//   GEMM2r  D2res = z (K = 256) . W2res^T                                        -> F
-//   GEMM2s  SKIP += z . W2skip^T                                                  -> TMEM columns S = [256, 512), accumulated
-//                                                                                  over ALL layers, read once at the end
+//           (chunk 0 drains F0 under chunk 1's MMAs)
+//   GEMM2r  D2res = z (K = 256) . W2res^T                                        -> F0 (k-blocks 0, 1 under epi1 of chunk 1)
 //   epi2    x <- (x + D2res + b) / sqrt2   (x: 128 fp32 registers per epilogue thread = one frame row x 128 channels)
-//           y_{l+1} = fp16(x + d_{l+1})    -> straight into the next layer's A-operand tiles in shared memory; only the
-//                                              8 first / last rows of the tile also go to HBM for the neighbour tiles' halos
+//           y_{l+1} = fp16(x + d_{l+1})    -> straight into the next layer's A-operand tiles in shared memory; the 8 first /
+//                                              last rows of the tile are also sent to the neighbour tiles (halo rows of the
+//                                              dilated taps) as self-validating {data, sequence} packets, see below
+//   z_l     -> HBM by TMA store (64 KB per tile and layer)
+// and after the last layer ONE deferred GEMM for the skip path (net.py:126 sums the skip halves of all layers, which is a
+// single contraction over K = L * 256):
+//   SKIP    = [z_0 | z_1 | ... | z_{L-1}] (K = 20 * 256) . [W2skip_0; ...; W2skip_{L-1}]^T   -> F1, read once
+// so the per-layer critical path carries no skip work at all (no accumulator, no epilogue, no red.add traffic).
 //
 // Compared with the round-1 layer kernel (dsx_tc.cu, k_tc_layer) this removes, per layer and tile, the fp32 read-modify-
 // write of x through L2 (256 KB), the skip red.add (128 KB), the y round trip through L2 (64 KB + 144 KB of TMA loads) and
 // the transposing staging pass; the layer hand-over inside a tile is a shared-memory barrier instead of a global flag round
-// trip (only the 8-row halos still travel through global memory + publish counters).
+// trip.  Halo exchange between neighbouring tiles (different CTA pairs): every 16-byte packet in global memory carries 8
+// bytes of fp16 data and two copies of a per-layer sequence number (the scheme NCCL's LL protocol uses); the receiving
+// epilogue warps poll the packets themselves right after their own epi2, so there is no publish counter, no fence and no
+// second round trip, and the ~2k cycles of latency hide under the centre-tap MMAs of the next layer.
 //
 // Shared memory: [W ring 5 x 16 KB | y: 4 k-blocks x (8 halo + 128 + 8 halo rows) x 128 B | z: 4 k-blocks x 16 KB |
-//                 per-layer bias / FiLM vectors (1 KB per epilogue warp) | barriers]
-// TMEM: F (256 columns: D1 chunk 0, D1 chunk 1, D2res in turn) + S (256 columns, skip accumulator).
-// Roles (384 threads): warp 0 lane 0 = halo / flag / CP-prefetch producer, warps 2, 3 lane 0 = weight producers, warp 1
-// lane 0 of the pair leader = MMA issuer, warps 4-11 = epilogue (thread = frame row = TMEM lane, two warps per lane quadrant
-// split the 256 columns).  setmaxnreg moves registers from warps 0-3 to the epilogue warps (x lives there).
+//                 per-layer bias / FiLM vectors (1 KB per epilogue warp) | barriers]; the deferred skip GEMM streams its A
+// tiles (z of every layer) through the z and y areas.
+// TMEM: F0, F1 (256 columns each).
+// Roles (384 threads): warp 0 lane 0 = activation producer (layer-0 slots, z stores, CP prefetch, A tiles of the skip GEMM),
+// warps 2, 3 lane 0 = weight producers, warp 1 lane 0 of the pair leader = MMA issuer, warps 4-11 = epilogue (thread = frame
+// row = TMEM lane, two warps per lane quadrant split the 256 columns).  setmaxnreg moves registers from warps 0-3 to the
+// epilogue warps (x lives there).
 //
 // Weight tiles: WP = 2 reads the hi and lo planes of the round-1 pack (fp16x2 parity mode); WP = 1 reads one plane -- either
 // the round-to-nearest hi plane (fp16 fast mode) or one of R stochastically rounded weight sets, a different one at every
@@ -44,22 +55,27 @@ struct StackCfg {
   static constexpr int W_BYTES = WSLOTS * kUnitBytes;
   static constexpr int Y_BYTES = 4 * YSLOT;
   static constexpr int Z_BYTES = 4 * kUnitBytes;
+  static constexpr int ASLOTS = 8;                          // A ring of the skip GEMM: 4 units in the z area + 4 in the y area
   static constexpr int TAB_BYTES = kEpiWarps * 1024;       // per epilogue warp: [bias(128) | d_next(128)] fp32 of its column half
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = 1024 + W_BYTES + Y_BYTES + Z_BYTES + TAB_BYTES + BAR_BYTES;
-  static constexpr int REGS_LOW = 56, REGS_HIGH = 224;     // setmaxnreg targets: 128 * 56 + 256 * 224 = 64512 = 384 * 168 (the launch allocation)
+  static constexpr int REGS_LOW = 56, REGS_HIGH = 224;     // setmaxnreg targets: 128 * 56 + 256 * 224 = 64512 = 384 * 168 (the
+                                                            // CTA's register pool is its launch allocation)
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(YSLOT % 1024 == 0, "y slots must keep the 1024-byte swizzle atoms aligned");
+  static_assert(Y_BYTES >= 4 * kUnitBytes, "A ring units in the y area");
 };
 
 struct TcStackParams {
   CUtensorMap tm_w;        // weight tiles, 2D [rows][64], box 64 x 128 rows
   CUtensorMap tm_y0;       // Y buffer 0 (written by the input projection), box 64 ch x 144 frames: layer 0 incl. halos
-  CUtensorMap tm_ye[2];    // Y buffer 0 / 1, box 64 ch x 8 frames: halo rows published by the neighbour tiles
+  CUtensorMap tm_z;        // Z [L * B][T][256] fp16, box 64 ch x 128 frames: z of every layer (store per layer, load for the skip GEMM)
   float* X;                // [B][Tp][256] residual stream: read at entry, written back at exit
   float* SKIP;             // [B][Tp][256] skip sum (debug tap / fp32 copy), written at exit
-  __half* Y;               // [2 buffers][2 planes][plane_elems]; only the edge rows of the hi plane are written here
   size_t plane_elems;
+  uint4* ll;               // halo packets [tiles][2 layer parities][2 sides: first / last 8 rows][512] x 16 B:
+                           // {fp16 x2, seq, fp16 x2, seq}, packet = 4 channels of one row (row * 64 + channel / 4)
+  unsigned int seq_base;   // sequence number of layer l's y: seq_base + l (monotonic over the handle's lifetime, never 0)
   const float* CP;         // [L][tiles][2 chunks][64 column groups][128 rows][4] conditioner projection + biases
   int cp_prefetch;
   const float* b2;         // [L][512] output_projection bias (residual half | skip half)
@@ -72,17 +88,16 @@ struct TcStackParams {
   int w_row0;              // first row of this evaluation's weight set in tm_w
   int w_layer_rows;        // rows per layer
   int w_sr;                // 0: round-1 pack (80 tiles per layer, hi / lo planes); 1: single-plane set (32 tiles per layer)
-  unsigned int* flags;     // [tiles] publish counters
-  unsigned int flag_base;
   __half* s16;             // fp16 split of skip_total / sqrt(L): plane 0 hi, plane 1 (at + plane_elems) lo
   float inv_sqrt_l;
   int fast_act;            // 1: tanh.approx gate (fp16 fast mode)
+  int taps;                // 1: write the residual stream and the fp32 skip sum back to X / SKIP at exit (debug taps of
+                           // dsx_diffnet_forward); the sampling loops do not need them
   int* status;
   unsigned long long budget_ns;
   long long* trace;        // debug: [2 CTAs][3 roles][256] clock64 stamps, or nullptr
 };
 
-constexpr int kFlagsPerLayer = 4;      // edge warps (rows 0-31 and 96-127, two column halves) publish per layer
 
 #define DSX_STRACE(role, slot)                                                         \
   do {                                                                                 \
@@ -90,34 +105,12 @@ constexpr int kFlagsPerLayer = 4;      // edge warps (rows 0-31 and 96-127, two 
       p.trace[(blockIdx.x * 3 + (role)) * 256 + (slot)] = clock64();                   \
   } while (0)
 
-// wait until the (up to two) neighbour tiles' counters have reached `target`
-__device__ __forceinline__ bool flag_wait2(const unsigned int* lo, const unsigned int* hi, unsigned int target,
-                                           const Watchdog& wd, int code) {
-  if (!lo && !hi) return true;
-  uint32_t spins = 0;
-  while (true) {
-    unsigned int v1 = target, v2 = target;
-    if (lo) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(lo) : "memory");
-    if (hi) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v2) : "l"(hi) : "memory");
-    if (static_cast<int>(v1 - target) >= 0 && static_cast<int>(v2 - target) >= 0) {
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      return true;
-    }
-    if (((++spins) & 0xff) == 0) {
-      if (*(volatile int*)wd.status != 0) return false;
-      if (globaltimer_ns() > wd.deadline_ns) {
-        atomicCAS(wd.status, 0, code);
-        return false;
-      }
-    }
-  }
-}
-
 template <int WP>
 __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant__ TcStackParams p) {
   using Cfg = StackCfg;
   constexpr int G = kG;
   constexpr int WS = Cfg::WSLOTS;
+  constexpr int AS = Cfg::ASLOTS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* wring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* yslots = wring + Cfg::W_BYTES;
@@ -126,12 +119,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tab) + Cfg::TAB_BYTES);
   uint64_t* full = bars;            // [WS] weight tile landed (both CTAs' halves; leader's barrier)
   uint64_t* empty = full + WS;      // [WS] weight tile consumed (tcgen05.commit, both CTAs)
-  uint64_t* tfull = empty + WS;     // accumulator F (or S at the very end) complete -> epilogue
-  uint64_t* tempty = tfull + 1;     // epilogue phase done (F drained, z / y written), 8 warps x 2 CTAs -> leader
-  uint64_t* g1done = tempty + 1;    // all GEMM1 MMAs of the layer complete: the y slots may be overwritten
-  uint64_t* yhalo = g1done + 1;     // halo rows (layer 0: whole slots) landed (leader's barrier)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yhalo + 1);
-  static_assert((2 * Cfg::WSLOTS + 4) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
+  uint64_t* tfull = empty + WS;     // [2] accumulator F0 / F1 complete -> epilogue
+  uint64_t* tempty = tfull + 2;     // [2] epilogue phase on F0 / F1 done (drained, its z / y written), 8 warps x 2 CTAs -> leader
+  uint64_t* y0full = tempty + 2;    // layer 0: the whole y slots landed by TMA (leader's barrier)
+  uint64_t* yhalo = y0full + 1;     // halo rows of the layer received and written by the epilogue warps, 8 warps x 2 CTAs -> leader
+  uint64_t* zdone = yhalo + 1;      // this CTA's 8 epilogue warps have written z of the layer (local)
+  uint64_t* zfree = zdone + 1;      // the TMA store of z has finished reading it (local)
+  uint64_t* lfin = zfree + 1;       // every MMA of the layers complete: z / y areas become the A ring of the skip GEMM
+  uint64_t* afull = lfin + 1;       // [AS] A tile of the skip GEMM landed (leader's barrier)
+  uint64_t* aempty = afull + AS;    // [AS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + AS);
+  static_assert((2 * Cfg::WSLOTS + 9 + 2 * Cfg::ASLOTS) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
+  auto aslot = [&](int s) -> uint8_t* { return s < 4 ? zbuf + s * kUnitBytes : yslots + (s - 4) * kUnitBytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -145,22 +144,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
   const int cp_tile = tile_valid ? tile : 0;      // padding CTAs read (and discard) tile 0's slice of CP
   const int t0 = tile_valid ? tr * kTile : 0;
   const bool nb_lo = tile_valid && tr > 0, nb_hi = tile_valid && tr + 1 < p.tiles_per_utt;
+  const int zq = tile_valid ? b : p.L * p.B;      // Z coordinate base: (l * B + b); out of bounds for padding CTAs
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_w);
     tma_prefetch_desc(&p.tm_y0);
-    tma_prefetch_desc(&p.tm_ye[0]);
-    tma_prefetch_desc(&p.tm_ye[1]);
+    tma_prefetch_desc(&p.tm_z);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < WS; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, kEpiWarps * G);
-    mbar_init(g1done, 1);
-    mbar_init(yhalo, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], kEpiWarps * G);
+    }
+    mbar_init(y0full, 1);
+    mbar_init(yhalo, kEpiWarps * G);
+    mbar_init(zdone, kEpiWarps);
+    mbar_init(zfree, 1);
+    mbar_init(lfin, 1);
+    for (int s = 0; s < AS; ++s) {
+      mbar_init(&afull[s], 1);
+      mbar_init(&aempty[s], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<G>(tmem_slot, 512);
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_LOW));
     if (warp == 0 && lane == 0) {
-      // ================================ halo / flag / CP-prefetch producer ================================
+      // ================================ activation producer ================================
       bool ok = true;
       auto cp_prefetch = [&](int l, int h) {
         if (!p.cp_prefetch || l >= p.nl) return;
@@ -193,31 +201,36 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         for (int i = 0; i < 8; ++i) prefetch_l2_bulk(src + i * 16384, 16384);
       };
       // layer 0: the whole [8 | 128 | 8]-row slots come from Y buffer 0 (written by the input projection kernel)
-      if (prank == 0) mbar_arrive_expect_tx(yhalo, G * Cfg::Y_BYTES);
-      for (int cb = 0; cb < 4; ++cb) tma_load_3d<G>(&p.tm_y0, yhalo, yslots + cb * Cfg::YSLOT, cb * 64, t0 - 8, bq, lead);
+      if (prank == 0) mbar_arrive_expect_tx(y0full, G * Cfg::Y_BYTES);
+      for (int cb = 0; cb < 4; ++cb) tma_load_3d<G>(&p.tm_y0, y0full, yslots + cb * Cfg::YSLOT, cb * 64, t0 - 8, bq, lead);
       cp_prefetch(0, 0);
       cp_prefetch(0, 1);
-      cp_prefetch(1, 0);
-      for (int l = 1; l < p.nl && ok; ++l) {
-        // y_l: the centre rows are written into the slots by this tile's own epilogue; the halo rows come from the
-        // neighbour tiles through global memory once (a) GEMM1 of layer l-1 no longer reads the slots and (b) the
-        // neighbours have published their edge rows of y_l
-        ok = mbar_wait(g1done, (l - 1) & 1, wd, 105);
-        DSX_STRACE(0, l * 4);
-        if (ok)
-          ok = flag_wait2(nb_lo ? p.flags + tile - 1 : nullptr, nb_hi ? p.flags + tile + 1 : nullptr,
-                          p.flag_base + static_cast<unsigned int>(kFlagsPerLayer * l), wd, 107);
+      for (int l = 0; l < p.nl && ok; ++l) {
+        // z_l (complete once this CTA's epilogue warps are through chunk 1) -> Z[l] in HBM for the deferred skip GEMM;
+        // the z area may be overwritten (next layer's chunk 0) once the store has read it
+        ok = mbar_wait(zdone, l & 1, wd, 108);
         if (!ok) break;
-        fence_proxy_async_all();
-        DSX_STRACE(0, l * 4 + 1);
-        if (prank == 0) mbar_arrive_expect_tx(yhalo, G * 8 * 1024);
-        for (int cb = 0; cb < 4; ++cb) {
-          tma_load_3d<G>(&p.tm_ye[l & 1], yhalo, yslots + cb * Cfg::YSLOT, cb * 64, t0 - 8, bq, lead);
-          tma_load_3d<G>(&p.tm_ye[l & 1], yhalo, yslots + cb * Cfg::YSLOT + (kTile + 8) * 128, cb * 64, t0 + kTile, bq, lead);
-        }
-        DSX_STRACE(0, l * 4 + 2);
-        cp_prefetch(l, 1);
-        cp_prefetch(l + 1, 0);
+        for (int kb = 0; kb < 4; ++kb) tma_store_3d(&p.tm_z, zbuf + kb * kUnitBytes, kb * 64, t0, l * p.B + zq);
+        bulk_commit_group();
+        bulk_wait_group_read0();
+        mbar_arrive(zfree);
+        DSX_STRACE(0, l * 4 + 3);
+        cp_prefetch(l + 1, 0);                            // HBM -> L2, most of a layer ahead of the gate epilogue that reads it
+        cp_prefetch(l + 1, 1);
+      }
+      // ---- deferred skip GEMM: A tiles = z of every layer, back from HBM (this tile's own stores) ----
+      if (ok) {
+        bulk_wait_group0();                               // the stores are complete (visible to the loads below)
+        ok = mbar_wait(lfin, 0, wd, 109);                 // no MMA reads the y / z areas any more
+        uint32_t ai = 0;
+        for (int l = 0; l < p.nl && ok; ++l)
+          for (int kb = 0; kb < 4 && ok; ++kb, ++ai) {
+            const uint32_t s = ai % AS;
+            ok = mbar_wait(&aempty[s], ((ai / AS) & 1) ^ 1, wd, 110);
+            if (!ok) break;
+            if (prank == 0) mbar_arrive_expect_tx(&afull[s], G * kUnitBytes);
+            tma_load_3d<G>(&p.tm_z, &afull[s], aslot(s), kb * 64, t0, l * p.B + zq, lead);
+          }
       }
     } else if ((warp == 2 || warp == 3) && lane == 0) {
       // ================================ weight producers ================================
@@ -236,22 +249,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         ++wi;
       };
       for (int l = 0; l < p.nl && ok; ++l) {
-        for (int h = 0; h < 2 && ok; ++h) {
-          for (int cb = 0; cb < 4 && ok; ++cb)                      // centre tap first: needs no halo rows
+        for (int h = 0; h < 2 && ok; ++h)                           // centre taps of both chunks first: they need no halo rows
+          for (int cb = 0; cb < 4 && ok; ++cb)
             for (int pl = 0; pl < WP && ok; ++pl) load_w(w1_row(l, h, 1, cb, pl));
+        for (int h = 0; h < 2 && ok; ++h)
           for (int cb = 0; cb < 4 && ok; ++cb)
             for (int tap = 0; tap < 3 && ok; tap += 2)
               for (int pl = 0; pl < WP && ok; ++pl) load_w(w1_row(l, h, tap, cb, pl));
-        }
-        for (int q = 0; q < 2 && ok; ++q)
-          for (int kb = 0; kb < 4 && ok; ++kb)
-            for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, q, kb, pl));
+        for (int kb = 0; kb < 4 && ok; ++kb)
+          for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, 0, kb, pl));
       }
+      for (int l = 0; l < p.nl && ok; ++l)                          // skip GEMM
+        for (int kb = 0; kb < 4 && ok; ++kb)
+          for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, 1, kb, pl));
     } else if (warp == 1 && lane == 0 && prank == 0) {
       // ================================ MMA issuer (pair leader) ================================
       constexpr uint32_t idesc = umma_idesc_f16(128 * G, 256);
-      const uint32_t dF = tmem_base, dS = tmem_base + 256;
-      uint32_t wi = 0, te = 0;
+      uint32_t wi = 0;
       bool ok = true;
       auto mma_tile = [&](uint32_t d, uint64_t a, uint32_t& acc, int code) {   // one weight tile of the global order
         const uint32_t s = wi % WS;
@@ -267,65 +281,76 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         umma_commit<G>(&empty[s], pair_mask);
         ++wi;
       };
-      auto wait_epi = [&](int code) {                   // next epilogue phase done: F drained, its z / y in shared memory
-        ok = ok && mbar_wait(tempty, te & 1, wd, code);
-        ++te;
+      // epilogue phases (drained accumulator, its z / y in shared memory).  tempty[0] completes twice per layer: chunk 0's
+      // gate epilogue (parity 0), then the residual epilogue (parity 1); tempty[1] once per layer (parity l & 1)
+      auto wait_epi = [&](uint64_t* bar, uint32_t parity, int code) {
+        ok = ok && mbar_wait(bar, parity, wd, code);
         tc_fence_after();
       };
-      uint32_t acc_s = 0;
       for (int l = 0; l < p.nl && ok; ++l) {
         const int dil = 1 << (l % p.cycle);
-        for (int h = 0; h < 2 && ok; ++h) {
-          if (l > 0 || h > 0) wait_epi(201);            // h = 0: epi2 of layer l-1 (y_l centre rows); h = 1: epi1 chunk 0
-          if (!ok) break;
-          DSX_STRACE(1, l * 8 + h * 2);
-          uint32_t acc = 0;
-          if (h == 0 && l == 0) {                       // layer 0: the whole slots (centre rows too) arrive by TMA
-            ok = mbar_wait(yhalo, 0, wd, 206);
-            tc_fence_after();
-          }
-          for (int cb = 0; cb < 4 && ok; ++cb) {        // centre tap: rows written by this pair's own epilogue
+        uint32_t acc0 = 0, acc1 = 0;
+        if (l == 0) {                                   // layer 0: the whole slots (centre rows too) arrive by TMA
+          ok = mbar_wait(y0full, 0, wd, 206);
+          tc_fence_after();
+        } else {
+          wait_epi(&tempty[0], 1, 201);                 // epi2 of layer l-1: F0 drained, centre rows of y_l written
+        }
+        DSX_STRACE(1, l * 8);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)                     // centre taps (F1 has been free since chunk 1's epilogue of layer l-1)
+          for (int cb = 0; cb < 4 && ok; ++cb) {
             const uint64_t a = umma_desc_sw128(smem_u32(yslots + cb * Cfg::YSLOT)) + static_cast<uint64_t>((8 * 128) >> 4);
-            for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dF, a, acc, 207);
+            for (int pl = 0; pl < WP && ok; ++pl) mma_tile(tmem_base + h * 256, a, h == 0 ? acc0 : acc1, 207);
           }
-          if (h == 0 && l > 0 && ok) {                  // halo rows of this layer (from the neighbour tiles) landed
-            ok = mbar_wait(yhalo, l & 1, wd, 206);
-            tc_fence_after();
-          }
+        DSX_STRACE(1, l * 8 + 1);
+        if (l > 0 && ok) {                              // halo rows of this layer (from the neighbour tiles) are in the slots
+          ok = mbar_wait(yhalo, (l - 1) & 1, wd, 206);
+          tc_fence_after();
+        }
+        DSX_STRACE(1, l * 8 + 2);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
           for (int cb = 0; cb < 4 && ok; ++cb) {
             const uint64_t y = umma_desc_sw128(smem_u32(yslots + cb * Cfg::YSLOT));
             for (int tap = 0; tap < 3 && ok; tap += 2) {
               const uint64_t a = y + static_cast<uint64_t>(((8 + (tap - 1) * dil) * 128) >> 4);   // row-shifted start
-              for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dF, a, acc, 207);
+              for (int pl = 0; pl < WP && ok; ++pl) mma_tile(tmem_base + h * 256, a, h == 0 ? acc0 : acc1, 207);
             }
           }
-          if (ok && h == 1) umma_commit<G>(g1done, pair_mask);
-          if (ok) umma_commit<G>(tfull, pair_mask);
-          DSX_STRACE(1, l * 8 + h * 2 + 1);
+          if (ok) umma_commit<G>(&tfull[h], pair_mask);
         }
-        if (!ok) break;
-        wait_epi(203);                                  // epi1 chunk 1: all four z k-blocks written, F free
-        if (!ok) break;
-        DSX_STRACE(1, l * 8 + 4);
-        {
-          uint32_t acc = 0;
-          for (int kb = 0; kb < 4 && ok; ++kb) {
-            const uint64_t z = umma_desc_sw128(smem_u32(zbuf + kb * kUnitBytes));
-            for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dF, z, acc, 205);
-          }
-          if (ok) umma_commit<G>(tfull, pair_mask);
-        }
-        DSX_STRACE(1, l * 8 + 5);
+        DSX_STRACE(1, l * 8 + 3);
+        // GEMM2 (residual half) -> F0: k-blocks 0, 1 after chunk 0's epilogue (F0 drained, z k-blocks 0, 1 written),
+        // k-blocks 2, 3 after chunk 1's
+        uint32_t acc2 = 0;
         for (int kb = 0; kb < 4 && ok; ++kb) {
+          if (kb == 0) wait_epi(&tempty[0], 0, 203);
+          if (kb == 2) wait_epi(&tempty[1], l & 1, 204);
+          if (!ok) break;
+          if (kb == 0) DSX_STRACE(1, l * 8 + 4);
+          if (kb == 2) DSX_STRACE(1, l * 8 + 5);
           const uint64_t z = umma_desc_sw128(smem_u32(zbuf + kb * kUnitBytes));
-          for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dS, z, acc_s, 205);
+          for (int pl = 0; pl < WP && ok; ++pl) mma_tile(tmem_base, z, acc2, 205);
         }
+        if (ok) umma_commit<G>(&tfull[0], pair_mask);
         DSX_STRACE(1, l * 8 + 6);
       }
-      if (ok) {
-        wait_epi(208);                                  // epi2 of the last layer (so that tfull's phases stay in order)
-        if (ok) umma_commit<G>(tfull, pair_mask);        // every MMA (incl. the skip accumulation) complete
-      }
+      // ---- deferred skip GEMM -> F1 (free since chunk 1's epilogue of the last layer) ----
+      if (ok) umma_commit<G>(lfin, pair_mask);
+      uint32_t ai = 0, accs = 0;
+      for (int l = 0; l < p.nl && ok; ++l)
+        for (int kb = 0; kb < 4 && ok; ++kb, ++ai) {
+          const uint32_t s = ai % AS;
+          ok = mbar_wait(&afull[s], (ai / AS) & 1, wd, 209);
+          if (!ok) break;
+          tc_fence_after();
+          const uint64_t a = umma_desc_sw128(smem_u32(aslot(s)));
+          for (int pl = 0; pl < WP && ok; ++pl) mma_tile(tmem_base + 256, a, accs, 210);
+          if (ok) umma_commit<G>(&aempty[s], pair_mask);
+        }
+      if (ok) umma_commit<G>(&tfull[1], pair_mask);
+      DSX_STRACE(1, 250);
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_HIGH));
@@ -336,20 +361,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
     const uint32_t tlane = static_cast<uint32_t>(quad * 32) << 16;
     const bool tracer = (warp == 4 && lane == 0);
     const bool row_valid = tile_valid && (t0 + r < p.T);
-    const bool edge_lo = r < 8, edge_hi = r >= kTile - 8;
+    const bool edge = (r < 8 || r >= kTile - 8) && tile_valid;       // rows the neighbour tiles need as halo rows
+    const int et = threadIdx.x - 128;               // 0..255: halo reception (side, row, 16-channel group)
     const size_t grow = (static_cast<size_t>(tile_valid ? b : 0) * p.Tp + t0 + r) * kC + half * 128;   // this thread's row
-    uint32_t tf = 0;
     bool ok = true;
-    auto release = [&]() {                          // this warp's part of the phase is done
+    auto release = [&](uint64_t* bar) {             // this warp's part of the phase on F0 / F1 is done
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(tempty, lead);
+      if (lane == 0) mbar_arrive_remote(bar, lead);
     };
-    auto wait_acc = [&](int code) -> bool {         // one lane polls, the warp reconverges on the shuffle
+    // tfull[0] completes twice per layer (GEMM1 chunk 0: parity 0, GEMM2: parity 1), tfull[1] once (parity l & 1; the skip GEMM
+    // after the last layer: parity nl & 1).  One lane polls, the warp reconverges on the shuffle.
+    auto wait_acc = [&](uint64_t* bar, uint32_t parity, int code) -> bool {
       int okv = 1;
-      if (lane == 0) okv = mbar_wait(tfull, tf & 1, wd, code) ? 1 : 0;
-      ++tf;
+      if (lane == 0) okv = mbar_wait(bar, parity, wd, code) ? 1 : 0;
       okv = __shfl_sync(0xffffffffu, okv, 0);
       tc_fence_after();
       return okv != 0;
@@ -378,76 +404,86 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
                    : make_float4(0.f, 0.f, 0.f, 0.f);
       __syncwarp();
 
-      // ---- epi1: z = sigmoid(gate) * tanh(filter), gate / filter = accumulator + CP; sub-passes of 8 column pairs, the CP
-      //      loads of the next sub-pass (and across the chunk boundary) fly while this one is computed ----
+      // ---- epi1: z = sigmoid(gate) * tanh(filter), gate / filter = accumulator + CP.  16 sub-passes of 8 column pairs (8 per
+      //      chunk); the CP stream is the latency that matters (ncu: long-scoreboard stalls on the accumulator + CP adds), so its
+      //      loads run TWO sub-passes ahead through three register buffers, across the chunk boundary too ----
       const float* cpl = p.CP + (static_cast<size_t>(l) * p.tiles + cp_tile) * 2 * kCpChunk + r * 4;
-      float4 cg[2][2], cf[2][2];
-      auto cp_issue = [&](const float* cph, int c, float4* g4, float4* f4) {
+      constexpr int NB = 3;
+      float4 cg[NB][2], cf[NB][2];
+      auto gcol = [&](int sp) { return (sp >> 2) * 64 + half * 32 + (sp & 3) * 8; };   // gate column of sub-pass sp of a chunk
+      auto cp_issue = [&](int q, float4* g4, float4* f4) {                               // q = chunk * 8 + sub-pass
+        const float* cph = cpl + (q >> 3) * kCpChunk;
+        const int c = gcol(q & 7);
 #pragma unroll
         for (int v4 = 0; v4 < 2; ++v4) {
           g4[v4] = ld_stream_f4(cph + ((c >> 2) + v4) * (kTile * 4), cp_policy);
           f4[v4] = ld_stream_f4(cph + (((128 + c) >> 2) + v4) * (kTile * 4), cp_policy);
         }
       };
-      auto gcol = [&](int sp) { return (sp >> 2) * 64 + half * 32 + (sp & 3) * 8; };   // gate column of sub-pass sp
-      cp_issue(cpl, gcol(0), cg[0], cf[0]);
-#pragma unroll 1
-      for (int h = 0; h < 2 && ok; ++h) {
-        const float* cph = cpl + h * kCpChunk;
-        if (tracer) DSX_STRACE(2, l * 12 + h * 3);
-        ok = wait_acc(301 + h);
+      cp_issue(0, cg[0], cf[0]);
+      cp_issue(1, cg[1], cf[1]);
+      if (l > 0) {                                  // the TMA store of z_{l-1} has finished reading the z area
+        int okv = 1;
+        if (lane == 0) okv = mbar_wait(zfree, (l - 1) & 1, wd, 305) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, okv, 0) != 0;
         if (!ok) break;
-        if (tracer) DSX_STRACE(2, l * 12 + h * 3 + 1);
-        uint32_t g[2][8], f[2][8];
-        tmem_ld_32x8(tmem_base + tlane + gcol(0), g[0]);
-        tmem_ld_32x8(tmem_base + tlane + 128 + gcol(0), f[0]);
+      }
 #pragma unroll
-        for (int sp = 0; sp < 8; ++sp) {
-          const int c = gcol(sp), cur = sp & 1, nxt = cur ^ 1;
-          tmem_ld_wait();
-          if (sp + 1 < 8) {
-            cp_issue(cph, gcol(sp + 1), cg[nxt], cf[nxt]);
-            tmem_ld_32x8(tmem_base + tlane + gcol(sp + 1), g[nxt]);
-            tmem_ld_32x8(tmem_base + tlane + 128 + gcol(sp + 1), f[nxt]);
-          } else if (h == 0) {
-            cp_issue(cph + kCpChunk, gcol(0), cg[nxt], cf[nxt]);
-          }
-          uint32_t hz[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float4 bg = cg[cur][e >> 1], bf = cf[cur][e >> 1];
-            const float g0 = __uint_as_float(g[cur][2 * e]) + ((e & 1) ? bg.z : bg.x);
-            const float g1 = __uint_as_float(g[cur][2 * e + 1]) + ((e & 1) ? bg.w : bg.y);
-            const float f0 = __uint_as_float(f[cur][2 * e]) + ((e & 1) ? bf.z : bf.x);
-            const float f1 = __uint_as_float(f[cur][2 * e + 1]) + ((e & 1) ? bf.w : bf.y);
-            float z0, z1;
-            if (p.fast_act) {
-              z0 = sigmoid_fast(g0) * tanh_approx(f0);
-              z1 = sigmoid_fast(g1) * tanh_approx(f1);
-            } else {
-              z0 = gate_acc(g0, f0);
-              z1 = gate_acc(g1, f1);
-            }
-            hz[e] = h2_bits(__floats2half2_rn(z0, z1));
-          }
-          // channel 128 h + c  ->  z k-block 2 h + (sp >> 2), 16-byte chunk half * 4 + (sp & 3) of row r
-          uint8_t* zrow = zbuf + (2 * h + (sp >> 2)) * kUnitBytes + r * 128;
-          *reinterpret_cast<uint4*>(zrow + (((half * 4 + (sp & 3)) ^ (r & 7)) << 4)) = make_uint4(hz[0], hz[1], hz[2], hz[3]);
+      for (int q = 0; q < 16; ++q) {
+        const int h = q >> 3, sp = q & 7;
+        if (sp == 0) {
+          if (tracer) DSX_STRACE(2, l * 12 + h * 3);
+          ok = wait_acc(&tfull[h], h == 0 ? 0u : static_cast<uint32_t>(l & 1), 301 + h);
+          if (!ok) break;
+          if (tracer) DSX_STRACE(2, l * 12 + h * 3 + 1);
         }
-        release();
-        if (tracer) DSX_STRACE(2, l * 12 + h * 3 + 2);
+        const uint32_t tF = tmem_base + tlane + h * 256;
+        uint32_t g[8], f[8];
+        tmem_ld_32x8(tF + gcol(sp), g);
+        tmem_ld_32x8(tF + 128 + gcol(sp), f);
+        if (q + 2 < 16) cp_issue(q + 2, cg[(q + 2) % NB], cf[(q + 2) % NB]);
+        tmem_ld_wait();
+        uint32_t hz[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 bg = cg[q % NB][e >> 1], bf = cf[q % NB][e >> 1];
+          const float g0 = __uint_as_float(g[2 * e]) + ((e & 1) ? bg.z : bg.x);
+          const float g1 = __uint_as_float(g[2 * e + 1]) + ((e & 1) ? bg.w : bg.y);
+          const float f0 = __uint_as_float(f[2 * e]) + ((e & 1) ? bf.z : bf.x);
+          const float f1 = __uint_as_float(f[2 * e + 1]) + ((e & 1) ? bf.w : bf.y);
+          float z0, z1;
+          if (p.fast_act) {
+            z0 = sigmoid_fast(g0) * tanh_approx(f0);
+            z1 = sigmoid_fast(g1) * tanh_approx(f1);
+          } else {
+            z0 = gate_acc(g0, f0);
+            z1 = gate_acc(g1, f1);
+          }
+          hz[e] = h2_bits(__floats2half2_rn(z0, z1));
+        }
+        // channel 128 h + c  ->  z k-block 2 h + (sp >> 2), 16-byte chunk half * 4 + (sp & 3) of row r
+        uint8_t* zrow = zbuf + (2 * h + (sp >> 2)) * kUnitBytes + r * 128;
+        *reinterpret_cast<uint4*>(zrow + (((half * 4 + (sp & 3)) ^ (r & 7)) << 4)) = make_uint4(hz[0], hz[1], hz[2], hz[3]);
+        if (sp == 7) {
+          release(&tempty[h]);
+          if (h == 1 && lane == 0) mbar_arrive(zdone);    // (after the proxy fence + warp sync of release())
+          if (tracer) DSX_STRACE(2, l * 12 + h * 3 + 2);
+        }
       }
       if (!ok) break;
 
       // ---- epi2: x <- (x + D2res + b) / sqrt2 in registers; y_{l+1} = fp16(x + d_{l+1}) -> next layer's A tiles ----
       if (tracer) DSX_STRACE(2, l * 12 + 6);
-      ok = wait_acc(303);
+      ok = wait_acc(&tfull[0], 1, 303);
       if (!ok) break;
       if (tracer) DSX_STRACE(2, l * 12 + 7);
       {
         const float4* bt = reinterpret_cast<const float4*>(tb);
         const float4* dt = reinterpret_cast<const float4*>(tb + 128);
-        __half* const yedge = p.Y + static_cast<size_t>(((l + 1) & 1) * 2) * p.plane_elems + grow;
+        // halo packets of y_{l+1}: side 0 = this tile's first 8 rows, side 1 = its last 8 rows
+        uint4* const ll_out = p.ll + ((static_cast<size_t>(tile_valid ? tile : 0) * 2 + ((l + 1) & 1)) * 2 + (r < 8 ? 0 : 1)) * 512 +
+                              (r & 7) * 64 + half * 32;
+        const unsigned int seq_next = p.seq_base + static_cast<unsigned int>(l + 1);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           uint32_t o[32];
@@ -472,25 +508,64 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
             if (has_next) {
               const uint4 v = make_uint4(hy[0], hy[1], hy[2], hy[3]);
               *reinterpret_cast<uint4*>(yrow + ((((jj & 1) * 4 + c8) ^ (r & 7)) << 4)) = v;
-              if ((edge_lo || edge_hi) && row_valid) *reinterpret_cast<uint4*>(yedge + jj * 32 + c8 * 8) = v;
+              if (edge) {                               // rows beyond T travel as zeros (the conv's zero padding)
+                uint4* q = ll_out + jj * 8 + c8 * 2;
+                asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(q), "r"(v.x), "r"(seq_next), "r"(v.y), "r"(seq_next) : "memory");
+                asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(q + 1), "r"(v.z), "r"(seq_next), "r"(v.w), "r"(seq_next) : "memory");
+              }
             }
           }
         }
       }
-      release();
+      release(&tempty[0]);
       if (tracer) DSX_STRACE(2, l * 12 + 8);
-      if (has_next && tile_valid && (quad == 0 || quad == 3)) {
-        // publish the edge rows of y_{l+1}: generic-proxy global stores -> async-proxy (TMA) readers in the neighbour CTAs
-        fence_proxy_async_all();
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) flag_publish(p.flags + tile);
+      if (has_next) {
+        // ---- receive the halo rows of y_{l+1} from the neighbour tiles (GEMM2 of this layer has completed, so no MMA reads
+        //      the slots): thread -> (side, row, 16 channels) = 4 packets; a packet is valid once both of its sequence words
+        //      match.  Tiles at an utterance end (and padding CTAs) write zeros. ----
+        const int side = et >> 7, row8 = (et >> 4) & 7, c16 = et & 15;
+        const bool have = side == 0 ? nb_lo : nb_hi;
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+        if (have) {
+          const unsigned int seq_next = p.seq_base + static_cast<unsigned int>(l + 1);
+          const uint4* src = p.ll + ((static_cast<size_t>(side == 0 ? tile - 1 : tile + 1) * 2 + ((l + 1) & 1)) * 2 + (side == 0 ? 1 : 0)) * 512 +
+                             row8 * 64 + c16 * 4;
+          uint32_t spins = 0;
+          while (true) {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "l"(src) : "memory");
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(src + 1) : "memory");
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q2.x), "=r"(q2.y), "=r"(q2.z), "=r"(q2.w) : "l"(src + 2) : "memory");
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q3.x), "=r"(q3.y), "=r"(q3.z), "=r"(q3.w) : "l"(src + 3) : "memory");
+            if (q0.y == seq_next && q0.w == seq_next && q1.y == seq_next && q1.w == seq_next && q2.y == seq_next && q2.w == seq_next &&
+                q3.y == seq_next && q3.w == seq_next)
+              break;
+            if (((++spins) & 0x3f) == 0) {
+              if (*(volatile int*)wd.status != 0) { ok = false; break; }
+              if (globaltimer_ns() > wd.deadline_ns) {
+                atomicCAS(wd.status, 0, 307);
+                ok = false;
+                break;
+              }
+            }
+          }
+        }
+        {
+          const int hrow = (side == 0 ? 0 : kTile + 8) + row8;            // row of the slot: [0, 8) left halo, [136, 144) right halo
+          uint8_t* dst = yslots + (c16 >> 2) * Cfg::YSLOT + hrow * 128;
+          const int ch = (c16 & 3) * 2;                                    // first of the two 16-byte chunks
+          *reinterpret_cast<uint4*>(dst + ((ch ^ row8) << 4)) = make_uint4(q0.x, q0.z, q1.x, q1.z);
+          *reinterpret_cast<uint4*>(dst + (((ch + 1) ^ row8) << 4)) = make_uint4(q2.x, q2.z, q3.x, q3.z);
+        }
+        fence_proxy_async_smem();
+        ok = __all_sync(0xffffffffu, ok);
+        if (lane == 0) mbar_arrive_remote(yhalo, lead);
+        if (tracer) DSX_STRACE(2, l * 12 + 9);
       }
     }
 
-    // ---- exit: skip sum (TMEM S, accumulated over all layers) -> SKIP (fp32) and the fp16 hi / lo operand of the head
+    // ---- exit: skip sum (deferred GEMM over all layers, in F1) -> SKIP (fp32) and the fp16 hi / lo operand of the head
     //      GEMM; residual stream back to X (debug tap) ----
-    if (ok) ok = wait_acc(304);
+    if (ok) ok = wait_acc(&tfull[1], static_cast<uint32_t>(p.nl & 1), 304);
     if (ok) {
       const float* bs = p.bskip + static_cast<size_t>(p.nl - 1) * kC + half * 128;
 #pragma unroll 1
@@ -507,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
             v.y = __uint_as_float(o[c4 * 4 + 1]) + bb.y;
             v.z = __uint_as_float(o[c4 * 4 + 2]) + bb.z;
             v.w = __uint_as_float(o[c4 * 4 + 3]) + bb.w;
-            *reinterpret_cast<float4*>(p.SKIP + grow + jj * 32 + c4 * 4) = v;
+            if (p.taps) *reinterpret_cast<float4*>(p.SKIP + grow + jj * 32 + c4 * 4) = v;
             if (p.nl == p.L) {
               const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l, sc = v.z * p.inv_sqrt_l, sd = v.w * p.inv_sqrt_l;
               const __half2 h0 = __floats2half2_rn(sa, sb), h1 = __floats2half2_rn(sc, sd);
@@ -520,7 +595,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
           }
         }
       }
-      if (row_valid) {
+      if (row_valid && p.taps) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           *reinterpret_cast<float4*>(p.X + grow + i * 4) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
@@ -667,11 +742,10 @@ int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_
   memset(&prm, 0, sizeof(prm));
   prm.tm_w = sr ? h->tm_wsr : h->tm_w;
   prm.tm_y0 = h->tm_yh[0];
-  prm.tm_ye[0] = h->tm_ye[0];
-  prm.tm_ye[1] = h->tm_ye[1];
+  prm.tm_z = h->tm_z;
+  prm.taps = h->want_taps;
   prm.X = h->ws.X;
   prm.SKIP = h->ws.SKIP;
-  prm.Y = h->ws.Y;
   prm.plane_elems = g.frames_padded() * kC;
   prm.CP = h->ws.CP;
   prm.cp_prefetch = h->cp_prefetch;
@@ -686,7 +760,7 @@ int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_
   prm.w_row0 = sr ? (wset % std::max(1, m.wsr_sets)) * m.L * kStackSetRowsPerLayer : 0;
   prm.s16 = h->ws.S16;
   prm.inv_sqrt_l = 1.0f / sqrtf(static_cast<float>(m.L));
-  prm.fast_act = (h->precision == DSX_PREC_FP16) ? 1 : 0;
+  prm.fast_act = h->gate_approx >= 0 ? h->gate_approx : 1;
   prm.status = h->status_dev;
   prm.budget_ns = 4000000000ull;
   prm.trace = h->trace_dev;
@@ -695,16 +769,23 @@ int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_
   const int utt_per_group = cap_tiles / g.tiles_per_utt;
   DSX_CHECK(utt_per_group >= 1, DSX_E_INVALID, "stack kernel: an utterance of %d tiles does not fit %d co-resident CTAs",
             g.tiles_per_utt, cap_tiles);
-  DSX_TRY(ensure_flags(h, g.tiles + 2));
-  if (h->flags_geom_b != g.B || h->flags_geom_t != g.T || h->flags_kind != 2) {   // counters are in lockstep only within one geometry
-    DSX_CUDA(cudaMemsetAsync(h->flags_dev, 0, static_cast<size_t>(h->flags_cap) * sizeof(unsigned int), s));
-    h->flag_count = 0;
-    h->flags_geom_b = g.B;
-    h->flags_geom_t = g.T;
-    h->flags_kind = 2;
+  // halo packets: 32 KB per tile, zeroed once (sequence numbers start at 1 and only grow, so packets left behind by earlier
+  // evaluations, other geometries or an aborted launch can never be mistaken for the current layer's)
+  const size_t ll_bytes = static_cast<size_t>(g.tiles + 2) * 4 * 512 * sizeof(uint4);
+  if (h->ll_cap < ll_bytes) {
+    if (h->ll_dev) cudaFree(h->ll_dev);
+    h->ll_dev = nullptr;
+    h->ll_cap = 0;
+    DSX_CUDA(cudaMalloc(&h->ll_dev, ll_bytes));
+    DSX_CUDA(cudaMemsetAsync(h->ll_dev, 0, ll_bytes, s));
+    h->ll_cap = ll_bytes;
   }
-  prm.flags = h->flags_dev;
-  prm.flag_base = h->flag_count;
+  if (h->ll_seq > 0xFFFF0000u) {                      // (practically unreachable) wrap: start over on a clean buffer
+    DSX_CUDA(cudaMemsetAsync(h->ll_dev, 0, h->ll_cap, s));
+    h->ll_seq = 1;
+  }
+  prm.ll = static_cast<uint4*>(h->ll_dev);
+  prm.seq_base = h->ll_seq;
   bool& attr_done = h->attr_stack[x2 ? 1 : 0];
   if (!attr_done) {
     if (x2) DSX_CUDA(cudaFuncSetAttribute(k_tc_stack<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg::SMEM_BYTES));
@@ -733,7 +814,7 @@ int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_
     h->launches++;
     h->stack_launches++;
   }
-  h->flag_count += static_cast<unsigned int>(kFlagsPerLayer * std::max(nl - 1, 0));
+  h->ll_seq += static_cast<unsigned int>(nl);
   return DSX_OK;
 }
 

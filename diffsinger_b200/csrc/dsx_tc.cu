@@ -1005,6 +1005,7 @@ struct TcHeadParams {
   unsigned long long seed, offset;
   int b_off;               // global index of utterance 0 (Philox counters of a sharded batch)
   DdpmCoef c;
+  PlmsFuse pl;             // TC_PLMS
   float* X;                // [B][Tp][256]
   __half* Y;               // conv input of layer 0, plane 0; plane 1 at + plane_elems
   size_t plane_elems;
@@ -1316,7 +1317,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
     if (ok) {
       tc_fence_after();
       const int m_lo = half * 40;
-      const bool need_x = (p.flags & (TC_UPDATE | TC_INPROJ)) != 0;
+      const bool need_x = (p.flags & (TC_UPDATE | TC_INPROJ | TC_PLMS)) != 0;
       const bool need_z = (p.flags & TC_UPDATE) && p.c.sigma != 0.f;
       const size_t xrow = static_cast<size_t>(b) * p.xs.b + static_cast<size_t>(t) * p.xs.t;
 #pragma unroll 1
@@ -1355,6 +1356,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_head(const __grid_constant__
             const float mean = __fadd_rn(__fmul_rn(p.c.c1, xr), __fmul_rn(p.c.c2, xv[i]));
             xv[i] = __fadd_rn(mean, __fmul_rn(p.c.sigma, zn[i]));
             if (row_valid) p.x[xrow + static_cast<size_t>(m) * p.xs.c] = xv[i];
+          }
+          if ((p.flags & TC_PLMS) && row_valid) {
+            // linear multistep combination + get_x_pred, the reference's left-to-right fp32 order (k_plms_update)
+            const size_t ei = (static_cast<size_t>(b) * p.M + m) * p.T + t;
+            float comb = __fmul_rn(p.pl.c.w0, ev);
+            if (p.pl.h1) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w1, p.pl.h1[ei]));
+            if (p.pl.h2) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w2, p.pl.h2[ei]));
+            if (p.pl.h3) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w3, p.pl.h3[ei]));
+            const float ep = __fdiv_rn(comb, p.pl.c.denom);
+            const float inner = __fsub_rn(__fmul_rn(p.pl.c.kx, xv[i]), __fmul_rn(p.pl.c.ke, ep));
+            xv[i] = __fadd_rn(xv[i], __fmul_rn(p.pl.c.a_diff, inner));
+            if (p.pl.eps_store) p.pl.eps_store[ei] = ev;
+            if (p.pl.x_out) p.pl.x_out[ei] = xv[i];
+            else p.x[xrow + static_cast<size_t>(m) * p.xs.c] = xv[i];
           }
         }
         if (do_in) {
@@ -1603,6 +1618,7 @@ int tc_prepare_maps(dsx_handle* h, const Geom& g) {
     DSX_TRY(make_map_act(&h->tm_s16[pl], h->ws.S16 + static_cast<size_t>(pl) * plane, kC, g.T, g.Tp, g.B));
   }
   DSX_TRY(make_map_2d(&h->tm_whead, h->m.whead, 32 * 128, 128));
+  DSX_TRY(make_map_act(&h->tm_z, h->ws.Z, kC, g.T, g.Tp, h->m.L * g.B));
   h->tm_geom = g;
   h->tm_epoch = h->ws_epoch;
   h->tm_group = h->tc_group;
@@ -1786,7 +1802,7 @@ static int launch_tc_head_t(dsx_handle* h, const TcHeadParams& prm, int tiles, c
 
 int launch_tc_head(dsx_handle* h, const Geom& g, int flags, float* x_state, dsx_strides xs, float* eps_out,
                    const float* noise, uint64_t seed, uint64_t offset, DdpmCoef c, int next_row0, int row_per_b,
-                   cudaStream_t s) {
+                   cudaStream_t s, const PlmsFuse* plms) {
   const ModelDev& m = h->m;
   TcHeadParams prm;
   memset(&prm, 0, sizeof(prm));
@@ -1801,6 +1817,7 @@ int launch_tc_head(dsx_handle* h, const Geom& g, int flags, float* x_state, dsx_
   prm.b_off = h->batch_offset;
   prm.offset = offset;
   prm.c = c;
+  if (plms) prm.pl = *plms;
   prm.X = h->ws.X;
   prm.Y = h->ws.Y;                       // layer 0 reads buffer 0
   prm.plane_elems = g.frames_padded() * kC;

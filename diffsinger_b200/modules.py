@@ -110,10 +110,20 @@ class DiffNet(nn.Module):
         return self._dsx
 
     def forward(self, spec, diffusion_step, cond):
-        """spec [B,1,M,T], diffusion_step [B], cond [B,H,T] -> [B,1,M,T] (net.py:107-130)."""
-        if torch.is_grad_enabled() and (spec.requires_grad or any(p.requires_grad for p in self.parameters())):
+        """spec [B,1,M,T], diffusion_step [B], cond [B,H,T] -> [B,1,M,T] (net.py:107-130).
+
+        Training mode (``self.training``: p_losses under autograd) or an input that itself requires grad keeps the module
+        graph in plain PyTorch ops; everything else -- ``model.eval()``, with or without ``torch.no_grad()`` -- is inference
+        and goes to libdsx (no silent PyTorch path: CPU tensors / a missing library raise)."""
+        if self.training or (torch.is_grad_enabled() and spec.requires_grad):
             return self._forward_autograd(spec, diffusion_step, cond)
         return self.dsx.diffnet_forward(spec, diffusion_step, cond)
+
+    def __getstate__(self):
+        # the lazily created sampler holds a ctypes handle: copies (EMA deepcopy, torch.save of the module) rebuild theirs
+        state = self.__dict__.copy()
+        state["_dsx"] = None
+        return state
 
     def _forward_autograd(self, spec, diffusion_step, cond):
         # training branch only (p_losses); not a fallback for inference

@@ -273,7 +273,15 @@ class DsxSampler:
         h = self.ensure_weights(dev)
         B, _, T = cond.shape
         M = self.M
-        assert not cond.is_cuda
+        for name, t in (("cond", cond), ("fs2_mel", fs2_mel), ("x_start", x_start), ("mel2ph", mel2ph), ("out", out)):
+            if t is not None and t.is_cuda:
+                raise DsxError(f"infer_host takes HOST tensors ({name} is a CUDA tensor); use infer() for device tensors")
+        cond = cond.float()
+        # the C side copies B*H*T contiguous floats and then addresses them through the strides: the view must be dense
+        # (a permutation of a contiguous [B,H,T] block, e.g. the reference's transposed [B,T,H]); anything else is compacted
+        span = sum((n - 1) * st for n, st in zip(cond.shape, cond.stride())) + 1
+        if span != cond.numel() or min(cond.stride()) < 1:
+            cond = cond.contiguous()
         c = lambda t: None if t is None else t.float().contiguous()
         fs2_mel, x_start = c(fs2_mel), c(x_start)
         smin, smax = spec_min.float().reshape(-1).contiguous().cpu(), spec_max.float().reshape(-1).contiguous().cpu()

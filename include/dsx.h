@@ -203,6 +203,9 @@ enum {
   DSX_OPT_STACK_KERNEL = 4, /* 1 (default): the register-resident stack kernel (residual stream in registers, conv input in
                                shared memory, skip sum in tensor memory) for FP16 / FP16X2 / FP16S; 0: the round-1 layer kernel */
   DSX_OPT_SR_SETS = 5,      /* number of stochastically rounded weight sets of DSX_PREC_FP16S; set before dsx_load_diffnet */
+  DSX_OPT_GATE_APPROX = 7,  /* stack kernel: gate sigmoid(g) * tanh(f) with tanh.approx.f32 (1) or with ex2 / rcp to ~2e-7 (0);
+                               -1 (default) = 1: its 2^-11 relative error is below the fp16 rounding of the gate output that
+                               follows (K = 100 golden loop: 3.3e-4 either way in FP16S, 1.5e-4 / 1.6e-4 in FP16X2) */
   DSX_OPT_BATCH_OFFSET = 6  /* global index of this call's utterance 0: the in-kernel Philox noise of utterance b is drawn for
                                index (offset + b), so a batch sharded over ranks (one seed) reproduces the unsharded noise */
 };
@@ -221,8 +224,8 @@ int dsx_debug_set_layer_limit(dsx_handle* h, int n_layers);
 /* Hardware self-tests of the tcgen05 / TMA encodings this library relies on (one small
  * launch each, results checked on the host).  which = -1 runs all; returns 0 when every
  * selected test passes, otherwise DSX_E_KERNEL with the failing names in dsx_last_error().
- * which = 0 / 1: UMMA + TMA round trip with cta_group::1 / ::2; informational experiments (not part of -1):
- * 2 = row-shifted SWIZZLE_128B operand descriptors, 3 = TMA ingest rate of one SM versus issuing threads / box size.
+ * which = 0 / 1: UMMA + TMA round trip with cta_group::1 / ::2; 2 = row-shifted SWIZZLE_128B operand descriptors (the
+ * dilated taps rely on them); 3 = TMA ingest micro-benchmark (informational, only in -DDSX_EXPERIMENTS builds, not part of -1).
  * report (may be NULL): host buffer receiving a text report. */
 int dsx_selftest(int device, int which, char* report, int report_bytes);
 

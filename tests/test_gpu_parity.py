@@ -284,26 +284,51 @@ def test_strided_inputs(dsx):
     assert (outs[2] - ref).abs().max() < 2e-4
 
 
+SHAPES = ((1, 96), (2, 96), (3, 333), (1, 300), (2, 1000), (5, 128), (2, 129), (40, 520))     # last: 200 tiles -> 2 launch groups
+
+
+def _eval_shapes(dsx, prec, options):
+    s, dev = make_sampler(dsx, 4, prec)
+    for k, v in options:
+        s.set_option(k, v)
+    outs = []
+    for B, T in SHAPES:
+        x, cond = rs_normal(40 + B, (B, 1, 80, T)).to(dev), rs_normal(50 + T, (B, 256, T)).to(dev)
+        t = torch.full((B,), 7, dtype=torch.long, device=dev)
+        outs.append(s.diffnet_forward(x, t, cond).cpu())
+        outs.append(s.diffnet_forward(x, t + 1, cond).cpu())
+    launches = s.info(9)
+    s.close()
+    return outs, launches
+
+
 @pytest.mark.parametrize("prec", ["fp16x2", "fp16x3"])
 def test_stack_mode_matches_per_layer_launches(dsx, prec):
-    """The persistent layer-stack launch (tiles synchronise through publish counters) must reproduce the
-    one-launch-per-layer path bit for bit, across changing batch geometries on one handle (padding tiles,
-    partial tiles, dilation cycle 4)."""
+    """Round-1 layer kernel: its persistent layer-stack launch (tiles synchronise through publish counters) must reproduce
+    its one-launch-per-layer mode bit for bit, across changing batch geometries on one handle (padding tiles, partial
+    tiles, dilation cycle 4)."""
     from diffsinger_b200 import _capi
-    res = {}
-    for mode in (0, 1):
-        s, dev = make_sampler(dsx, 4, prec)
-        s.set_option(_capi.OPT_STACK_MODE, mode)
-        outs = []
-        for B, T in ((1, 96), (2, 96), (3, 333), (1, 300), (2, 1000), (40, 520)):     # last: 200 tiles -> 2 groups
-            x, cond = rs_normal(40 + B, (B, 1, 80, T)).to(dev), rs_normal(50 + T, (B, 256, T)).to(dev)
-            t = torch.full((B,), 7, dtype=torch.long, device=dev)
-            outs.append(s.diffnet_forward(x, t, cond).cpu())
-            outs.append(s.diffnet_forward(x, t + 1, cond).cpu())
-        res[mode] = outs
-        s.close()
-    for a, b in zip(res[0], res[1]):
-        assert torch.equal(a, b)
+    a, _ = _eval_shapes(dsx, prec, ((_capi.OPT_STACK_KERNEL, 0), (_capi.OPT_STACK_MODE, 0)))
+    b, _ = _eval_shapes(dsx, prec, ((_capi.OPT_STACK_KERNEL, 0), (_capi.OPT_STACK_MODE, 1)))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("prec", ["fp16x2", "fp16"])
+def test_stack_kernel_matches_layer_kernel(dsx, prec):
+    """The register-resident stack kernel (dsx_stack.cu: x in registers, y in shared memory, halo packets, deferred skip GEMM)
+    against the round-1 layer kernel on the same operands: same products, different fp32 summation order (centre taps first,
+    skip sum as one K = 5120 contraction), so agreement is to rounding, not bit for bit -- over ragged geometries changing on
+    one handle (partial last tiles, single-tile utterances, odd tile counts -> padding CTA, > 148 tiles -> launch groups).
+    The stack kernel itself is deterministic: the same call twice is bit-identical."""
+    from diffsinger_b200 import _capi
+    a, la = _eval_shapes(dsx, prec, ((_capi.OPT_STACK_KERNEL, 0), (_capi.OPT_GATE_APPROX, 0)))
+    b, lb = _eval_shapes(dsx, prec, ((_capi.OPT_STACK_KERNEL, 1), (_capi.OPT_GATE_APPROX, 0 if prec == "fp16x2" else 1)))
+    c, _ = _eval_shapes(dsx, prec, ((_capi.OPT_STACK_KERNEL, 1), (_capi.OPT_GATE_APPROX, 0 if prec == "fp16x2" else 1)))
+    assert la == 0 and lb > 0
+    for u, v, w in zip(a, b, c):
+        assert (u - v).abs().max() < (6e-4 if prec == "fp16x2" else 3e-3), (u - v).abs().max()
+        assert torch.equal(v, w)
 
 
 @pytest.mark.parametrize("prec", ["fp16x2", "fp16x3"])
@@ -336,6 +361,69 @@ def test_shard_equivalence_and_determinism(dsx):
     halves = torch.cat([s.sample_ddpm(xT[i:i + 2], cond[i:i + 2], 100, K, noise=noise[:, i:i + 2].contiguous())
                         for i in (0, 2)], 0)
     assert torch.equal(full, again) and torch.equal(full, halves)
+    s.close()
+
+
+def test_seed_mode_shard_equivalence(dsx):
+    """In-kernel Philox noise is indexed by the GLOBAL utterance number (DSX_OPT_BATCH_OFFSET, set by
+    parallel.sharded_infer): with one seed, two half-batch shards reproduce the unsharded batch bit for bit and the
+    utterances of different shards get different noise."""
+    from diffsinger_b200 import _capi
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    s, dev = make_sampler(dsx, 1, "fp16s", S)
+    B, T, K = 4, 200, 5
+    cond = rs_normal(3, (B, 256, T)).to(dev)
+    smin, smax = torch.full((80,), -5.0, device=dev), torch.full((80,), 0.5, device=dev)
+    fs2 = rs_normal(8, (B, T, 80)).to(dev) - 2.0
+    full = s.infer(cond, K, smin, smax, fs2_mel=fs2, seed=77)                 # Philox start noise + step noise
+    halves = []
+    for lo in (0, 2):
+        s.set_option(_capi.OPT_BATCH_OFFSET, lo)
+        halves.append(s.infer(cond[lo:lo + 2], K, smin, smax, fs2_mel=fs2[lo:lo + 2], seed=77))
+    s.set_option(_capi.OPT_BATCH_OFFSET, 0)
+    assert torch.equal(full, torch.cat(halves, 0))
+    same_inputs = s.infer(cond[:1].repeat(2, 1, 1), K, smin, smax, fs2_mel=fs2[:1].repeat(2, 1, 1), seed=77)
+    assert not torch.equal(same_inputs[0], same_inputs[1])                   # different utterance index -> different noise
+    s.close()
+
+
+def test_conditioner_cache_and_host_checks(dsx):
+    """cond == NULL re-uses the packed conditioner (dsx_set_cond); a stale geometry is refused; dsx_infer_host refuses a
+    non-dense host view instead of reading outside its staging copy."""
+    import ctypes
+    from diffsinger_b200 import _capi
+    from diffsinger_b200.sampler import _ptr, _strides_bct, _stream
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    s, dev = make_sampler(dsx, 1, "fp16x2", S)
+    B, T = 2, 150
+    x, cond = rs_normal(1, (B, 1, 80, T)).to(dev), rs_normal(2, (B, 256, T)).to(dev)
+    t = torch.tensor([5, 60], device=dev)
+    a = s.diffnet_forward(x, t, cond)
+    l0 = s.info(_capi.INFO_KERNEL_LAUNCHES)
+    b = s.diffnet_forward(x, t, cond)                      # same conditioner tensor: pack + projection skipped
+    l1 = s.info(_capi.INFO_KERNEL_LAUNCHES)
+    cond2 = cond.clone()
+    c = s.diffnet_forward(x, t, cond2)                     # new tensor: packed again
+    l2 = s.info(_capi.INFO_KERNEL_LAUNCHES)
+    assert torch.equal(a, b) and torch.equal(a, c) and (l2 - l1) > (l1 - l0)
+    cond2.add_(1.0)                                        # in-place change bumps the version counter -> re-packed
+    d = s.diffnet_forward(x, t, cond2)
+    assert not torch.equal(a, d)
+    eps = torch.empty_like(x)
+    rc = _capi.lib.dsx_diffnet_forward(s._h, _ptr(x[:1]), _strides_bct(x[:1], (0, 2, 3)), _ptr(t[:1]), ctypes.c_void_p(0),
+                                       _strides_bct(cond, (0, 1, 2)), _ptr(eps), 1, T, _stream(dev))
+    assert rc == -3 and b"dsx_set_cond" in _capi.lib.dsx_last_error()          # DSX_E_STATE: other (B, T)
+    host_cond = rs_normal(4, (B, 256, T + 10))[:, :, :T]                        # non-dense view: compacted by the wrapper ...
+    out = s.infer_host(host_cond, 3, torch.full((80,), -5.0), torch.full((80,), 0.5), x_start=rs_normal(5, (B, 1, 80, T)), seed=1)
+    assert torch.isfinite(out).all()
+    smin = torch.full((80,), -5.0)
+    xs = rs_normal(5, (B, 1, 80, T))
+    mel = torch.empty(B, T, 80)
+    rc = _capi.lib.dsx_infer_host(s._h, _ptr(host_cond), _strides_bct(host_cond, (0, 1, 2)), None, _ptr(xs), 1, None, _ptr(smin),
+                                  _ptr(smin + 5), B, T, 3, 0, _ptr(mel), _stream(dev))
+    assert rc == -1 and b"dense" in _capi.lib.dsx_last_error()                 # ... and refused by the C ABI itself
+    with pytest.raises(dsx.DsxError, match="HOST"):
+        s.infer_host(host_cond.contiguous(), 3, smin, smin + 5, x_start=xs.to(dev), seed=1)
     s.close()
 
 

@@ -23,7 +23,7 @@ from conftest import HP, golden, rs_normal  # noqa: E402
 DEV = torch.device("cuda", 0)
 
 
-def make(cycle, prec, stack_kernel=1, schedule=None, sets=None):
+def make(cycle, prec, stack_kernel=1, schedule=None, sets=None, opts=()):
     hp = dict(HP, dilation_cycle_length=cycle)
     torch.manual_seed(0)
     net = dsx.DiffNet(80, hparams=hp)
@@ -35,6 +35,8 @@ def make(cycle, prec, stack_kernel=1, schedule=None, sets=None):
         s.set_option(_capi.OPT_SR_SETS, sets)
     s.ensure_weights(DEV)
     s.set_option(_capi.OPT_STACK_KERNEL, stack_kernel)
+    for k, v in opts:
+        s.set_option(k, v)
     if schedule is not None:
         s.set_schedule(schedule)
     return s
@@ -124,6 +126,42 @@ def parity():
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "dev_parity.json"), "w"), indent=1)
 
 
+def experiments():
+    """tuning knobs: publish mode (fences of the halo hand-over) and the approximate gate, timing + K=100 golden error"""
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    g = golden("ddpm_lj_K100.npz")
+    condg, xTg = torch.from_numpy(g["cond"]).to(DEV), torch.from_numpy(g["xT"]).to(DEV)
+    noise = rs_normal(int(g["noise_seed"]), (100,) + tuple(g["xT"].shape)).to(DEV)
+    B, T = 16, 1024
+    gen = torch.Generator().manual_seed(1)
+    cond = torch.randn(B, T, 256, generator=gen).transpose(1, 2).to(DEV)
+    x = torch.randn(B, 1, 80, T, generator=gen).to(DEV)
+    res = {}
+    for prec in ("fp16s", "fp16x2"):
+        for pm in (0,):
+            for ga in (0, 1):
+                s = make(1, prec, 1, S, opts=((_capi.OPT_GATE_APPROX, ga),))
+                x0 = s.sample_ddpm(xTg, condg, 100, 100, noise=noise).cpu().numpy()
+                d = np.abs(x0 - g["x0"])
+                s.sample_ddpm(x, cond, 100, 4, seed=1)
+                torch.cuda.synchronize()
+                s.set_option(_capi.OPT_PROFILE, 1)
+                ref = None
+                for rep in range(3):
+                    out = s.sample_ddpm(x, cond, 100, 10, seed=1)
+                    ref = out if ref is None else ref
+                    assert torch.equal(out, ref), "non-deterministic result (race?)"
+                torch.cuda.synchronize()
+                layer_ms = s.info(_capi.INFO_LAYER_KERNEL_NS) / 1e6 / max(s.info(_capi.INFO_LAYER_KERNEL_LAUNCHES), 1)
+                s.set_option(_capi.OPT_PROFILE, 0)
+                r = dict(max=float(d.max()), mae=float(d.mean()), stack_ms=layer_ms,
+                         stack_tflops=B * T * 20 * 1048576 / (layer_ms * 1e-3) / 1e12)
+                res[f"{prec}_pm{pm}_ga{ga}"] = r
+                print(f"exp {prec} publish_mode={pm} gate_approx={ga}: {r}", flush=True)
+                s.close()
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "dev_experiments.json"), "w"), indent=1)
+
+
 def timing():
     S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
     res = {}
@@ -176,15 +214,16 @@ def trace():
         a = np.array(buf[:], dtype=np.int64).reshape(2, 3, 256)
         out[prec] = a.tolist()
         base = a[0, 1, 0]
-        print(f"--- {prec}: MMA thread (CTA 0) per layer: start G1c0, end G1c0, start G1c1, end G1c1, G2res start, G2res end, G2skip end")
+        print(f"--- {prec}: MMA thread (CTA 0) per layer: G1 start, centre taps issued, halo landed, G1 issued, G2 kb0 start, G2 kb2 start, G2 issued")
         for l in range(0, 6):
             print(l, [int(a[0, 1, l * 8 + k] - base) for k in range(7)])
         print("epilogue (warp 4): per layer e1c0 [enter, acc ready, done], e1c1 [...], e2 [enter, ready, done]")
         for l in range(0, 6):
             print(l, [int(a[0, 2, l * 12 + k] - base) for k in range(9)])
-        print("producer 0: per layer [g1done seen, flags seen, halo issued]")
+        print("producer 0: per layer [g1done seen, flags seen, halo issued, z stored]")
         for l in range(1, 6):
-            print(l, [int(a[0, 0, l * 4 + k] - base) for k in range(3)])
+            print(l, [int(a[0, 0, l * 4 + k] - base) for k in range(4)])
+        print("end of skip GEMM issue (MMA thread)", int(a[0, 1, 250] - base), "epilogue exit", int(a[0, 2, 250] - base))
         per_layer = (a[0, 1, 19 * 8] - a[0, 1, 1 * 8]) / 18.0
         print(f"{prec}: cycles per layer (MMA thread, layers 1..19): {per_layer:.0f}")
         s.close()
@@ -192,4 +231,4 @@ def trace():
 
 
 if __name__ == "__main__":
-    {"quick": quick, "parity": parity, "timing": timing, "trace": trace}[sys.argv[1]]()
+    {"quick": quick, "experiments": experiments, "parity": parity, "timing": timing, "trace": trace}[sys.argv[1]]()
