@@ -70,6 +70,7 @@ struct TcStackParams {
   CUtensorMap tm_w;        // weight tiles, 2D [rows][64], box 64 x 128 rows
   CUtensorMap tm_y0;       // Y buffer 0 (written by the input projection), box 64 ch x 144 frames: layer 0 incl. halos
   CUtensorMap tm_z;        // Z [L * B][T][256] fp16, box 64 ch x 128 frames: z of every layer (store per layer, load for the skip GEMM)
+  CUtensorMap tm_s16[2];   // S16 hi / lo planes [B][T][256], box 64 ch x 128 frames (TMA store at exit)
   float* X;                // [B][Tp][256] residual stream: read at entry, written back at exit
   float* SKIP;             // [B][Tp][256] skip sum (debug tap / fp32 copy), written at exit
   size_t plane_elems;
@@ -128,8 +129,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
   uint64_t* lfin = zfree + 1;       // every MMA of the layers complete: z / y areas become the A ring of the skip GEMM
   uint64_t* afull = lfin + 1;       // [AS] A tile of the skip GEMM landed (leader's barrier)
   uint64_t* aempty = afull + AS;    // [AS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + AS);
-  static_assert((2 * Cfg::WSLOTS + 9 + 2 * Cfg::ASLOTS) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
+  uint64_t* sdone = aempty + AS;    // exit: this CTA's 8 epilogue warps have written the S16 tiles (local)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdone + 1);
+  static_assert((2 * Cfg::WSLOTS + 10 + 2 * Cfg::ASLOTS) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
   auto aslot = [&](int s) -> uint8_t* { return s < 4 ? zbuf + s * kUnitBytes : yslots + (s - 4) * kUnitBytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
     tma_prefetch_desc(&p.tm_w);
     tma_prefetch_desc(&p.tm_y0);
     tma_prefetch_desc(&p.tm_z);
+    tma_prefetch_desc(&p.tm_s16[0]);
+    tma_prefetch_desc(&p.tm_s16[1]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < WS; ++s) {
@@ -165,6 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
     mbar_init(zdone, kEpiWarps);
     mbar_init(zfree, 1);
     mbar_init(lfin, 1);
+    mbar_init(sdone, kEpiWarps);
     for (int s = 0; s < AS; ++s) {
       mbar_init(&afull[s], 1);
       mbar_init(&aempty[s], 1);
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
     if (warp == 0 && lane == 0) {
       // ================================ activation producer ================================
       bool ok = true;
+      const uint64_t z_policy = l2_policy_evict_last();   // z comes back for the skip GEMM: keep it in L2 ahead of the CP stream
       auto cp_prefetch = [&](int l, int h) {
         if (!p.cp_prefetch || l >= p.nl) return;
         const char* src = reinterpret_cast<const char*>(p.CP + ((static_cast<size_t>(l) * p.tiles + cp_tile) * 2 + h) * kCpChunk);
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         // the z area may be overwritten (next layer's chunk 0) once the store has read it
         ok = mbar_wait(zdone, l & 1, wd, 108);
         if (!ok) break;
-        for (int kb = 0; kb < 4; ++kb) tma_store_3d(&p.tm_z, zbuf + kb * kUnitBytes, kb * 64, t0, l * p.B + zq);
+        for (int kb = 0; kb < 4; ++kb) tma_store_3d_hint(&p.tm_z, zbuf + kb * kUnitBytes, kb * 64, t0, l * p.B + zq, z_policy);
         bulk_commit_group();
         bulk_wait_group_read0();
         mbar_arrive(zfree);
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         bulk_wait_group0();                               // the stores are complete (visible to the loads below)
         ok = mbar_wait(lfin, 0, wd, 109);                 // no MMA reads the y / z areas any more
         uint32_t ai = 0;
-        for (int l = 0; l < p.nl && ok; ++l)
+        for (int l = p.nl - 1; l >= 0 && ok; --l)           // most recent layers first: their z is still in L2
           for (int kb = 0; kb < 4 && ok; ++kb, ++ai) {
             const uint32_t s = ai % AS;
             ok = mbar_wait(&aempty[s], ((ai / AS) & 1) ^ 1, wd, 110);
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         for (int kb = 0; kb < 4 && ok; ++kb)
           for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, 0, kb, pl));
       }
-      for (int l = 0; l < p.nl && ok; ++l)                          // skip GEMM
+      for (int l = p.nl - 1; l >= 0 && ok; --l)                      // skip GEMM (same order as its A tiles)
         for (int kb = 0; kb < 4 && ok; ++kb)
           for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, 1, kb, pl));
     } else if (warp == 1 && lane == 0 && prank == 0) {
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       // ---- deferred skip GEMM -> F1 (free since chunk 1's epilogue of the last layer) ----
       if (ok) umma_commit<G>(lfin, pair_mask);
       uint32_t ai = 0, accs = 0;
-      for (int l = 0; l < p.nl && ok; ++l)
+      for (int l = p.nl - 1; l >= 0 && ok; --l)
         for (int kb = 0; kb < 4 && ok; ++kb, ++ai) {
           const uint32_t s = ai % AS;
           ok = mbar_wait(&afull[s], (ai / AS) & 1, wd, 209);
@@ -484,23 +490,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         uint4* const ll_out = p.ll + ((static_cast<size_t>(tile_valid ? tile : 0) * 2 + ((l + 1) & 1)) * 2 + (r < 8 ? 0 : 1)) * 512 +
                               (r & 7) * 64 + half * 32;
         const unsigned int seq_next = p.seq_base + static_cast<unsigned int>(l + 1);
+        uint32_t o[2][16];                          // accumulator pieces of 16 columns, the next one in flight
+        tmem_ld_32x16(tmem_base + tlane + half * 128, o[0]);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          uint32_t o[32];
-          tmem_ld_32x32(tmem_base + tlane + half * 128 + jj * 32, o);
+        for (int pc = 0; pc < 8; ++pc) {
+          const int jj = pc >> 1;
           tmem_ld_wait();
+          if (pc + 1 < 8) tmem_ld_32x16(tmem_base + tlane + half * 128 + (pc + 1) * 16, o[(pc + 1) & 1]);
           uint8_t* yrow = yslots + (half * 2 + (jj >> 1)) * Cfg::YSLOT + (8 + r) * 128;
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const int c8 = (pc & 1) * 2 + c2;         // 16-byte chunk (8 channels) within the 32-column group jj
             uint32_t hy[4];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int i = c8 * 8 + e * 4, col = jj * 32 + i;
+              const int i = c2 * 8 + e * 4, col = pc * 16 + i;
               const float4 bias = bt[col >> 2], dn = dt[col >> 2];
-              const float x0 = (x[col] + (__uint_as_float(o[i]) + bias.x)) * 0.70710678118654752440f;
-              const float x1 = (x[col + 1] + (__uint_as_float(o[i + 1]) + bias.y)) * 0.70710678118654752440f;
-              const float x2 = (x[col + 2] + (__uint_as_float(o[i + 2]) + bias.z)) * 0.70710678118654752440f;
-              const float x3 = (x[col + 3] + (__uint_as_float(o[i + 3]) + bias.w)) * 0.70710678118654752440f;
+              const float x0 = (x[col] + (__uint_as_float(o[pc & 1][i]) + bias.x)) * 0.70710678118654752440f;
+              const float x1 = (x[col + 1] + (__uint_as_float(o[pc & 1][i + 1]) + bias.y)) * 0.70710678118654752440f;
+              const float x2 = (x[col + 2] + (__uint_as_float(o[pc & 1][i + 2]) + bias.z)) * 0.70710678118654752440f;
+              const float x3 = (x[col + 3] + (__uint_as_float(o[pc & 1][i + 3]) + bias.w)) * 0.70710678118654752440f;
               x[col] = x0; x[col + 1] = x1; x[col + 2] = x2; x[col + 3] = x3;
               hy[2 * e] = row_valid ? h2_bits(__floats2half2_rn(x0 + dn.x, x1 + dn.y)) : 0u;
               hy[2 * e + 1] = row_valid ? h2_bits(__floats2half2_rn(x2 + dn.z, x3 + dn.w)) : 0u;
@@ -563,36 +572,57 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       }
     }
 
-    // ---- exit: skip sum (deferred GEMM over all layers, in F1) -> SKIP (fp32) and the fp16 hi / lo operand of the head
-    //      GEMM; residual stream back to X (debug tap) ----
+    // ---- exit: skip sum (deferred GEMM over all layers, in F1) -> fp16 hi / lo operand of the head GEMM, written as
+    //      swizzled tiles into the (now idle) z / y areas and stored to S16 by TMA; debug taps (dsx_diffnet_forward only):
+    //      fp32 skip sum -> SKIP, residual stream -> X ----
+    if (tracer) DSX_STRACE(2, 248);
     if (ok) ok = wait_acc(&tfull[1], static_cast<uint32_t>(p.nl & 1), 304);
+    if (tracer) DSX_STRACE(2, 249);
     if (ok) {
       const float* bs = p.bskip + static_cast<size_t>(p.nl - 1) * kC + half * 128;
-#pragma unroll 1
-      for (int jj = 0; jj < 4; ++jj) {
-        uint32_t o[32];
-        tmem_ld_32x32(tmem_base + tlane + 256 + half * 128 + jj * 32, o);
-        tmem_ld_wait();
-        if (row_valid) {
+      uint32_t o[2][16];
+      tmem_ld_32x16(tmem_base + tlane + 256 + half * 128, o[0]);
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bs + jj * 32) + c4);
+      for (int pc = 0; pc < 8; ++pc) {
+        tmem_ld_wait();
+        if (pc + 1 < 8) tmem_ld_32x16(tmem_base + tlane + 256 + half * 128 + (pc + 1) * 16, o[(pc + 1) & 1]);
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = c2 * 8 + e * 4, col = pc * 16 + i;
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bs + col));
             float4 v;
-            v.x = __uint_as_float(o[c4 * 4]) + bb.x;
-            v.y = __uint_as_float(o[c4 * 4 + 1]) + bb.y;
-            v.z = __uint_as_float(o[c4 * 4 + 2]) + bb.z;
-            v.w = __uint_as_float(o[c4 * 4 + 3]) + bb.w;
-            if (p.taps) *reinterpret_cast<float4*>(p.SKIP + grow + jj * 32 + c4 * 4) = v;
-            if (p.nl == p.L) {
-              const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l, sc = v.z * p.inv_sqrt_l, sd = v.w * p.inv_sqrt_l;
-              const __half2 h0 = __floats2half2_rn(sa, sb), h1 = __floats2half2_rn(sc, sd);
-              const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-              __half* sp = p.s16 + grow + jj * 32 + c4 * 4;
-              *reinterpret_cast<uint2*>(sp) = make_uint2(h2_bits(h0), h2_bits(h1));
-              *reinterpret_cast<uint2*>(sp + p.plane_elems) =
-                  make_uint2(h2_bits(__floats2half2_rn(sa - f0.x, sb - f0.y)), h2_bits(__floats2half2_rn(sc - f1.x, sd - f1.y)));
-            }
+            v.x = __uint_as_float(o[pc & 1][i]) + bb.x;
+            v.y = __uint_as_float(o[pc & 1][i + 1]) + bb.y;
+            v.z = __uint_as_float(o[pc & 1][i + 2]) + bb.z;
+            v.w = __uint_as_float(o[pc & 1][i + 3]) + bb.w;
+            if (p.taps && row_valid) *reinterpret_cast<float4*>(p.SKIP + grow + col) = v;
+            const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l, sc = v.z * p.inv_sqrt_l, sd = v.w * p.inv_sqrt_l;
+            const __half2 h0 = __floats2half2_rn(sa, sb), h1 = __floats2half2_rn(sc, sd);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            hi[2 * e] = h2_bits(h0);
+            hi[2 * e + 1] = h2_bits(h1);
+            lo[2 * e] = h2_bits(__floats2half2_rn(sa - f0.x, sb - f0.y));
+            lo[2 * e + 1] = h2_bits(__floats2half2_rn(sc - f1.x, sd - f1.y));
           }
+          // channel half * 128 + pc * 16 + c2 * 8 .. + 8 of row r: k-block (channel >> 6), 16-byte chunk ((channel & 63) >> 3)
+          const int ch = half * 128 + pc * 16 + c2 * 8;
+          const int off = r * 128 + ((((ch & 63) >> 3) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(aslot(ch >> 6) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(aslot(4 + (ch >> 6)) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdone);
+      if (p.nl == p.L && warp == 4 && lane == 0) {      // one thread stores the 2 x 4 tiles (rows beyond T are clipped)
+        if (mbar_wait(sdone, 0, wd, 306)) {
+          for (int pl = 0; pl < 2; ++pl)
+            for (int kb = 0; kb < 4; ++kb) tma_store_3d(&p.tm_s16[pl], aslot(pl * 4 + kb), kb * 64, t0, bq);
+          bulk_commit_group();
+          bulk_wait_group0();
         }
       }
       if (row_valid && p.taps) {
@@ -743,6 +773,8 @@ int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_
   prm.tm_w = sr ? h->tm_wsr : h->tm_w;
   prm.tm_y0 = h->tm_yh[0];
   prm.tm_z = h->tm_z;
+  prm.tm_s16[0] = h->tm_s16[0];
+  prm.tm_s16[1] = h->tm_s16[1];
   prm.taps = h->want_taps;
   prm.X = h->ws.X;
   prm.SKIP = h->ws.SKIP;

@@ -204,12 +204,12 @@ def trace():
     t = torch.full((B,), 57, dtype=torch.long, device=DEV)
     out = {}
     for prec in ("fp16s", "fp16x2"):
-        s = make(1, prec, 1)
-        s.diffnet_forward(x, t, cond)
+        s = make(1, prec, 1, O.make_schedule(O.linear_beta_schedule(100, 0.06)))
+        xs = torch.randn(B, 1, 80, T, generator=gen).to(DEV)
+        s.sample_ddpm(xs, cond, 100, 2, seed=1)          # the loop entry point: no debug taps, as in production
         buf = (ctypes.c_int64 * (6 * 256))()
         _capi.check(_capi.lib.dsx_debug_trace(s._h, 1, None), "trace on")
-        s.diffnet_forward(x, t, cond)
-        s.diffnet_forward(x, t, cond)
+        s.sample_ddpm(xs, cond, 100, 2, seed=1)
         _capi.check(_capi.lib.dsx_debug_trace(s._h, 1, ctypes.cast(buf, ctypes.c_void_p)), "trace read")
         a = np.array(buf[:], dtype=np.int64).reshape(2, 3, 256)
         out[prec] = a.tolist()
@@ -223,7 +223,8 @@ def trace():
         print("producer 0: per layer [g1done seen, flags seen, halo issued, z stored]")
         for l in range(1, 6):
             print(l, [int(a[0, 0, l * 4 + k] - base) for k in range(4)])
-        print("end of skip GEMM issue (MMA thread)", int(a[0, 1, 250] - base), "epilogue exit", int(a[0, 2, 250] - base))
+        print("end of skip GEMM issue (MMA thread)", int(a[0, 1, 250] - base), "| exit epilogue: enter", int(a[0, 2, 248] - base),
+              "skip sum ready", int(a[0, 2, 249] - base), "done", int(a[0, 2, 250] - base), "| layer 19 G2 issued", int(a[0, 1, 19 * 8 + 6] - base))
         per_layer = (a[0, 1, 19 * 8] - a[0, 1, 1 * 8]) / 18.0
         print(f"{prec}: cycles per layer (MMA thread, layers 1..19): {per_layer:.0f}")
         s.close()
