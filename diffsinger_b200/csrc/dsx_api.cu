@@ -626,6 +626,7 @@ int dsx_get_info(dsx_handle* h, int what, int64_t* out) {
     case DSX_INFO_STACK_MODE: *out = h->stack_mode; break;
     case DSX_INFO_CLUSTER_OCCUPANCY: *out = h->cluster_occ; break;
     case DSX_INFO_STACK_KERNEL_LAUNCHES: *out = h->stack_launches; break;
+    case DSX_INFO_STACK_ROWS: *out = h->stack_rows_used; break;
     case DSX_INFO_LAYER_KERNEL_NS: {
       double total_ms = 0;
       for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
@@ -654,6 +655,10 @@ int dsx_set_option(dsx_handle* h, int what, int64_t value) {
     case DSX_OPT_STACK_MODE: h->stack_mode = static_cast<int>(value); break;
     case DSX_OPT_STACK_KERNEL: h->stack_kernel = static_cast<int>(value); break;
     case DSX_OPT_GATE_APPROX: h->gate_approx = static_cast<int>(value); break;
+    case DSX_OPT_STACK_ROWS:
+      DSX_CHECK(value == 0 || value == 64 || value == 128, DSX_E_INVALID, "DSX_OPT_STACK_ROWS must be 0 (automatic), 64 or 128");
+      h->stack_rows = static_cast<int>(value);
+      break;
     case DSX_OPT_BATCH_OFFSET:
       DSX_CHECK(value >= 0 && value < (1ll << 30), DSX_E_INVALID, "DSX_OPT_BATCH_OFFSET out of range");
       h->batch_offset = static_cast<int>(value);

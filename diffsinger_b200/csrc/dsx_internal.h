@@ -35,6 +35,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 constexpr int kTile = 128;  // frames per tile (= UMMA M per CTA)
+constexpr int kStackRowsPerLayer = 64 * 256;      // rows per layer of the stack kernel's hi / lo weight pack (fp16 / fp16x2)
 constexpr int kStackSetRowsPerLayer = 32 * 256;   // rows (of 64 fp16) per layer of one stochastically rounded weight set
 
 // Geometry of one call: B utterances of T frames, stored frames-major with the frame axis
@@ -76,6 +77,7 @@ struct ModelDev {
   const float* b1p;    // [L][2 chunks][256]  gate(128) | filter(128) per chunk
   const __half* whead; // [32 tiles][128 rows][64]: skip_projection, output_projection, input_projection packs
   const float* bskip;  // [L][256] prefix sums over layers of the skip-half biases of output_projection (stack kernel)
+  const __half* wstk;  // [L][16384 rows][64] hi / lo planes in the stack kernel's row order (DSX_PREC_FP16 / FP16X2), or nullptr
   const __half* wsr;   // [R][L][8192 rows][64] stochastically rounded weight sets (DSX_PREC_FP16S), or nullptr
   int wsr_sets;        // R
 };
@@ -124,7 +126,8 @@ struct dsx_handle {
   dsx::Workspace ws;
   int* status_dev = nullptr;   // kernel watchdog / self-check word
   int* status_host = nullptr;  // pinned mirror
-  CUtensorMap tm_w{}, tm_y[2][2]{}, tm_yh[2]{}, tm_ye[2]{}, tm_cond[2]{}, tm_s16[2]{}, tm_whead{}, tm_wsr{}, tm_z{};
+  CUtensorMap tm_w{}, tm_y[2][2]{}, tm_yh[2]{}, tm_ye[2]{}, tm_cond[2]{}, tm_s16[2]{}, tm_whead{}, tm_wsr{}, tm_wstk{}, tm_z{};
+  CUtensorMap tm_y0s[2]{}, tm_zs[2]{}, tm_s16s[2][2]{};   // stack kernel, [0]: 128 rows per CTA, [1]: 64 rows per CTA
   dsx::Geom tm_geom;           // geometry the activation maps were built for
   int tm_group = 0;
   int profile = 0;
@@ -139,8 +142,10 @@ struct dsx_handle {
   unsigned int ll_seq = 1;             // next sequence number (monotonic, never 0)
   int flags_kind = 0;                  // which kernel's counting convention the counters follow (1: k_tc_layer, 2: k_tc_stack)
   int stack_kernel = 1;                // DSX_OPT_STACK_KERNEL: 1 = register-resident stack kernel (dsx_stack.cu) where it applies
-  int stack_occ[2] = {0, 0};           // co-resident CTA pairs of k_tc_stack<1>, <2> (0 unknown, -1 none)
-  bool attr_stack[2] = {false, false};
+  int stack_occ[2][2] = {};            // co-resident CTA pairs of k_tc_stack<WP, R> [WP - 1][R == 64] (0 unknown, -1 none)
+  bool attr_stack[2][2] = {};
+  int stack_rows = 0;                  // DSX_OPT_STACK_ROWS: 0 = automatic, 64 / 128 forced
+  int stack_rows_used = 0;             // rows per CTA of the last stack launch
   int sr_sets = 64;                    // DSX_OPT_SR_SETS: weight sets of DSX_PREC_FP16S (takes effect at the next dsx_load_diffnet)
   unsigned long long sr_seed = 0x5DEECE66Dull;
   unsigned long long ws_epoch = 0;     // bumped whenever a workspace buffer moves (tensor maps are rebuilt)

@@ -29,6 +29,8 @@
 //                 per-layer bias / FiLM vectors (1 KB per epilogue warp) | barriers]; the deferred skip GEMM streams its A
 // tiles (z of every layer) through the z and y areas.
 // TMEM: F0, F1 (256 columns each).
+// Small batches run the same kernel with 64 rows per CTA (UMMA M = 128: twice the CTAs, about half the time per layer), see
+// StackCfg.
 // Roles (384 threads): warp 0 lane 0 = activation producer (layer-0 slots, z stores, CP prefetch, A tiles of the skip GEMM),
 // warps 2, 3 lane 0 = weight producers, warp 1 lane 0 of the pair leader = MMA issuer, warps 4-11 = epilogue (thread = frame
 // row = TMEM lane, two warps per lane quadrant split the 256 columns).  setmaxnreg moves registers from warps 0-3 to the
@@ -49,49 +51,59 @@
 
 namespace dsx {
 
+// Rows per CTA.  R = 128: UMMA M = 256, accumulator lane = frame row, column = N index.  R = 64 (small batches: twice the CTAs,
+// half the MMA and epilogue time per layer): UMMA M = 128, whose cta_group::2 accumulator holds the FIRST half of N in lanes
+// 0-63 and the SECOND half in lanes 64-127 (columns 0 .. N/2-1).  The weight rows of GEMM1 are ordered so that a channel's
+// gate and filter land in the same lane either way: N index = g * 128 + j with j < 64 -> gate of chunk-channel g * 64 + j,
+// j >= 64 -> filter of chunk-channel g * 64 + j - 64 (k_pack_wstk / k_pack_wsr).
+template <int R>
 struct StackCfg {
-  static constexpr int WSLOTS = 5;
-  static constexpr int YSLOT = (kTile + 16) * 128;         // [8 halo | 128 centre | 8 halo] rows of 64 channels
-  static constexpr int W_BYTES = WSLOTS * kUnitBytes;
+  static constexpr int UNIT = R * 128;                      // one A k-block tile of this CTA: R rows x 64 fp16
+  static constexpr int YSLOT = (R + 16) * 128;              // [8 halo | R centre | 8 halo] rows of 64 channels
+  static constexpr int WSLOTS = (R == 128) ? 5 : 8;
+  static constexpr int W_BYTES = WSLOTS * kUnitBytes;       // weight tiles are 128 rows x 64 per CTA in both modes
   static constexpr int Y_BYTES = 4 * YSLOT;
-  static constexpr int Z_BYTES = 4 * kUnitBytes;
+  static constexpr int Z_BYTES = 4 * UNIT;
   static constexpr int ASLOTS = 8;                          // A ring of the skip GEMM: 4 units in the z area + 4 in the y area
-  static constexpr int TAB_BYTES = kEpiWarps * 1024;       // per epilogue warp: [bias(128) | d_next(128)] fp32 of its column half
+  static constexpr int TAB_BYTES = kEpiWarps * 1024;       // per epilogue warp: [bias | d_next] fp32 of its channels
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = 1024 + W_BYTES + Y_BYTES + Z_BYTES + TAB_BYTES + BAR_BYTES;
   static constexpr int REGS_LOW = 56, REGS_HIGH = 224;     // setmaxnreg targets: 128 * 56 + 256 * 224 = 64512 = 384 * 168 (the
                                                             // CTA's register pool is its launch allocation)
+  static constexpr int F1_COL = (R == 128) ? 256 : 128;     // TMEM column of the second accumulator
+  static constexpr int NCH = R;                             // channels (N indices) per epilogue thread in epi2 / exit
+  static constexpr int NSP = R / 16;                        // gate sub-passes (8 channels each) per chunk and thread
+  static_assert(R == 128 || R == 64, "rows per CTA");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  static_assert(YSLOT % 1024 == 0, "y slots must keep the 1024-byte swizzle atoms aligned");
-  static_assert(Y_BYTES >= 4 * kUnitBytes, "A ring units in the y area");
+  static_assert(YSLOT % 1024 == 0 && UNIT % 1024 == 0, "tiles must keep the 1024-byte swizzle atoms aligned");
+  static_assert(Y_BYTES >= 4 * UNIT, "A ring units in the y area");
 };
 
 struct TcStackParams {
   CUtensorMap tm_w;        // weight tiles, 2D [rows][64], box 64 x 128 rows
-  CUtensorMap tm_y0;       // Y buffer 0 (written by the input projection), box 64 ch x 144 frames: layer 0 incl. halos
-  CUtensorMap tm_z;        // Z [L * B][T][256] fp16, box 64 ch x 128 frames: z of every layer (store per layer, load for the skip GEMM)
-  CUtensorMap tm_s16[2];   // S16 hi / lo planes [B][T][256], box 64 ch x 128 frames (TMA store at exit)
-  float* X;                // [B][Tp][256] residual stream: read at entry, written back at exit
-  float* SKIP;             // [B][Tp][256] skip sum (debug tap / fp32 copy), written at exit
-  size_t plane_elems;
+  CUtensorMap tm_y0;       // Y buffer 0 (written by the input projection), box 64 ch x (R + 16) frames: layer 0 incl. halos
+  CUtensorMap tm_z;        // Z [L * B][T][256] fp16, box 64 ch x R frames: z of every layer (store per layer, load for the skip GEMM)
+  CUtensorMap tm_s16[2];   // S16 hi / lo planes [B][T][256], box 64 ch x R frames (TMA store at exit)
+  float* X;                // [B][Tp][256] residual stream: read at entry, written back at exit (taps)
+  float* SKIP;             // [B][Tp][256] skip sum (debug tap / fp32 copy), written at exit (taps)
   uint4* ll;               // halo packets [tiles][2 layer parities][2 sides: first / last 8 rows][512] x 16 B:
                            // {fp16 x2, seq, fp16 x2, seq}, packet = 4 channels of one row (row * 64 + channel / 4)
   unsigned int seq_base;   // sequence number of layer l's y: seq_base + l (monotonic over the handle's lifetime, never 0)
-  const float* CP;         // [L][tiles][2 chunks][64 column groups][128 rows][4] conditioner projection + biases
+  const float* CP;         // [L][128-frame tiles][2 chunks][64 column groups][128 rows][4] conditioner projection + biases
+  int cp_tiles;            // 128-frame tiles of the call (CP stride)
   int cp_prefetch;
   const float* b2;         // [L][512] output_projection bias (residual half | skip half)
   const float* bskip;      // [L][256] prefix sums over layers of the skip-half biases
   const float* dtab;       // FiLM rows of this evaluation: [L][256], utterance b at + b * d_row_stride
   int d_row_stride;
-  int T, Tp, tiles_per_utt, tiles, B;
+  int T, Tp, tiles_per_utt, B;   // tiles_per_utt: R-frame tiles per utterance (Tp / R)
   int tile0, tile_end;     // this launch covers tiles [tile0, tile_end) (whole utterances); CTA i -> tile tile0 + i
   int nl, L, cycle;        // layers [0, nl); dilation of layer l = 1 << (l % cycle)
   int w_row0;              // first row of this evaluation's weight set in tm_w
   int w_layer_rows;        // rows per layer
-  int w_sr;                // 0: round-1 pack (80 tiles per layer, hi / lo planes); 1: single-plane set (32 tiles per layer)
-  __half* s16;             // fp16 split of skip_total / sqrt(L): plane 0 hi, plane 1 (at + plane_elems) lo
+  int w_sr;                // 0: hi / lo planes (64 tiles per layer); 1: single-plane stochastically rounded set (32 tiles per layer)
   float inv_sqrt_l;
-  int fast_act;            // 1: tanh.approx gate (fp16 fast mode)
+  int fast_act;            // 1: tanh.approx gate
   int taps;                // 1: write the residual stream and the fp32 skip sum back to X / SKIP at exit (debug taps of
                            // dsx_diffnet_forward); the sampling loops do not need them
   int* status;
@@ -99,19 +111,19 @@ struct TcStackParams {
   long long* trace;        // debug: [2 CTAs][3 roles][256] clock64 stamps, or nullptr
 };
 
-
 #define DSX_STRACE(role, slot)                                                         \
   do {                                                                                 \
     if (p.trace && blockIdx.x < 2 && (slot) < 256)                                      \
       p.trace[(blockIdx.x * 3 + (role)) * 256 + (slot)] = clock64();                   \
   } while (0)
 
-template <int WP>
+template <int WP, int R>
 __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant__ TcStackParams p) {
-  using Cfg = StackCfg;
+  using Cfg = StackCfg<R>;
   constexpr int G = kG;
   constexpr int WS = Cfg::WSLOTS;
   constexpr int AS = Cfg::ASLOTS;
+  constexpr int UNIT = Cfg::UNIT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* wring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* yslots = wring + Cfg::W_BYTES;
@@ -132,19 +144,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
   uint64_t* sdone = aempty + AS;    // exit: this CTA's 8 epilogue warps have written the S16 tiles (local)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdone + 1);
   static_assert((2 * Cfg::WSLOTS + 10 + 2 * Cfg::ASLOTS) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
-  auto aslot = [&](int s) -> uint8_t* { return s < 4 ? zbuf + s * kUnitBytes : yslots + (s - 4) * kUnitBytes; };
+  auto aslot = [&](int s) -> uint8_t* { return s < 4 ? zbuf + s * UNIT : yslots + (s - 4) * UNIT; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const uint32_t prank = crank & 1;
   const uint32_t lead = crank & ~1u;
   const uint16_t pair_mask = static_cast<uint16_t>(3u << lead);
-  const int tile = p.tile0 + blockIdx.x;
+  const int tile = p.tile0 + blockIdx.x;                     // R-frame tile
   const bool tile_valid = tile < p.tile_end;
   const int b = tile / p.tiles_per_utt, tr = tile % p.tiles_per_utt;
   const int bq = tile_valid ? b : p.B;            // b == B: every TMA row out of bounds (zeros)
-  const int cp_tile = tile_valid ? tile : 0;      // padding CTAs read (and discard) tile 0's slice of CP
-  const int t0 = tile_valid ? tr * kTile : 0;
+  const int t0 = tile_valid ? tr * R : 0;
+  // CP is laid out by 128-frame tiles: this CTA's rows start at cp_row0 of tile cp_tile (padding CTAs read tile 0)
+  const int cp_tile = tile_valid ? (b * (p.Tp / 128) + t0 / 128) : 0;
+  const int cp_row0 = t0 % 128;
   const bool nb_lo = tile_valid && tr > 0, nb_hi = tile_valid && tr + 1 < p.tiles_per_utt;
   const int zq = tile_valid ? b : p.L * p.B;      // Z coordinate base: (l * B + b); out of bounds for padding CTAs
 
@@ -187,11 +201,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
 
   // weight tile row in tm_w: GEMM1 (chunk h, tap, channel block cb, plane) / GEMM2 (half q, k-block kb, plane)
   auto w1_row = [&](int l, int h, int tap, int cb, int plane) -> int {
-    const int idx = p.w_sr ? (h * 12 + tap * 4 + cb) : ((plane * 2 + h) * 16 + tap * 4 + cb);
+    const int idx = p.w_sr ? (h * 12 + tap * 4 + cb) : ((plane * 2 + h) * 12 + tap * 4 + cb);
     return p.w_row0 + l * p.w_layer_rows + idx * 256 + static_cast<int>(prank) * 128;
   };
   auto w2_row = [&](int l, int q, int kb, int plane) -> int {
-    const int idx = p.w_sr ? (24 + q * 4 + kb) : (64 + (plane * 2 + q) * 4 + kb);
+    const int idx = p.w_sr ? (24 + q * 4 + kb) : (48 + (plane * 2 + q) * 4 + kb);
     return p.w_row0 + l * p.w_layer_rows + idx * 256 + static_cast<int>(prank) * 128;
   };
 
@@ -201,12 +215,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       // ================================ activation producer ================================
       bool ok = true;
       const uint64_t z_policy = l2_policy_evict_last();   // z comes back for the skip GEMM: keep it in L2 ahead of the CP stream
-      auto cp_prefetch = [&](int l, int h) {
+      auto cp_prefetch = [&](int l, int h) {             // HBM -> L2; the two CTAs of a pair share a 128-frame tile when R = 64
         if (!p.cp_prefetch || l >= p.nl) return;
-        const char* src = reinterpret_cast<const char*>(p.CP + ((static_cast<size_t>(l) * p.tiles + cp_tile) * 2 + h) * kCpChunk);
-        for (int i = 0; i < 8; ++i) prefetch_l2_bulk(src + i * 16384, 16384);
+        const char* src = reinterpret_cast<const char*>(p.CP + ((static_cast<size_t>(l) * p.cp_tiles + cp_tile) * 2 + h) * kCpChunk);
+        if (R == 128) {
+          for (int i = 0; i < 8; ++i) prefetch_l2_bulk(src + i * 16384, 16384);
+        } else {
+          for (int i = 0; i < 4; ++i) prefetch_l2_bulk(src + (cp_row0 ? 65536 : 0) + i * 16384, 16384);
+        }
       };
-      // layer 0: the whole [8 | 128 | 8]-row slots come from Y buffer 0 (written by the input projection kernel)
+      // layer 0: the whole [8 | R | 8]-row slots come from Y buffer 0 (written by the input projection kernel)
       if (prank == 0) mbar_arrive_expect_tx(y0full, G * Cfg::Y_BYTES);
       for (int cb = 0; cb < 4; ++cb) tma_load_3d<G>(&p.tm_y0, y0full, yslots + cb * Cfg::YSLOT, cb * 64, t0 - 8, bq, lead);
       cp_prefetch(0, 0);
@@ -216,15 +234,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         // the z area may be overwritten (next layer's chunk 0) once the store has read it
         ok = mbar_wait(zdone, l & 1, wd, 108);
         if (!ok) break;
-        for (int kb = 0; kb < 4; ++kb) tma_store_3d_hint(&p.tm_z, zbuf + kb * kUnitBytes, kb * 64, t0, l * p.B + zq, z_policy);
+        for (int kb = 0; kb < 4; ++kb) tma_store_3d_hint(&p.tm_z, zbuf + kb * UNIT, kb * 64, t0, l * p.B + zq, z_policy);
         bulk_commit_group();
         bulk_wait_group_read0();
         mbar_arrive(zfree);
         DSX_STRACE(0, l * 4 + 3);
-        cp_prefetch(l + 1, 0);                            // HBM -> L2, most of a layer ahead of the gate epilogue that reads it
+        cp_prefetch(l + 1, 0);                            // most of a layer ahead of the gate epilogue that reads it
         cp_prefetch(l + 1, 1);
       }
-      // ---- deferred skip GEMM: A tiles = z of every layer, back from HBM (this tile's own stores) ----
+      // ---- deferred skip GEMM: A tiles = z of every layer, back from L2 / HBM (this tile's own stores) ----
       if (ok) {
         bulk_wait_group0();                               // the stores are complete (visible to the loads below)
         ok = mbar_wait(lfin, 0, wd, 109);                 // no MMA reads the y / z areas any more
@@ -234,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
             const uint32_t s = ai % AS;
             ok = mbar_wait(&aempty[s], ((ai / AS) & 1) ^ 1, wd, 110);
             if (!ok) break;
-            if (prank == 0) mbar_arrive_expect_tx(&afull[s], G * kUnitBytes);
+            if (prank == 0) mbar_arrive_expect_tx(&afull[s], G * UNIT);
             tma_load_3d<G>(&p.tm_z, &afull[s], aslot(s), kb * 64, t0, l * p.B + zq, lead);
           }
       }
@@ -270,7 +288,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
           for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, 1, kb, pl));
     } else if (warp == 1 && lane == 0 && prank == 0) {
       // ================================ MMA issuer (pair leader) ================================
-      constexpr uint32_t idesc = umma_idesc_f16(128 * G, 256);
+      constexpr uint32_t idesc = umma_idesc_f16(R * G, 256);
+      const uint32_t dF1 = tmem_base + Cfg::F1_COL;
       uint32_t wi = 0;
       bool ok = true;
       auto mma_tile = [&](uint32_t d, uint64_t a, uint32_t& acc, int code) {   // one weight tile of the global order
@@ -307,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         for (int h = 0; h < 2; ++h)                     // centre taps (F1 has been free since chunk 1's epilogue of layer l-1)
           for (int cb = 0; cb < 4 && ok; ++cb) {
             const uint64_t a = umma_desc_sw128(smem_u32(yslots + cb * Cfg::YSLOT)) + static_cast<uint64_t>((8 * 128) >> 4);
-            for (int pl = 0; pl < WP && ok; ++pl) mma_tile(tmem_base + h * 256, a, h == 0 ? acc0 : acc1, 207);
+            for (int pl = 0; pl < WP && ok; ++pl) mma_tile(h == 0 ? tmem_base : dF1, a, h == 0 ? acc0 : acc1, 207);
           }
         DSX_STRACE(1, l * 8 + 1);
         if (l > 0 && ok) {                              // halo rows of this layer (from the neighbour tiles) are in the slots
@@ -321,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
             const uint64_t y = umma_desc_sw128(smem_u32(yslots + cb * Cfg::YSLOT));
             for (int tap = 0; tap < 3 && ok; tap += 2) {
               const uint64_t a = y + static_cast<uint64_t>(((8 + (tap - 1) * dil) * 128) >> 4);   // row-shifted start
-              for (int pl = 0; pl < WP && ok; ++pl) mma_tile(tmem_base + h * 256, a, h == 0 ? acc0 : acc1, 207);
+              for (int pl = 0; pl < WP && ok; ++pl) mma_tile(h == 0 ? tmem_base : dF1, a, h == 0 ? acc0 : acc1, 207);
             }
           }
           if (ok) umma_commit<G>(&tfull[h], pair_mask);
@@ -336,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
           if (!ok) break;
           if (kb == 0) DSX_STRACE(1, l * 8 + 4);
           if (kb == 2) DSX_STRACE(1, l * 8 + 5);
-          const uint64_t z = umma_desc_sw128(smem_u32(zbuf + kb * kUnitBytes));
+          const uint64_t z = umma_desc_sw128(smem_u32(zbuf + kb * UNIT));
           for (int pl = 0; pl < WP && ok; ++pl) mma_tile(tmem_base, z, acc2, 205);
         }
         if (ok) umma_commit<G>(&tfull[0], pair_mask);
@@ -352,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
           if (!ok) break;
           tc_fence_after();
           const uint64_t a = umma_desc_sw128(smem_u32(aslot(s)));
-          for (int pl = 0; pl < WP && ok; ++pl) mma_tile(tmem_base + 256, a, accs, 210);
+          for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dF1, a, accs, 210);
           if (ok) umma_commit<G>(&aempty[s], pair_mask);
         }
       if (ok) umma_commit<G>(&tfull[1], pair_mask);
@@ -361,15 +380,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_HIGH));
     // ================================ epilogue (8 warps) ================================
-    const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
-    const int half = (warp - 4) >> 2;               // which half of the 256 columns
-    const int r = quad * 32 + lane;                 // frame row in the tile == TMEM lane
+    // thread <-> accumulator: TMEM lane quadrant `quad` (32 lanes) is fixed by the warp index; the two warps of a quadrant
+    // (wh = 0, 1) split the columns.  R = 128: row = lane index, N indices [wh * 128, +128).  R = 64: rows (quad & 1) * 32 + lane,
+    // N half quad >> 1, of which this warp has columns [wh * 64, +64).
+    const int quad = warp & 3;
+    const int wh = (warp - 4) >> 2;
+    const int r = (R == 128 ? quad : (quad & 1)) * 32 + lane;             // frame row in the tile
+    const int ng = (R == 128) ? wh : (quad >> 1);                          // 128-wide N group of this thread
     const uint32_t tlane = static_cast<uint32_t>(quad * 32) << 16;
+    const int nbase = (R == 128) ? wh * 128 : (quad >> 1) * 128 + wh * 64;  // first N index (= channel in epi2 / exit)
+    const int cbase = (R == 128) ? nbase : wh * 64;                        // its TMEM column
+    constexpr int NCH = Cfg::NCH, NSP = Cfg::NSP, NQ = 2 * NSP;
     const bool tracer = (warp == 4 && lane == 0);
     const bool row_valid = tile_valid && (t0 + r < p.T);
-    const bool edge = (r < 8 || r >= kTile - 8) && tile_valid;       // rows the neighbour tiles need as halo rows
+    const bool edge = (r < 8 || r >= R - 8) && tile_valid;               // rows the neighbour tiles need as halo rows
     const int et = threadIdx.x - 128;               // 0..255: halo reception (side, row, 16-channel group)
-    const size_t grow = (static_cast<size_t>(tile_valid ? b : 0) * p.Tp + t0 + r) * kC + half * 128;   // this thread's row
+    const size_t grow = (static_cast<size_t>(tile_valid ? b : 0) * p.Tp + t0 + r) * kC + nbase;   // this thread's row / channels
     bool ok = true;
     auto release = [&](uint64_t* bar) {             // this warp's part of the phase on F0 / F1 is done
       tc_fence_before();
@@ -388,38 +414,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
     };
     const uint64_t cp_policy = l2_policy_evict_first();
 
-    // residual stream of this thread's row: 128 channels, fp32, in registers for the whole stack
-    float x[128];
+    // residual stream of this thread's row: NCH channels, fp32, in registers for the whole stack
+    float x[NCH];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < NCH / 4; ++i) {
       const float4 v = *reinterpret_cast<const float4*>(p.X + grow + i * 4);
       x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
     }
     const float* dbase = p.dtab + static_cast<size_t>(tile_valid ? b : 0) * p.d_row_stride;
+    float* const tb = tab + (warp - 4) * 256;       // this warp's table: [bias(NCH) | d_next(NCH)]
 
     for (int l = 0; l < p.nl && ok; ++l) {
       const bool has_next = (l + 1 < p.nl);
-      // ---- per-layer vectors of this warp's column half -> its own shared-memory table (the gpu-scope fences of the halo
-      //      hand-over invalidate L1, so reading them from global inside the epilogue would cost an L2 round trip each;
-      //      one table per warp: no cross-warp barrier) ----
-      float* tb = tab + (warp - 4) * 256;
+      // ---- per-layer vectors of this warp's channels -> its own shared-memory table (the polling loads of the halo
+      //      exchange and the fences of the hand-over keep L1 cold, so reading them from global inside the epilogue would cost
+      //      an L2 round trip each; one table per warp: no cross-warp barrier) ----
       __syncwarp();
-      *reinterpret_cast<float4*>(tb + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.b2 + static_cast<size_t>(l) * 512 + half * 128) + lane);
-      *reinterpret_cast<float4*>(tb + 128 + lane * 4) =
-          has_next ? __ldg(reinterpret_cast<const float4*>(dbase + static_cast<size_t>(l + 1) * kC + half * 128) + lane)
-                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < NCH / 4) {
+        *reinterpret_cast<float4*>(tb + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.b2 + static_cast<size_t>(l) * 512 + nbase) + lane);
+        *reinterpret_cast<float4*>(tb + NCH + lane * 4) =
+            has_next ? __ldg(reinterpret_cast<const float4*>(dbase + static_cast<size_t>(l + 1) * kC + nbase) + lane)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       __syncwarp();
 
-      // ---- epi1: z = sigmoid(gate) * tanh(filter), gate / filter = accumulator + CP.  16 sub-passes of 8 column pairs (8 per
+      // ---- epi1: z = sigmoid(gate) * tanh(filter), gate / filter = accumulator + CP.  NQ sub-passes of 8 channels (NSP per
       //      chunk); the CP stream is the latency that matters (ncu: long-scoreboard stalls on the accumulator + CP adds), so its
-      //      loads run TWO sub-passes ahead through three register buffers, across the chunk boundary too ----
-      const float* cpl = p.CP + (static_cast<size_t>(l) * p.tiles + cp_tile) * 2 * kCpChunk + r * 4;
+      //      loads run TWO sub-passes ahead through three register buffers, across the chunk boundary too.
+      //      Sub-pass sp of a chunk: chunk-channels c .. c + 8, gate in TMEM column tg, filter in tg + 64 (N order g * 128 + j) ----
+      const float* cpl = p.CP + (static_cast<size_t>(l) * p.cp_tiles + cp_tile) * 2 * kCpChunk + (cp_row0 + r) * 4;
       constexpr int NB = 3;
       float4 cg[NB][2], cf[NB][2];
-      auto gcol = [&](int sp) { return (sp >> 2) * 64 + half * 32 + (sp & 3) * 8; };   // gate column of sub-pass sp of a chunk
-      auto cp_issue = [&](int q, float4* g4, float4* f4) {                               // q = chunk * 8 + sub-pass
-        const float* cph = cpl + (q >> 3) * kCpChunk;
-        const int c = gcol(q & 7);
+      auto chan = [&](int sp) { return (R == 128) ? wh * 64 + sp * 8 : ng * 64 + wh * 32 + sp * 8; };      // chunk-channel
+      auto tcol = [&](int sp) { return (R == 128) ? wh * 128 + sp * 8 : wh * 32 + sp * 8; };               // TMEM column of its gate
+      auto cp_issue = [&](int q, float4* g4, float4* f4) {                               // q = chunk * NSP + sub-pass
+        const float* cph = cpl + (q / NSP) * kCpChunk;
+        const int c = chan(q % NSP);
 #pragma unroll
         for (int v4 = 0; v4 < 2; ++v4) {
           g4[v4] = ld_stream_f4(cph + ((c >> 2) + v4) * (kTile * 4), cp_policy);
@@ -435,19 +465,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         if (!ok) break;
       }
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int h = q >> 3, sp = q & 7;
+      for (int q = 0; q < NQ; ++q) {
+        const int h = q / NSP, sp = q % NSP;
         if (sp == 0) {
           if (tracer) DSX_STRACE(2, l * 12 + h * 3);
           ok = wait_acc(&tfull[h], h == 0 ? 0u : static_cast<uint32_t>(l & 1), 301 + h);
           if (!ok) break;
           if (tracer) DSX_STRACE(2, l * 12 + h * 3 + 1);
         }
-        const uint32_t tF = tmem_base + tlane + h * 256;
+        const uint32_t tF = tmem_base + tlane + h * Cfg::F1_COL + tcol(sp);
         uint32_t g[8], f[8];
-        tmem_ld_32x8(tF + gcol(sp), g);
-        tmem_ld_32x8(tF + 128 + gcol(sp), f);
-        if (q + 2 < 16) cp_issue(q + 2, cg[(q + 2) % NB], cf[(q + 2) % NB]);
+        tmem_ld_32x8(tF, g);
+        tmem_ld_32x8(tF + 64, f);
+        if (q + 2 < NQ) cp_issue(q + 2, cg[(q + 2) % NB], cf[(q + 2) % NB]);
         tmem_ld_wait();
         uint32_t hz[4];
 #pragma unroll
@@ -467,10 +497,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
           }
           hz[e] = h2_bits(__floats2half2_rn(z0, z1));
         }
-        // channel 128 h + c  ->  z k-block 2 h + (sp >> 2), 16-byte chunk half * 4 + (sp & 3) of row r
-        uint8_t* zrow = zbuf + (2 * h + (sp >> 2)) * kUnitBytes + r * 128;
-        *reinterpret_cast<uint4*>(zrow + (((half * 4 + (sp & 3)) ^ (r & 7)) << 4)) = make_uint4(hz[0], hz[1], hz[2], hz[3]);
-        if (sp == 7) {
+        // channel 128 h + c  ->  z k-block 2 h + (c >> 6), 16-byte chunk (c & 63) >> 3 of row r
+        const int c = chan(sp);
+        uint8_t* zrow = zbuf + (2 * h + (c >> 6)) * UNIT + r * 128;
+        *reinterpret_cast<uint4*>(zrow + ((((c & 63) >> 3) ^ (r & 7)) << 4)) = make_uint4(hz[0], hz[1], hz[2], hz[3]);
+        if (sp == NSP - 1) {
           release(&tempty[h]);
           if (h == 1 && lane == 0) mbar_arrive(zdone);    // (after the proxy fence + warp sync of release())
           if (tracer) DSX_STRACE(2, l * 12 + h * 3 + 2);
@@ -485,22 +516,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       if (tracer) DSX_STRACE(2, l * 12 + 7);
       {
         const float4* bt = reinterpret_cast<const float4*>(tb);
-        const float4* dt = reinterpret_cast<const float4*>(tb + 128);
+        const float4* dt = reinterpret_cast<const float4*>(tb + NCH);
         // halo packets of y_{l+1}: side 0 = this tile's first 8 rows, side 1 = its last 8 rows
         uint4* const ll_out = p.ll + ((static_cast<size_t>(tile_valid ? tile : 0) * 2 + ((l + 1) & 1)) * 2 + (r < 8 ? 0 : 1)) * 512 +
-                              (r & 7) * 64 + half * 32;
+                              (r & 7) * 64 + nbase / 4;
         const unsigned int seq_next = p.seq_base + static_cast<unsigned int>(l + 1);
         uint32_t o[2][16];                          // accumulator pieces of 16 columns, the next one in flight
-        tmem_ld_32x16(tmem_base + tlane + half * 128, o[0]);
+        tmem_ld_32x16(tmem_base + tlane + cbase, o[0]);
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc) {
-          const int jj = pc >> 1;
+        for (int pc = 0; pc < NCH / 16; ++pc) {
           tmem_ld_wait();
-          if (pc + 1 < 8) tmem_ld_32x16(tmem_base + tlane + half * 128 + (pc + 1) * 16, o[(pc + 1) & 1]);
-          uint8_t* yrow = yslots + (half * 2 + (jj >> 1)) * Cfg::YSLOT + (8 + r) * 128;
+          if (pc + 1 < NCH / 16) tmem_ld_32x16(tmem_base + tlane + cbase + (pc + 1) * 16, o[(pc + 1) & 1]);
 #pragma unroll
           for (int c2 = 0; c2 < 2; ++c2) {
-            const int c8 = (pc & 1) * 2 + c2;         // 16-byte chunk (8 channels) within the 32-column group jj
             uint32_t hy[4];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -515,10 +543,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
               hy[2 * e + 1] = row_valid ? h2_bits(__floats2half2_rn(x2 + dn.z, x3 + dn.w)) : 0u;
             }
             if (has_next) {
+              // channel ch .. ch + 8 of row r: y k-block ch >> 6, 16-byte chunk (ch & 63) >> 3 of slot row 8 + r
+              const int ch = nbase + pc * 16 + c2 * 8;
               const uint4 v = make_uint4(hy[0], hy[1], hy[2], hy[3]);
-              *reinterpret_cast<uint4*>(yrow + ((((jj & 1) * 4 + c8) ^ (r & 7)) << 4)) = v;
+              *reinterpret_cast<uint4*>(yslots + (ch >> 6) * Cfg::YSLOT + (8 + r) * 128 + ((((ch & 63) >> 3) ^ (r & 7)) << 4)) = v;
               if (edge) {                               // rows beyond T travel as zeros (the conv's zero padding)
-                uint4* q = ll_out + jj * 8 + c8 * 2;
+                uint4* q = ll_out + pc * 4 + c2 * 2;
                 asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(q), "r"(v.x), "r"(seq_next), "r"(v.y), "r"(seq_next) : "memory");
                 asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(q + 1), "r"(v.z), "r"(seq_next), "r"(v.w), "r"(seq_next) : "memory");
               }
@@ -559,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
           }
         }
         {
-          const int hrow = (side == 0 ? 0 : kTile + 8) + row8;            // row of the slot: [0, 8) left halo, [136, 144) right halo
+          const int hrow = (side == 0 ? 0 : R + 8) + row8;                 // row of the slot: [0, 8) left halo, [R + 8, R + 16) right halo
           uint8_t* dst = yslots + (c16 >> 2) * Cfg::YSLOT + hrow * 128;
           const int ch = (c16 & 3) * 2;                                    // first of the two 16-byte chunks
           *reinterpret_cast<uint4*>(dst + ((ch ^ row8) << 4)) = make_uint4(q0.x, q0.z, q1.x, q1.z);
@@ -579,20 +609,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
     if (ok) ok = wait_acc(&tfull[1], static_cast<uint32_t>(p.nl & 1), 304);
     if (tracer) DSX_STRACE(2, 249);
     if (ok) {
-      const float* bs = p.bskip + static_cast<size_t>(p.nl - 1) * kC + half * 128;
+      // summed skip-half biases of this warp's channels -> its shared-memory table (as the per-layer vectors)
+      __syncwarp();
+      if (lane < NCH / 4)
+        *reinterpret_cast<float4*>(tb + lane * 4) =
+            __ldg(reinterpret_cast<const float4*>(p.bskip + static_cast<size_t>(p.nl - 1) * kC + nbase) + lane);
+      __syncwarp();
+      const float4* bs4 = reinterpret_cast<const float4*>(tb);
       uint32_t o[2][16];
-      tmem_ld_32x16(tmem_base + tlane + 256 + half * 128, o[0]);
+      tmem_ld_32x16(tmem_base + tlane + Cfg::F1_COL + cbase, o[0]);
 #pragma unroll
-      for (int pc = 0; pc < 8; ++pc) {
+      for (int pc = 0; pc < NCH / 16; ++pc) {
         tmem_ld_wait();
-        if (pc + 1 < 8) tmem_ld_32x16(tmem_base + tlane + 256 + half * 128 + (pc + 1) * 16, o[(pc + 1) & 1]);
+        if (pc + 1 < NCH / 16) tmem_ld_32x16(tmem_base + tlane + Cfg::F1_COL + cbase + (pc + 1) * 16, o[(pc + 1) & 1]);
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int i = c2 * 8 + e * 4, col = pc * 16 + i;
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bs + col));
+            const float4 bb = bs4[col >> 2];
             float4 v;
             v.x = __uint_as_float(o[pc & 1][i]) + bb.x;
             v.y = __uint_as_float(o[pc & 1][i + 1]) + bb.y;
@@ -607,8 +643,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
             lo[2 * e] = h2_bits(__floats2half2_rn(sa - f0.x, sb - f0.y));
             lo[2 * e + 1] = h2_bits(__floats2half2_rn(sc - f1.x, sd - f1.y));
           }
-          // channel half * 128 + pc * 16 + c2 * 8 .. + 8 of row r: k-block (channel >> 6), 16-byte chunk ((channel & 63) >> 3)
-          const int ch = half * 128 + pc * 16 + c2 * 8;
+          // channel ch .. ch + 8 of row r: k-block ch >> 6, 16-byte chunk (ch & 63) >> 3
+          const int ch = nbase + pc * 16 + c2 * 8;
           const int off = r * 128 + ((((ch & 63) >> 3) ^ (r & 7)) << 4);
           *reinterpret_cast<uint4*>(aslot(ch >> 6) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(aslot(4 + (ch >> 6)) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -627,7 +663,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       }
       if (row_valid && p.taps) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
+        for (int i = 0; i < NCH / 4; ++i)
           *reinterpret_cast<float4*>(p.X + grow + i * 4) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
       }
     }
@@ -658,22 +694,50 @@ __global__ void k_bskip_prefix(const float* __restrict__ b2, float* __restrict__
   }
 }
 
+// Source row (in w1f / w2f, see dsx_simt.cu) of row n of a stack-kernel weight tile.  GEMM1 tile (chunk h): N index
+// n = g * 128 + j; j < 64 -> gate of channel 128 h + 64 g + j (conv output row of that channel), j >= 64 -> its filter
+// (row 256 + channel): a channel's gate and filter share a TMEM lane in both accumulator layouts (StackCfg).
+__device__ __forceinline__ const float* stack_w_src(const float* w1f, const float* w2f, int l, bool is_w1, int hq, int kb, int n) {
+  if (is_w1) {
+    const int g = n >> 7, j = n & 127;
+    const int ch = 128 * hq + 64 * g + (j & 63);
+    const int row = (j < 64) ? ch : kC + ch;
+    return w1f + (static_cast<size_t>(l) * 2 * kC + row) * (4 * kC) + kb * 64;
+  }
+  return w2f + (static_cast<size_t>(l) * 2 * kC + hq * 256 + n) * kC + kb * 64;
+}
+
+// hi / lo fp16 planes for the fp16x2 / fp16 modes: [L][64 tiles][256 rows][64]; W1 tile = (plane * 2 + h) * 12 + tap * 4 + cb
+// (k-block kb = tap * 4 + cb of [tap0 | tap1 | tap2]), W2 tile = 48 + (plane * 2 + q) * 4 + kb
+__global__ void k_pack_wstk(const float* __restrict__ w1f, const float* __restrict__ w2f, __half* __restrict__ wstk) {
+  const int l = blockIdx.y, tileidx = blockIdx.x, n = threadIdx.x;
+  const float* src;
+  int plane;
+  if (tileidx < 48) {
+    plane = tileidx / 24;
+    src = stack_w_src(w1f, w2f, l, true, (tileidx / 12) & 1, tileidx % 12, n);
+  } else {
+    const int u = tileidx - 48;
+    plane = u / 8;
+    src = stack_w_src(w1f, w2f, l, false, (u / 4) & 1, u & 3, n);
+  }
+  __half* dst = wstk + ((static_cast<size_t>(l) * 64 + tileidx) * 256 + n) * 64;
+  for (int kk = 0; kk < 64; ++kk) {
+    const float v = src[kk];
+    const __half hi = __float2half_rn(v);
+    dst[kk] = plane == 0 ? hi : __float2half_rn(v - __half2float(hi));
+  }
+}
+
 // R stochastically rounded fp16 copies of the GEMM1 / GEMM2 weights (fp16s mode): element v lies between two fp16
 // neighbours lo <= v <= hi and becomes hi with probability (v - lo) / (hi - lo), so E[w] = v; set r is used by diffusion
-// step j with j % R == r.  Layout [R][L][32 tiles][256 rows][64]: W1 tile = h * 12 + tap * 4 + cb, W2 tile = 24 + q * 4 + kb
-// (same row / k conventions as k_pack_wtc in dsx_tc.cu).  Philox4x32-10 keyed by (seed, set), counter = element index.
+// step j with j % R == r.  Layout [R][L][32 tiles][256 rows][64]: W1 tile = h * 12 + tap * 4 + cb, W2 tile = 24 + q * 4 + kb.
+// Philox4x32-10 keyed by (seed, set), counter = element index.
 __global__ void k_pack_wsr(const float* __restrict__ w1f, const float* __restrict__ w2f, __half* __restrict__ wsr, int L,
                            unsigned long long seed) {
   const int l = blockIdx.y, tileidx = blockIdx.x, set = blockIdx.z, n = threadIdx.x;
-  const float* src;
-  if (tileidx < 24) {
-    const int h = tileidx / 12, kb = tileidx % 12;
-    const int j = (n < 128) ? (128 * h + n) : (kC + 128 * h + (n - 128));
-    src = w1f + (static_cast<size_t>(l) * 2 * kC + j) * (4 * kC) + kb * 64;
-  } else {
-    const int u = tileidx - 24, q = u / 4, kb = u & 3;
-    src = w2f + (static_cast<size_t>(l) * 2 * kC + q * 256 + n) * kC + kb * 64;
-  }
+  const float* src = (tileidx < 24) ? stack_w_src(w1f, w2f, l, true, tileidx / 12, tileidx % 12, n)
+                                    : stack_w_src(w1f, w2f, l, false, (tileidx - 24) / 4, (tileidx - 24) & 3, n);
   const size_t row = ((static_cast<size_t>(set) * L + l) * 32 + tileidx) * 256 + n;
   __half* dst = wsr + row * 64;
   const uint2 key = make_uint2(static_cast<uint32_t>(seed) ^ (0x9E3779B9u * static_cast<uint32_t>(set + 1)),
@@ -714,6 +778,7 @@ int tc_stack_pack(dsx_handle* h, cudaStream_t s) {
   h->m.bskip = bskip;
   h->m.wsr = nullptr;
   h->m.wsr_sets = 0;
+  h->m.wstk = nullptr;
   if (h->precision == DSX_PREC_FP16S) {
     const int R = std::max(1, h->sr_sets);
     __half* wsr;
@@ -725,18 +790,29 @@ int tc_stack_pack(dsx_handle* h, cudaStream_t s) {
     DSX_CUDA(cudaGetLastError());
     h->m.wsr = wsr;
     h->m.wsr_sets = R;
+    DSX_TRY(make_map_2d(&h->tm_wsr, wsr, rows, 128));
+  } else if (h->precision == DSX_PREC_FP16 || h->precision == DSX_PREC_FP16X2) {
+    __half* wstk;
+    const size_t rows = static_cast<size_t>(h->m.L) * kStackRowsPerLayer;
+    DSX_TRY(dev_alloc(h, reinterpret_cast<void**>(&wstk), rows * 64 * sizeof(__half), true));
+    dim3 grid(64, h->m.L);
+    k_pack_wstk<<<grid, 256, 0, s>>>(h->m.w1f, h->m.w2f, wstk);
+    h->launches++;
+    DSX_CUDA(cudaGetLastError());
+    h->m.wstk = wstk;
+    DSX_TRY(make_map_2d(&h->tm_wstk, wstk, rows, 128));
   }
   return DSX_OK;
 }
 
-template <int WP>
+template <int WP, int R>
 static int stack_occupancy(dsx_handle* h) {
-  int& cache = h->stack_occ[WP - 1];
+  int& cache = h->stack_occ[WP - 1][R == 128 ? 0 : 1];
   if (cache == 0) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(kG);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = StackCfg::SMEM_BYTES;
+    cfg.dynamicSmemBytes = StackCfg<R>::SMEM_BYTES;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kG;
@@ -745,21 +821,74 @@ static int stack_occupancy(dsx_handle* h) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = 0;
-    cudaFuncSetAttribute(k_tc_stack<WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg::SMEM_BYTES);
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, k_tc_stack<WP>, &cfg);
+    cudaFuncSetAttribute(k_tc_stack<WP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg<R>::SMEM_BYTES);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, k_tc_stack<WP, R>, &cfg);
     if (e != cudaSuccess) cudaGetLastError();
     cache = (e == cudaSuccess && n >= 1) ? n : -1;
   }
   return cache;
 }
 
+static int stack_occ(dsx_handle* h, int rows) {
+  const bool x2 = (h->precision == DSX_PREC_FP16X2);
+  if (rows == 64) return x2 ? stack_occupancy<2, 64>(h) : stack_occupancy<1, 64>(h);
+  return x2 ? stack_occupancy<2, 128>(h) : stack_occupancy<1, 128>(h);
+}
+
+// Rows per CTA for this call: 64-frame tiles (twice the CTAs, about half the time per layer) whenever the whole batch then
+// still fits the machine at once, i.e. for small batches that would otherwise leave most SMs idle; 128-frame tiles otherwise.
+static int stack_rows(dsx_handle* h, const Geom& g) {
+  if (h->stack_rows == 64 || h->stack_rows == 128) return h->stack_rows;      // DSX_OPT_STACK_ROWS
+  const int occ64 = stack_occ(h, 64);
+  if (occ64 > 0 && g.B * (g.Tp / 64) <= occ64 * kG) return 64;
+  return 128;
+}
+
 // Can the register-resident stack kernel take this call?  (every tile of an utterance must be co-resident)
 bool tc_stack_usable(dsx_handle* h, const Geom& g) {
   if (h->stack_kernel == 0 || !h->stack_mode) return false;
   if (h->precision != DSX_PREC_FP16 && h->precision != DSX_PREC_FP16X2 && h->precision != DSX_PREC_FP16S) return false;
-  const int occ = (h->precision == DSX_PREC_FP16X2) ? stack_occupancy<2>(h) : stack_occupancy<1>(h);
+  const int rows = stack_rows(h, g);
+  const int occ = stack_occ(h, rows);
   h->cluster_occ = occ;
-  return occ > 0 && g.tiles_per_utt <= occ * kG;
+  return occ > 0 && g.Tp / rows <= occ * kG;
+}
+
+template <int WP, int R>
+static int launch_stack_t(dsx_handle* h, TcStackParams& prm, const Geom& g, cudaStream_t s) {
+  const int occ = stack_occupancy<WP, R>(h);
+  const int tiles_per_utt = g.Tp / R;
+  const int utt_per_group = occ > 0 ? occ * kG / tiles_per_utt : 0;
+  DSX_CHECK(utt_per_group >= 1, DSX_E_INVALID, "stack kernel: an utterance of %d tiles does not fit %d co-resident CTAs",
+            tiles_per_utt, occ * kG);
+  bool& attr_done = h->attr_stack[WP - 1][R == 128 ? 0 : 1];
+  if (!attr_done) {
+    DSX_CUDA(cudaFuncSetAttribute(k_tc_stack<WP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg<R>::SMEM_BYTES));
+    attr_done = true;
+  }
+  prm.tiles_per_utt = tiles_per_utt;
+  for (int b0 = 0; b0 < g.B; b0 += utt_per_group) {
+    const int nb = std::min(utt_per_group, g.B - b0);
+    prm.tile0 = b0 * tiles_per_utt;
+    prm.tile_end = (b0 + nb) * tiles_per_utt;
+    const int grid = (prm.tile_end - prm.tile0 + kG - 1) / kG * kG;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = StackCfg<R>::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DSX_CUDA(cudaLaunchKernelEx(&cfg, k_tc_stack<WP, R>, prm));
+    h->launches++;
+    h->stack_launches++;
+  }
+  return DSX_OK;
 }
 
 // Layers [0, nl) of one evaluation (table row row0, weight set `wset`), one persistent launch per group of utterances.
@@ -768,42 +897,39 @@ int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_
   const bool x2 = (h->precision == DSX_PREC_FP16X2);
   const bool sr = (h->precision == DSX_PREC_FP16S);
   if (nl <= 0) return DSX_OK;
+  const int rows = stack_rows(h, g);
+  const int ri = rows == 128 ? 0 : 1;
+  h->stack_rows_used = rows;
   TcStackParams prm;
   memset(&prm, 0, sizeof(prm));
-  prm.tm_w = sr ? h->tm_wsr : h->tm_w;
-  prm.tm_y0 = h->tm_yh[0];
-  prm.tm_z = h->tm_z;
-  prm.tm_s16[0] = h->tm_s16[0];
-  prm.tm_s16[1] = h->tm_s16[1];
+  prm.tm_w = sr ? h->tm_wsr : h->tm_wstk;
+  prm.tm_y0 = h->tm_y0s[ri];
+  prm.tm_z = h->tm_zs[ri];
+  prm.tm_s16[0] = h->tm_s16s[ri][0];
+  prm.tm_s16[1] = h->tm_s16s[ri][1];
   prm.taps = h->want_taps;
   prm.X = h->ws.X;
   prm.SKIP = h->ws.SKIP;
-  prm.plane_elems = g.frames_padded() * kC;
   prm.CP = h->ws.CP;
+  prm.cp_tiles = g.tiles;
   prm.cp_prefetch = h->cp_prefetch;
   prm.b2 = m.b2f;
   prm.bskip = m.bskip;
   prm.dtab = h->ws.DTAB + static_cast<size_t>(row0) * m.L * kC;
   prm.d_row_stride = row_per_b * m.L * kC;
-  prm.T = g.T; prm.Tp = g.Tp; prm.tiles_per_utt = g.tiles_per_utt; prm.tiles = g.tiles; prm.B = g.B;
+  prm.T = g.T; prm.Tp = g.Tp; prm.B = g.B;
   prm.nl = nl; prm.L = m.L; prm.cycle = m.cycle;
   prm.w_sr = sr ? 1 : 0;
-  prm.w_layer_rows = sr ? kStackSetRowsPerLayer : kRowsPerLayer;
+  prm.w_layer_rows = sr ? kStackSetRowsPerLayer : kStackRowsPerLayer;
   prm.w_row0 = sr ? (wset % std::max(1, m.wsr_sets)) * m.L * kStackSetRowsPerLayer : 0;
-  prm.s16 = h->ws.S16;
   prm.inv_sqrt_l = 1.0f / sqrtf(static_cast<float>(m.L));
   prm.fast_act = h->gate_approx >= 0 ? h->gate_approx : 1;
   prm.status = h->status_dev;
   prm.budget_ns = 4000000000ull;
   prm.trace = h->trace_dev;
-  const int occ = x2 ? stack_occupancy<2>(h) : stack_occupancy<1>(h);
-  const int cap_tiles = occ * kG;
-  const int utt_per_group = cap_tiles / g.tiles_per_utt;
-  DSX_CHECK(utt_per_group >= 1, DSX_E_INVALID, "stack kernel: an utterance of %d tiles does not fit %d co-resident CTAs",
-            g.tiles_per_utt, cap_tiles);
   // halo packets: 32 KB per tile, zeroed once (sequence numbers start at 1 and only grow, so packets left behind by earlier
   // evaluations, other geometries or an aborted launch can never be mistaken for the current layer's)
-  const size_t ll_bytes = static_cast<size_t>(g.tiles + 2) * 4 * 512 * sizeof(uint4);
+  const size_t ll_bytes = static_cast<size_t>(g.B * (g.Tp / 64) + 2) * 4 * 512 * sizeof(uint4);
   if (h->ll_cap < ll_bytes) {
     if (h->ll_dev) cudaFree(h->ll_dev);
     h->ll_dev = nullptr;
@@ -818,34 +944,10 @@ int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_
   }
   prm.ll = static_cast<uint4*>(h->ll_dev);
   prm.seq_base = h->ll_seq;
-  bool& attr_done = h->attr_stack[x2 ? 1 : 0];
-  if (!attr_done) {
-    if (x2) DSX_CUDA(cudaFuncSetAttribute(k_tc_stack<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg::SMEM_BYTES));
-    else DSX_CUDA(cudaFuncSetAttribute(k_tc_stack<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, StackCfg::SMEM_BYTES));
-    attr_done = true;
-  }
-  for (int b0 = 0; b0 < g.B; b0 += utt_per_group) {
-    const int nb = std::min(utt_per_group, g.B - b0);
-    prm.tile0 = b0 * g.tiles_per_utt;
-    prm.tile_end = (b0 + nb) * g.tiles_per_utt;
-    const int grid = (prm.tile_end - prm.tile0 + kG - 1) / kG * kG;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = StackCfg::SMEM_BYTES;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (x2) DSX_CUDA(cudaLaunchKernelEx(&cfg, k_tc_stack<2>, prm));
-    else DSX_CUDA(cudaLaunchKernelEx(&cfg, k_tc_stack<1>, prm));
-    h->launches++;
-    h->stack_launches++;
-  }
+  int rc;
+  if (rows == 128) rc = x2 ? launch_stack_t<2, 128>(h, prm, g, s) : launch_stack_t<1, 128>(h, prm, g, s);
+  else rc = x2 ? launch_stack_t<2, 64>(h, prm, g, s) : launch_stack_t<1, 64>(h, prm, g, s);
+  DSX_TRY(rc);
   h->ll_seq += static_cast<unsigned int>(nl);
   return DSX_OK;
 }

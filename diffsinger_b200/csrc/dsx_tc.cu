@@ -1551,8 +1551,6 @@ int tc_pack_model(dsx_handle* h, cudaStream_t s) {
   DSX_CUDA(cudaGetLastError());
   h->m.whead = whead;
   DSX_TRY(tc_stack_pack(h, s));
-  if (h->m.wsr)
-    DSX_TRY(make_map_2d(&h->tm_wsr, h->m.wsr, static_cast<uint64_t>(h->m.wsr_sets) * h->m.L * kStackSetRowsPerLayer, 128));
   return DSX_OK;
 }
 
@@ -1619,6 +1617,13 @@ int tc_prepare_maps(dsx_handle* h, const Geom& g) {
   }
   DSX_TRY(make_map_2d(&h->tm_whead, h->m.whead, 32 * 128, 128));
   DSX_TRY(make_map_act(&h->tm_z, h->ws.Z, kC, g.T, g.Tp, h->m.L * g.B));
+  for (int ri = 0; ri < 2; ++ri) {        // stack kernel: boxes of 128 / 64 frames per CTA
+    const int rows = ri == 0 ? 128 : 64;
+    DSX_TRY(make_map_act(&h->tm_y0s[ri], h->ws.Y, kC, g.T, g.Tp, g.B, rows + 16));
+    DSX_TRY(make_map_act(&h->tm_zs[ri], h->ws.Z, kC, g.T, g.Tp, h->m.L * g.B, rows));
+    for (int pl = 0; pl < 2; ++pl)
+      DSX_TRY(make_map_act(&h->tm_s16s[ri][pl], h->ws.S16 + static_cast<size_t>(pl) * plane, kC, g.T, g.Tp, g.B, rows));
+  }
   h->tm_geom = g;
   h->tm_epoch = h->ws_epoch;
   h->tm_group = h->tc_group;

@@ -314,21 +314,54 @@ def test_stack_mode_matches_per_layer_launches(dsx, prec):
         assert torch.equal(u, v)
 
 
-@pytest.mark.parametrize("prec", ["fp16x2", "fp16"])
-def test_stack_kernel_matches_layer_kernel(dsx, prec):
+@pytest.mark.parametrize("prec,rows", [("fp16x2", 128), ("fp16x2", 64), ("fp16", 128), ("fp16", 64), ("fp16x2", 0)])
+def test_stack_kernel_matches_layer_kernel(dsx, prec, rows):
     """The register-resident stack kernel (dsx_stack.cu: x in registers, y in shared memory, halo packets, deferred skip GEMM)
     against the round-1 layer kernel on the same operands: same products, different fp32 summation order (centre taps first,
     skip sum as one K = 5120 contraction), so agreement is to rounding, not bit for bit -- over ragged geometries changing on
-    one handle (partial last tiles, single-tile utterances, odd tile counts -> padding CTA, > 148 tiles -> launch groups).
-    The stack kernel itself is deterministic: the same call twice is bit-identical."""
+    one handle (partial last tiles, single-tile utterances, odd tile counts -> padding CTA, > 148 tiles -> launch groups), with
+    128 and with 64 frames per CTA (the small-batch mode: UMMA M = 128, accumulator halves in lanes 0-63 / 64-127) and with the
+    automatic choice.  The stack kernel itself is deterministic: the same call twice is bit-identical."""
     from diffsinger_b200 import _capi
+    ga = 0 if prec == "fp16x2" else 1
     a, la = _eval_shapes(dsx, prec, ((_capi.OPT_STACK_KERNEL, 0), (_capi.OPT_GATE_APPROX, 0)))
-    b, lb = _eval_shapes(dsx, prec, ((_capi.OPT_STACK_KERNEL, 1), (_capi.OPT_GATE_APPROX, 0 if prec == "fp16x2" else 1)))
-    c, _ = _eval_shapes(dsx, prec, ((_capi.OPT_STACK_KERNEL, 1), (_capi.OPT_GATE_APPROX, 0 if prec == "fp16x2" else 1)))
+    b, lb = _eval_shapes(dsx, prec, ((_capi.OPT_STACK_KERNEL, 1), (_capi.OPT_GATE_APPROX, ga), (_capi.OPT_STACK_ROWS, rows)))
+    c, _ = _eval_shapes(dsx, prec, ((_capi.OPT_STACK_KERNEL, 1), (_capi.OPT_GATE_APPROX, ga), (_capi.OPT_STACK_ROWS, rows)))
     assert la == 0 and lb > 0
     for u, v, w in zip(a, b, c):
         assert (u - v).abs().max() < (6e-4 if prec == "fp16x2" else 3e-3), (u - v).abs().max()
         assert torch.equal(v, w)
+
+
+@pytest.mark.parametrize("prec", ["fp16s", "fp16x2"])
+def test_small_batch_mode_golden_loop(dsx, prec):
+    """64 frames per CTA (what small batches get automatically): the K = 100 golden loop and the dilation-cycle-4 PLMS fixture
+    hold the same bounds as with 128 frames per CTA."""
+    from diffsinger_b200 import _capi
+    g = golden("ddpm_lj_K100.npz")
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    s, dev = make_sampler(dsx, 1, prec, S)
+    cond, xT = torch.from_numpy(g["cond"]).to(dev), torch.from_numpy(g["xT"]).to(dev)
+    noise = rs_normal(int(g["noise_seed"]), (100,) + tuple(g["xT"].shape)).to(dev)
+    res = {}
+    for rows in (64, 128):
+        s.set_option(_capi.OPT_STACK_ROWS, rows)
+        x0 = s.sample_ddpm(xT, cond, 100, 100, noise=noise).cpu().numpy()
+        assert s.info(_capi.INFO_STACK_ROWS) == rows
+        res[rows] = np.abs(x0 - g["x0"]).max()
+        assert res[rows] < PARITY_TOL
+    s.set_option(_capi.OPT_STACK_ROWS, 0)
+    s.sample_ddpm(xT, cond, 100, 1, noise=noise[:1])
+    assert s.info(_capi.INFO_STACK_ROWS) == 64                 # B = 2, T = 96: the automatic choice
+    print(f"small-batch mode {prec}: max {res[64]:.3e} (64 rows) {res[128]:.3e} (128 rows)")
+    s.close()
+    g = golden("plms_K300_cycle4.npz")
+    S = O.make_schedule(O.linear_beta_schedule(1000, 0.02))
+    s, dev = make_sampler(dsx, 4, prec, S)
+    s.set_option(_capi.OPT_STACK_ROWS, 64)
+    out = s.sample_plms(torch.from_numpy(g["xT"]).to(dev), torch.from_numpy(g["cond"]).to(dev), 300, 10).cpu().numpy()
+    assert np.abs(out - g["x0_interval10"]).max() < PARITY_TOL
+    s.close()
 
 
 @pytest.mark.parametrize("prec", ["fp16x2", "fp16x3"])

@@ -47,12 +47,12 @@ def quick():
     g = golden("diffnet_fwd_cycle4.npz")
     spec, cond, t = (torch.from_numpy(g[k]).to(DEV) for k in ("spec", "cond", "t"))
     B, _, M, T = g["spec"].shape
-    for prec in ("fp16x2", "fp16s", "fp16"):
-        s = make(4, prec, 1)
+    for prec, rows in (("fp16x2", 128), ("fp16s", 128), ("fp16", 128), ("fp16x2", 64), ("fp16s", 64)):
+        s = make(4, prec, 1, opts=((_capi.OPT_STACK_ROWS, rows),))
         eps = s.diffnet_forward(spec, t, cond).cpu().numpy()
         x_last = s.debug_read(0, B, T).cpu().numpy()
         skip = s.debug_read(1, B, T).cpu().numpy()
-        print(f"quick {prec}: eps {np.abs(eps - g['eps']).max():.3e} x20 {np.abs(x_last[1].T - g['x20_b1']).max():.3e} "
+        print(f"quick {prec} rows {rows}/{s.info(_capi.INFO_STACK_ROWS)}: eps {np.abs(eps - g['eps']).max():.3e} x20 {np.abs(x_last[1].T - g['x20_b1']).max():.3e} "
               f"skip {np.abs(skip[0].T - g['skip_sum_b0']).max():.3e} stack launches {s.info(_capi.INFO_STACK_KERNEL_LAUNCHES)}",
               flush=True)
         s.close()
@@ -162,6 +162,37 @@ def experiments():
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "dev_experiments.json"), "w"), indent=1)
 
 
+def small():
+    """small batches: 64 vs 128 frames per CTA (BASELINE config 1 and the per-GPU shard of the strong-scaled config 4)"""
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    res = {}
+    for (B, T) in ((1, 512), (4, 1024), (8, 1024), (2, 2048)):
+        gen = torch.Generator().manual_seed(1)
+        cond = torch.randn(B, T, 256, generator=gen).transpose(1, 2).to(DEV)
+        x = torch.randn(B, 1, 80, T, generator=gen).to(DEV)
+        for prec in ("fp16s", "fp16x2"):
+            outs = {}
+            for rows in (128, 64):
+                s = make(1, prec, 1, S, opts=((_capi.OPT_STACK_ROWS, rows),))
+                K = 20
+                outs[rows] = s.sample_ddpm(x, cond, 100, 5, seed=1)
+                torch.cuda.synchronize()
+                s.set_option(_capi.OPT_PROFILE, 1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                s.sample_ddpm(x, cond, 100, K, seed=1)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / K
+                layer_ms = s.info(_capi.INFO_LAYER_KERNEL_NS) / 1e6 / max(s.info(_capi.INFO_LAYER_KERNEL_LAUNCHES), 1)
+                r = dict(ms_per_step=ms, stack_ms=layer_ms, frames_per_s_K100=B * T / (ms * 100 / 1e3), rows=s.info(_capi.INFO_STACK_ROWS))
+                res[f"{B}x{T}_{prec}_rows{rows}"] = r
+                print(f"small {B}x{T} {prec} rows={rows}: {r}", flush=True)
+                s.close()
+            print(f"   64 vs 128 rows, 5 DDPM steps (Philox noise): max diff {(outs[64] - outs[128]).abs().max().item():.3e}", flush=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "dev_small.json"), "w"), indent=1)
+
+
 def timing():
     S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
     res = {}
@@ -232,4 +263,4 @@ def trace():
 
 
 if __name__ == "__main__":
-    {"quick": quick, "experiments": experiments, "parity": parity, "timing": timing, "trace": trace}[sys.argv[1]]()
+    {"quick": quick, "small": small, "experiments": experiments, "parity": parity, "timing": timing, "trace": trace}[sys.argv[1]]()
