@@ -33,7 +33,7 @@ def _need_cuda(*tensors):
 
 
 def default_precision():
-    return os.environ.get("DSX_PRECISION", "fp16x2")
+    return os.environ.get("DSX_PRECISION", "fp16s")
 
 
 class DsxSampler:
