@@ -352,21 +352,32 @@ def timed_steps(arm, steps, warmup, world, dev, flush, gather_total=None, clocks
 
 
 def roofline_of(arm, prec, ms_per_step):
-    """Residual-stack kernel (all 20 layers of an evaluation), CUDA events around its launches on the launching stream."""
+    """The dominant kernel, CUDA events around its launches on the launching stream (DSX_OPT_PROFILE).  With the fused head
+    (default) that kernel is the whole diffusion step -- residual stack, skip GEMM, head projections, sampler update, next
+    input projection -- so its algorithmic FLOPs are those of a whole DiffNet evaluation; `stack_only` repeats the
+    measurement with the head as a separate kernel (DSX_OPT_FUSED_HEAD = 0): the residual stack alone, the quantity round 1
+    reported."""
     capi = arm.capi
     cfg, B, T = arm.cfg, arm.B, arm.T
-    arm.s.set_option(capi.OPT_PROFILE, 1)
-    arm.step(99)
-    ns, n = arm.s.info(capi.INFO_LAYER_KERNEL_NS), arm.s.info(capi.INFO_LAYER_KERNEL_LAUNCHES)
-    stack_launches = arm.s.info(capi.INFO_STACK_KERNEL_LAUNCHES)
-    arm.s.set_option(capi.OPT_PROFILE, 0)
-    avg_eval_s = ns * 1e-9 / max(n, 1)              # brackets are per evaluation (all 20 residual layers, every launch group)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
+
+    def profile(fused):
+        arm.s.set_option(capi.OPT_FUSED_HEAD, 1 if fused else 0)
+        arm.step(98)
+        arm.s.set_option(capi.OPT_PROFILE, 1)
+        arm.step(99)
+        ns, n = arm.s.info(capi.INFO_LAYER_KERNEL_NS), arm.s.info(capi.INFO_LAYER_KERNEL_LAUNCHES)
+        arm.s.set_option(capi.OPT_PROFILE, 0)
+        return ns, n, ns * 1e-9 / max(n, 1)       # brackets are per evaluation (every launch group)
+
+    ns_s, n_s, t_stack = profile(False)
+    ns, n, t_eval = profile(True)
+    stack_launches = arm.s.info(capi.INFO_STACK_KERNEL_LAUNCHES)
     traffic, traffic_note = None, "not captured for this configuration"
     try:     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel, per launch
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_stack_traffic.json")))
@@ -375,18 +386,24 @@ def roofline_of(arm, prec, ms_per_step):
             traffic_note = tj.get("note", "static: from the committed ncu capture of this command (profiles/), not re-measured by this run")
     except Exception:
         pass
-    flops = FLOP_PER_FRAME_LAYER * B * T * 20
-    ach = flops / avg_eval_s / 1e12
-    kernel = "k_tc_stack (dsx_stack.cu: residual stack, x in registers / y in smem / deferred skip GEMM, tcgen05)" if stack_launches else \
+    flops_stack = FLOP_PER_FRAME_LAYER * B * T * 20
+    flops_eval = FLOP_PER_FRAME_EVAL * B * T
+    fused = bool(stack_launches) and arm.s.info(capi.INFO_KERNEL_LAUNCHES) > 0
+    kernel = ("k_tc_stack (dsx_stack.cu, tcgen05): the whole diffusion step in one launch -- residual stack with x in registers / y in shared "
+              "memory, deferred skip GEMM, head projections, sampler update, next input projection") if stack_launches else \
         "k_tc_layer (dsx_tc.cu: round-1 residual-stack kernel)"
+    ach = flops_eval / t_eval / 1e12
+    whole = FLOP_PER_FRAME_EVAL * B * T * n_evals(cfg) / (ms_per_step * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
             "traffic": traffic, "traffic_note": traffic_note,
-            "flops_per_launch": flops, "avg_launch_us": avg_eval_s * 1e6, "avg_layer_us": avg_eval_s * 1e6 / 20,
-            "evaluations_profiled": n, "stack_share_of_step": ns * 1e-6 / ms_per_step,
-            "mma_passes": PASSES.get(prec), "executed_tflops": flops * PASSES.get(prec, 1.0) / avg_eval_s / 1e12,
-            "whole_step_algorithmic_tflops": FLOP_PER_FRAME_EVAL * B * T * n_evals(cfg) / (ms_per_step * 1e-3) / 1e12,
-            "whole_step_frac": FLOP_PER_FRAME_EVAL * B * T * n_evals(cfg) / (ms_per_step * 1e-3) / 1e12 / peak}
+            "flops_per_launch": flops_eval, "avg_launch_us": t_eval * 1e6, "evaluations_profiled": n,
+            "kernel_share_of_step": ns * 1e-6 / ms_per_step, "mma_passes": PASSES.get(prec),
+            "stack_only": {"note": "head as a separate kernel (DSX_OPT_FUSED_HEAD = 0): the 20 residual layers + skip GEMM alone",
+                           "achieved": flops_stack / t_stack / 1e12, "frac": flops_stack / t_stack / 1e12 / peak,
+                           "flops_per_launch": flops_stack, "avg_launch_us": t_stack * 1e6, "avg_layer_us": t_stack * 1e6 / 20,
+                           "evaluations_profiled": n_s},
+            "whole_step_algorithmic_tflops": whole, "whole_step_frac": whole / peak}
 
 
 def e2e_of(dsx, cfg, prec, dev, rank, world, steps):
@@ -502,7 +519,7 @@ def main():
                 r = bench_config(dsx, c, prec, quick, dev, rank, world, local_rank, flush, full=False)
                 sweep.append({"B": Bs, "T": Ts, "K": 25, "frames_per_s": r["value"], "ms_per_step": r["ms_per_step"],
                               "roofline_frac": r["roofline"]["frac"] if r["roofline"] else None,
-                              "stack_tflops": r["roofline"]["achieved"] if r["roofline"] else None,
+                              "stack_only_frac": r["roofline"]["stack_only"]["frac"] if r["roofline"] else None,
                               "workspace_bytes": r["workspace_bytes"]})
         for Ks, Tsch, mb in ((25, 100, 0.06), (100, 100, 0.06), (1000, 1000, 0.02)):
             c = dict(CONFIGS["2"], K=Ks, T_sched=Tsch, max_beta=mb, name=f"sweep B=16 T=1024 K={Ks}")

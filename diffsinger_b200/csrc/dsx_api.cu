@@ -122,7 +122,11 @@ void reset_flags(dsx_handle* h) {
   h->flags_kind = 0;
 }
 
-static int run_layers(dsx_handle* h, const Geom& g, int row0, int row_per_b, int nl, cudaStream_t s) {
+// Residual layers [0, nl) of one evaluation; `head` (may be null): what follows them in the step.  Returns through
+// *head_done whether the head ran inside the stack launch (the caller then skips launch_tc_head).
+static int run_layers(dsx_handle* h, const Geom& g, int row0, int row_per_b, int nl, cudaStream_t s, const HeadArgs* head = nullptr,
+                      bool* head_done = nullptr) {
+  if (head_done) *head_done = false;
   const bool tc = h->precision != DSX_PREC_FP32_SIMT;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profile == 1) {
@@ -138,8 +142,13 @@ static int run_layers(dsx_handle* h, const Geom& g, int row0, int row_per_b, int
   }
   if (tc) {
     // weight set of DSX_PREC_FP16S: evaluation (= table row) j of a loop uses set j % R
-    if (tc_stack_usable(h, g)) DSX_TRY(launch_tc_stack(h, nl, g, row0, row_per_b, row0, s));
-    else DSX_TRY(launch_tc_layers(h, 0, nl, g, row0, row_per_b, s));
+    if (tc_stack_usable(h, g)) {
+      const bool fuse = head && head->flags && h->fused_head && nl == h->m.L && h->profile != 2;
+      DSX_TRY(launch_tc_stack(h, nl, g, row0, row_per_b, row0, s, fuse ? head : nullptr));
+      if (fuse && head_done) *head_done = true;
+    } else {
+      DSX_TRY(launch_tc_layers(h, 0, nl, g, row0, row_per_b, s));
+    }
   } else {
     for (int l = 0; l < nl; ++l) DSX_TRY(launch_simt_layer(h, l, g, row0, row_per_b, s));
   }
@@ -157,8 +166,14 @@ static int run_eval(dsx_handle* h, const float* x, dsx_strides xs, const Geom& g
     DSX_TRY(launch_tc_head(h, g, TC_INPROJ, const_cast<float*>(x), xs, nullptr, nullptr, 0, 0, none, row0, row_per_b, s));
   else
     DSX_TRY(launch_inproj(h, x, xs, g, row0, row_per_b, s));
-  DSX_TRY(run_layers(h, g, row0, row_per_b, nl, s));
-  if (nl == h->m.L) {
+  HeadArgs ha;
+  ha.flags = TC_HEAD | TC_WRITE_EPS;
+  ha.x = const_cast<float*>(x);          // (read only with these flags)
+  ha.xs = xs;
+  ha.eps = eps;
+  bool head_done = false;
+  DSX_TRY(run_layers(h, g, row0, row_per_b, nl, s, (tc && nl == h->m.L) ? &ha : nullptr, &head_done));
+  if (nl == h->m.L && !head_done) {
     if (tc)
       DSX_TRY(launch_tc_head(h, g, TC_HEAD | TC_WRITE_EPS, nullptr, xs, eps, nullptr, 0, 0, none, row0, row_per_b, s));
     else
@@ -223,8 +238,13 @@ static int sample_ddpm_impl(dsx_handle* h, float* x, const Geom& g, int t_start,
     const float* nz = noise ? noise + static_cast<size_t>(j) * mel : nullptr;
     if (tc) {
       // 20 fused residual-layer kernels, then ONE kernel: head GEMMs + p_sample update + next step's input projection
-      DSX_TRY(run_layers(h, g, j, 0, h->m.L, s));
       const int flags = TC_HEAD | TC_UPDATE | (j + 1 < n_steps ? TC_INPROJ : 0);
+      HeadArgs ha;
+      ha.flags = flags; ha.x = x; ha.xs = xs; ha.noise = nz; ha.seed = seed; ha.offset = static_cast<uint64_t>(j); ha.c = c;
+      ha.next_row0 = j + 1; ha.row_per_b = 0;
+      bool head_done = false;
+      DSX_TRY(run_layers(h, g, j, 0, h->m.L, s, &ha, &head_done));
+      if (head_done) continue;               // ONE launch did the whole diffusion step
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (h->profile == 2) {                       // DSX_OPT_PROFILE = 2: bracket the head kernel instead of the layer stack
         while (h->prof_events.size() < h->prof_used + 2) {
@@ -288,19 +308,26 @@ static int sample_plms_impl(dsx_handle* h, float* x, const Geom& g, int t_start,
       float* e0 = E[slot];
       PlmsFuse pf{};
       plms_coefs(h, t, interval, pf.c);
-      DSX_TRY(run_layers(h, g, j, 0, h->m.L, s));
       const int next_flags = (j + 1 < n) ? TC_INPROJ : 0;
+      // residual stack of table row `row` followed by the head with `flags` / `pp` (fused into one launch where possible)
+      auto step = [&](int row, int flags, const PlmsFuse& pp, int next_row) -> int {
+        HeadArgs ha;
+        ha.flags = flags; ha.x = x; ha.xs = xs; ha.next_row0 = next_row; ha.row_per_b = 0; ha.plms = &pp;
+        bool head_done = false;
+        DSX_TRY(run_layers(h, g, row, 0, h->m.L, s, &ha, &head_done));
+        if (!head_done) DSX_TRY(launch_tc_head(h, g, flags, x, xs, nullptr, nullptr, 0, 0, none, next_row, 0, s, &pp));
+        return DSX_OK;
+      };
       if (nh == 0) {
         // x' = phi(x, eps_t, t) -> XTMP; eps'' = net(x', max(t - interval, 0)); eps* = (eps_t + eps'') / 2; x = phi(x, eps*, t)
         PlmsFuse p1 = pf;
         p1.c.w0 = 1.f; p1.c.denom = 1.f;
         p1.eps_store = e0;
         p1.x_out = h->ws.XTMP;
-        DSX_TRY(launch_tc_head(h, g, TC_HEAD | TC_PLMS | TC_INPROJ, x, xs, nullptr, nullptr, 0, 0, none, n, 0, s, &p1));
-        DSX_TRY(run_layers(h, g, n, 0, h->m.L, s));
+        DSX_TRY(step(j, TC_HEAD | TC_PLMS | TC_INPROJ, p1, n));
         pf.c.w0 = 1.f; pf.c.w1 = 1.f; pf.c.denom = 2.f;
         pf.h1 = e0;
-        DSX_TRY(launch_tc_head(h, g, TC_HEAD | TC_PLMS | next_flags, x, xs, nullptr, nullptr, 0, 0, none, j + 1, 0, s, &pf));
+        DSX_TRY(step(n, TC_HEAD | TC_PLMS | next_flags, pf, j + 1));
       } else {
         if (nh == 1) { pf.c.w0 = 3.f; pf.c.w1 = -1.f; pf.c.denom = 2.f; }
         else if (nh == 2) { pf.c.w0 = 23.f; pf.c.w1 = -16.f; pf.c.w2 = 5.f; pf.c.denom = 12.f; }
@@ -309,7 +336,7 @@ static int sample_plms_impl(dsx_handle* h, float* x, const Geom& g, int t_start,
         pf.h2 = nh >= 2 ? hist[1] : nullptr;
         pf.h3 = nh >= 3 ? hist[2] : nullptr;
         pf.eps_store = e0;
-        DSX_TRY(launch_tc_head(h, g, TC_HEAD | TC_PLMS | next_flags, x, xs, nullptr, nullptr, 0, 0, none, j + 1, 0, s, &pf));
+        DSX_TRY(step(j, TC_HEAD | TC_PLMS | next_flags, pf, j + 1));
       }
       hist[3] = hist[2]; hist[2] = hist[1]; hist[1] = hist[0]; hist[0] = e0;
       nh = std::min(nh + 1, 4);
@@ -655,6 +682,7 @@ int dsx_set_option(dsx_handle* h, int what, int64_t value) {
     case DSX_OPT_STACK_MODE: h->stack_mode = static_cast<int>(value); break;
     case DSX_OPT_STACK_KERNEL: h->stack_kernel = static_cast<int>(value); break;
     case DSX_OPT_GATE_APPROX: h->gate_approx = static_cast<int>(value); break;
+    case DSX_OPT_FUSED_HEAD: h->fused_head = static_cast<int>(value); break;
     case DSX_OPT_STACK_ROWS:
       DSX_CHECK(value == 0 || value == 64 || value == 128, DSX_E_INVALID, "DSX_OPT_STACK_ROWS must be 0 (automatic), 64 or 128");
       h->stack_rows = static_cast<int>(value);

@@ -127,7 +127,7 @@ struct dsx_handle {
   int* status_dev = nullptr;   // kernel watchdog / self-check word
   int* status_host = nullptr;  // pinned mirror
   CUtensorMap tm_w{}, tm_y[2][2]{}, tm_yh[2]{}, tm_ye[2]{}, tm_cond[2]{}, tm_s16[2]{}, tm_whead{}, tm_wsr{}, tm_wstk{}, tm_z{};
-  CUtensorMap tm_y0s[2]{}, tm_zs[2]{}, tm_s16s[2][2]{};   // stack kernel, [0]: 128 rows per CTA, [1]: 64 rows per CTA
+  CUtensorMap tm_y0s[2]{}, tm_zs[2]{}, tm_s16s[2][2]{}, tm_xst[2]{}, tm_y0st[2]{};   // stack kernel, [0]: 128 rows per CTA, [1]: 64 rows per CTA
   dsx::Geom tm_geom;           // geometry the activation maps were built for
   int tm_group = 0;
   int profile = 0;
@@ -144,6 +144,7 @@ struct dsx_handle {
   int stack_kernel = 1;                // DSX_OPT_STACK_KERNEL: 1 = register-resident stack kernel (dsx_stack.cu) where it applies
   int stack_occ[2][2] = {};            // co-resident CTA pairs of k_tc_stack<WP, R> [WP - 1][R == 64] (0 unknown, -1 none)
   bool attr_stack[2][2] = {};
+  int fused_head = 1;                  // DSX_OPT_FUSED_HEAD: the head / sampler update / next input projection run inside the stack launch
   int stack_rows = 0;                  // DSX_OPT_STACK_ROWS: 0 = automatic, 64 / 128 forced
   int stack_rows_used = 0;             // rows per CTA of the last stack launch
   int sr_sets = 64;                    // DSX_OPT_SR_SETS: weight sets of DSX_PREC_FP16S (takes effect at the next dsx_load_diffnet)
@@ -219,7 +220,20 @@ void reset_flags(dsx_handle* h);
 // ---- dsx_stack.cu ------------------------------------------------------------------------
 int tc_stack_pack(dsx_handle* h, cudaStream_t s);
 bool tc_stack_usable(dsx_handle* h, const Geom& g);
-int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_b, int wset, cudaStream_t s);
+// What follows the residual stack inside a diffusion step (k_tc_head's job), optionally fused into the stack launch
+struct HeadArgs {
+  int flags = 0;            // TC_* (0: no head)
+  float* x = nullptr;       // mel state
+  dsx_strides xs{};
+  float* eps = nullptr;     // TC_WRITE_EPS
+  const float* noise = nullptr;
+  uint64_t seed = 0, offset = 0;
+  DdpmCoef c{};
+  int next_row0 = 0, row_per_b = 0;   // FiLM table row of the NEXT evaluation (TC_INPROJ)
+  const PlmsFuse* plms = nullptr;
+};
+int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_b, int wset, cudaStream_t s,
+                    const HeadArgs* head = nullptr);
 
 int dev_alloc(dsx_handle* h, void** p, size_t bytes, bool model_owned);
 int ensure_workspace(dsx_handle* h, const Geom& g, int rows, cudaStream_t s);

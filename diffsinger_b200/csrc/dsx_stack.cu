@@ -77,6 +77,7 @@ struct StackCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(YSLOT % 1024 == 0 && UNIT % 1024 == 0, "tiles must keep the 1024-byte swizzle atoms aligned");
   static_assert(Y_BYTES >= 4 * UNIT, "A ring units in the y area");
+  static_assert(W_BYTES + Y_BYTES + Z_BYTES >= 12 * UNIT, "exit tiles of the fused head (8 fp32 + 4 fp16 units) over the W / y / z areas");
 };
 
 struct TcStackParams {
@@ -106,6 +107,27 @@ struct TcStackParams {
   int fast_act;            // 1: tanh.approx gate
   int taps;                // 1: write the residual stream and the fp32 skip sum back to X / SKIP at exit (debug taps of
                            // dsx_diffnet_forward); the sampling loops do not need them
+  // ---- fused head (head_flags != 0; flags as for k_tc_head): skip / output projections (net.py:115-118, 126-130), the sampler
+  //      update on the mel state (shallow_diffusion_tts.py:134-204) and the next evaluation's input projection -- the rest of
+  //      the diffusion step runs in this launch too: ONE kernel per step ----
+  int head_flags;
+  CUtensorMap tm_wh;       // whead tiles [32][128 rows][64]: skip_projection, output_projection, input_projection packs
+  CUtensorMap tm_xst;      // X fp32 [B][T][256], box 32 ch x R frames, SWIZZLE_128B: store of the next evaluation's x0
+  CUtensorMap tm_y0st;     // Y buffer 0 fp16, box 64 ch x R frames: store of the next evaluation's layer-0 conv input
+  float* xmel;             // mel state [B,1,M,T] through xs (in / out)
+  dsx_strides xs;
+  float* eps_out;          // TC_WRITE_EPS: [B][M][T]
+  const float* noise;      // [B][M][T] for this step, or nullptr -> Philox
+  unsigned long long seed, offset;
+  int b_off;
+  DdpmCoef c;
+  PlmsFuse pl;
+  const float* bs;         // skip_projection.bias [256]
+  const float* bf;         // output_projection.bias [M]
+  const float* bin;        // input_projection.bias [256]
+  const float* d0;         // FiLM vector of layer 0 for the NEXT evaluation, utterance b at + b * d0_row_stride
+  int d0_row_stride;
+  int M;
   int* status;
   unsigned long long budget_ns;
   long long* trace;        // debug: [2 CTAs][3 roles][256] clock64 stamps, or nullptr
@@ -168,6 +190,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
     tma_prefetch_desc(&p.tm_z);
     tma_prefetch_desc(&p.tm_s16[0]);
     tma_prefetch_desc(&p.tm_s16[1]);
+    if (p.head_flags) {
+      tma_prefetch_desc(&p.tm_wh);
+      tma_prefetch_desc(&p.tm_xst);
+      tma_prefetch_desc(&p.tm_y0st);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < WS; ++s) {
@@ -286,6 +313,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       for (int l = p.nl - 1; l >= 0 && ok; --l)                      // skip GEMM (same order as its A tiles)
         for (int kb = 0; kb < 4 && ok; ++kb)
           for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, 1, kb, pl));
+      if (p.head_flags) {
+        // fused head: 128-row tiles of the whead pack (hi plane, lo plane per k-block).  The N = 256 operand of a pair is
+        // [leader's tile | peer's tile]: the row halves of skip_projection / input_projection, twice the same tile for
+        // output_projection (N = 80 padded to 128; the upper 128 columns of its accumulator are a copy)
+        auto load_wh = [&](int tileidx) {
+          if ((wi & 1) == wid) {
+            const uint32_t s = wi % WS;
+            ok = mbar_wait(&empty[s], ((wi / WS) & 1) ^ 1, wd, 111);
+            if (ok) {
+              if (prank == 0) mbar_arrive_expect_tx(&full[s], G * kUnitBytes);
+              tma_load_2d<G>(&p.tm_wh, &full[s], wring + s * kUnitBytes, 0, tileidx * 128, lead);
+            }
+          }
+          ++wi;
+        };
+        const int nh = static_cast<int>(prank);
+        for (int kb = 0; kb < 4 && ok; ++kb)
+          for (int pl = 0; pl < 2 && ok; ++pl) load_wh((pl * 2 + nh) * 4 + kb);
+        for (int kb = 0; kb < 4 && ok; ++kb)
+          for (int pl = 0; pl < 2 && ok; ++pl) load_wh(16 + pl * 4 + kb);
+        if (p.head_flags & TC_INPROJ)
+          for (int kb = 0; kb < 2 && ok; ++kb)
+            for (int pl = 0; pl < 2 && ok; ++pl) load_wh(24 + (pl * 2 + nh) * 2 + kb);
+      }
     } else if (warp == 1 && lane == 0 && prank == 0) {
       // ================================ MMA issuer (pair leader) ================================
       constexpr uint32_t idesc = umma_idesc_f16(R * G, 256);
@@ -376,6 +427,46 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         }
       if (ok) umma_commit<G>(&tfull[1], pair_mask);
       DSX_STRACE(1, 250);
+      if (p.head_flags && ok) {
+        // ---- fused head: three small GEMMs, hi/lo split of both operands (A_hi W_hi + A_lo W_hi + A_hi W_lo), each K block's A
+        //      tiles (hi: A-ring units 0-3, lo: 4-7) written by the epilogue warps of both CTAs ----
+        auto mma_pair = [&](uint32_t d, uint64_t a_hi, uint64_t a_lo, uint32_t& acc) {
+          const uint32_t s = wi % WS;                                   // W_hi tile: with A_hi and A_lo
+          ok = ok && mbar_wait(&full[s], (wi / WS) & 1, wd, 215);
+          if (!ok) return;
+          tc_fence_after();
+          const uint64_t w = umma_desc_sw128(smem_u32(wring + s * kUnitBytes));
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            umma_f16<G>(d, a_hi + 2 * k4, w + 2 * k4, idesc, acc);
+            acc = 1;
+          }
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) umma_f16<G>(d, a_lo + 2 * k4, w + 2 * k4, idesc, acc);
+          umma_commit<G>(&empty[s], pair_mask);
+          ++wi;
+          mma_tile(d, a_hi, acc, 215);                                  // W_lo tile: with A_hi
+        };
+        wait_epi(&tempty[0], 1, 211);                                   // residual epilogue of the last layer: F0 drained
+        wait_epi(&tempty[1], p.nl & 1, 212);                            // skip sum -> S16 tiles in shared memory, F1 drained
+        uint32_t acch = 0;
+        for (int kb = 0; kb < 4 && ok; ++kb)                            // H1 = S16 . W_skip^T -> F0
+          mma_pair(tmem_base, umma_desc_sw128(smem_u32(aslot(kb))), umma_desc_sw128(smem_u32(aslot(4 + kb))), acch);
+        if (ok) umma_commit<G>(&tfull[0], pair_mask);
+        wait_epi(&tempty[0], 0, 213);                                   // h = relu(H1 + b) tiles written, F0 drained
+        acch = 0;
+        for (int kb = 0; kb < 4 && ok; ++kb)                            // H2 = h . W_out^T -> F1 (eps in columns [0, M))
+          mma_pair(dF1, umma_desc_sw128(smem_u32(aslot(kb))), umma_desc_sw128(smem_u32(aslot(4 + kb))), acch);
+        if (ok) umma_commit<G>(&tfull[1], pair_mask);
+        if (p.head_flags & TC_INPROJ) {
+          wait_epi(&tempty[1], (p.nl + 1) & 1, 214);                    // sampler update done: x_in tiles written, F1 drained
+          acch = 0;
+          for (int kb = 0; kb < 2 && ok; ++kb)                          // I = x_in . W_in^T -> F0
+            mma_pair(tmem_base, umma_desc_sw128(smem_u32(aslot(kb))), umma_desc_sw128(smem_u32(aslot(4 + kb))), acch);
+          if (ok) umma_commit<G>(&tfull[0], pair_mask);
+        }
+        DSX_STRACE(1, 251);
+      }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_HIGH));
@@ -650,24 +741,218 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
           *reinterpret_cast<uint4*>(aslot(4 + (ch >> 6)) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sdone);
-      if (p.nl == p.L && warp == 4 && lane == 0) {      // one thread stores the 2 x 4 tiles (rows beyond T are clipped)
-        if (mbar_wait(sdone, 0, wd, 306)) {
-          for (int pl = 0; pl < 2; ++pl)
-            for (int kb = 0; kb < 4; ++kb) tma_store_3d(&p.tm_s16[pl], aslot(pl * 4 + kb), kb * 64, t0, bq);
-          bulk_commit_group();
-          bulk_wait_group0();
-        }
-      }
       if (row_valid && p.taps) {
 #pragma unroll
         for (int i = 0; i < NCH / 4; ++i)
           *reinterpret_cast<float4*>(p.X + grow + i * 4) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
       }
+      if (p.head_flags) {
+        release(&tempty[1]);                          // S16 tiles -> the head GEMM of this launch
+      } else {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sdone);
+        if (p.nl == p.L && warp == 4 && lane == 0) {    // one thread stores the 2 x 4 tiles (rows beyond T are clipped)
+          if (mbar_wait(sdone, 0, wd, 306)) {
+            for (int pl = 0; pl < 2; ++pl)
+              for (int kb = 0; kb < 4; ++kb) tma_store_3d(&p.tm_s16[pl], aslot(pl * 4 + kb), kb * 64, t0, bq);
+            bulk_commit_group();
+            bulk_wait_group0();
+          }
+        }
+      }
     }
     if (tracer) DSX_STRACE(2, 250);
+
+    if (p.head_flags && ok) {
+      // ================================ fused head ================================
+      // ---- epi-H: h = relu(H1 + b_skip_projection) -> fp16 hi / lo tiles (A operand of H2) ----
+      __syncwarp();
+      if (lane < NCH / 4) *reinterpret_cast<float4*>(tb + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.bs + nbase) + lane);
+      __syncwarp();
+      ok = wait_acc(&tfull[0], 0, 311);
+      if (ok) {
+        const float4* b4 = reinterpret_cast<const float4*>(tb);
+        uint32_t o[2][16];
+        tmem_ld_32x16(tmem_base + tlane + cbase, o[0]);
+#pragma unroll
+        for (int pc = 0; pc < NCH / 16; ++pc) {
+          tmem_ld_wait();
+          if (pc + 1 < NCH / 16) tmem_ld_32x16(tmem_base + tlane + cbase + (pc + 1) * 16, o[(pc + 1) & 1]);
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = c2 * 8 + e * 4, col = pc * 16 + i;
+              const float4 bb = b4[col >> 2];
+              const float a0 = fmaxf(__uint_as_float(o[pc & 1][i]) + bb.x, 0.f), a1 = fmaxf(__uint_as_float(o[pc & 1][i + 1]) + bb.y, 0.f);
+              const float a2 = fmaxf(__uint_as_float(o[pc & 1][i + 2]) + bb.z, 0.f), a3 = fmaxf(__uint_as_float(o[pc & 1][i + 3]) + bb.w, 0.f);
+              const __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
+              const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+              hi[2 * e] = h2_bits(h0);
+              hi[2 * e + 1] = h2_bits(h1);
+              lo[2 * e] = h2_bits(__floats2half2_rn(a0 - f0.x, a1 - f0.y));
+              lo[2 * e + 1] = h2_bits(__floats2half2_rn(a2 - f1.x, a3 - f1.y));
+            }
+            const int ch = nbase + pc * 16 + c2 * 8;
+            const int off = r * 128 + ((((ch & 63) >> 3) ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(aslot(ch >> 6) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(aslot(4 + (ch >> 6)) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        release(&tempty[0]);
+      }
+      if (tracer) DSX_STRACE(2, 251);
+
+      // ---- mel phase: eps = H2 + b, sampler update of the mel state (thread = frame: coalesced in the reference's [B,1,M,T]
+      //      layout), x_in operand of the input projection.  Bins are split over the warps that hold the row: R = 128: two
+      //      (40 + 40); R = 64: four (the upper 128 accumulator columns are a copy): 24 + 16 + 24 + 16 ----
+      if (ok) ok = wait_acc(&tfull[1], static_cast<uint32_t>((p.nl + 1) & 1), 312);
+      if (ok) {
+        const int part = (R == 128) ? wh : (quad >> 1) * 2 + wh;
+        const int m_lo = (R == 128) ? part * 40 : (part >> 1) * 40 + (part & 1) * 24;
+        const int m_hi = (R == 128) ? m_lo + 40 : m_lo + ((part & 1) ? 16 : 24);
+        const int t = t0 + r;
+        const bool do_in = (p.head_flags & TC_INPROJ) != 0;
+        const bool need_z = (p.head_flags & TC_UPDATE) && p.c.sigma != 0.f;
+        const size_t xrow = static_cast<size_t>(tile_valid ? b : 0) * p.xs.b + static_cast<size_t>(t) * p.xs.t;
+#pragma unroll 1
+        for (int m0 = m_lo; m0 < m_hi; m0 += 8) {
+          uint32_t e8[8];
+          tmem_ld_32x8(tmem_base + tlane + Cfg::F1_COL + m0, e8);
+          float xv[8], zn[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            zn[i] = 0.f;
+            xv[i] = row_valid ? p.xmel[xrow + static_cast<size_t>(m0 + i) * p.xs.c] : 0.f;
+          }
+          if (need_z && row_valid) {
+            if (p.noise) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) zn[i] = p.noise[(static_cast<size_t>(b) * p.M + m0 + i) * p.T + t];
+            } else {
+#pragma unroll
+              for (int i4 = 0; i4 < 2; ++i4) {
+                const float4 z4 = philox_normal4(p.seed, p.offset, mel_noise_block(b + p.b_off, m0 + i4 * 4, t, p.M, p.T));
+                zn[i4 * 4] = z4.x; zn[i4 * 4 + 1] = z4.y; zn[i4 * 4 + 2] = z4.z; zn[i4 * 4 + 3] = z4.w;
+              }
+            }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = m0 + i;
+            const float ev = __uint_as_float(e8[i]) + __ldg(p.bf + m);
+            const size_t ei = (static_cast<size_t>(tile_valid ? b : 0) * p.M + m) * p.T + t;
+            if ((p.head_flags & TC_WRITE_EPS) && row_valid) p.eps_out[ei] = ev;
+            if (p.head_flags & TC_UPDATE) {                   // p_sample, the reference's fp32 operation order
+              float xr = __fsub_rn(__fmul_rn(p.c.A, xv[i]), __fmul_rn(p.c.Bc, ev));
+              xr = fminf(fmaxf(xr, -1.f), 1.f);
+              const float mean = __fadd_rn(__fmul_rn(p.c.c1, xr), __fmul_rn(p.c.c2, xv[i]));
+              xv[i] = __fadd_rn(mean, __fmul_rn(p.c.sigma, zn[i]));
+              if (row_valid) p.xmel[xrow + static_cast<size_t>(m) * p.xs.c] = xv[i];
+            }
+            if ((p.head_flags & TC_PLMS) && row_valid) {      // linear multistep combination + get_x_pred (k_plms_update)
+              float comb = __fmul_rn(p.pl.c.w0, ev);
+              if (p.pl.h1) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w1, p.pl.h1[ei]));
+              if (p.pl.h2) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w2, p.pl.h2[ei]));
+              if (p.pl.h3) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w3, p.pl.h3[ei]));
+              const float ep = __fdiv_rn(comb, p.pl.c.denom);
+              const float inner = __fsub_rn(__fmul_rn(p.pl.c.kx, xv[i]), __fmul_rn(p.pl.c.ke, ep));
+              xv[i] = __fadd_rn(xv[i], __fmul_rn(p.pl.c.a_diff, inner));
+              if (p.pl.eps_store) p.pl.eps_store[ei] = ev;
+              if (p.pl.x_out) p.pl.x_out[ei] = xv[i];
+              else p.xmel[xrow + static_cast<size_t>(m) * p.xs.c] = xv[i];
+            }
+          }
+          if (do_in) {                                        // 8 bins = one 16-byte chunk of row r in k-block m0 >> 6
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a0 = row_valid ? xv[2 * e] : 0.f, a1 = row_valid ? xv[2 * e + 1] : 0.f;
+              const __half2 hh = __floats2half2_rn(a0, a1);
+              const float2 hf = __half22float2(hh);
+              hi[e] = h2_bits(hh);
+              lo[e] = h2_bits(__floats2half2_rn(a0 - hf.x, a1 - hf.y));
+            }
+            const int off = r * 128 + ((((m0 & 63) >> 3) ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(aslot(m0 >> 6) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(aslot(4 + (m0 >> 6)) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        if (do_in) {
+          if (m_hi == p.M) {                                  // the K padding (bins M .. 127 = chunks 2 .. 7 of k-block 1)
+#pragma unroll
+            for (int c = 2; c < 8; ++c) {
+              const int off = r * 128 + ((c ^ (r & 7)) << 4);
+              *reinterpret_cast<uint4*>(aslot(1) + off) = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(aslot(5) + off) = make_uint4(0, 0, 0, 0);
+            }
+          }
+          release(&tempty[1]);
+        }
+      }
+      if (tracer) DSX_STRACE(2, 252);
+
+      // ---- epi-I: x0 = relu(I + b_in) (fp32) and y0 = fp16(x0 + d_0(next step)) as swizzled tiles over the idle W / y / z areas,
+      //      stored by TMA to X and to Y buffer 0: the entry state of the next evaluation's launch ----
+      if (ok && (p.head_flags & TC_INPROJ)) {
+        __syncwarp();
+        if (lane < NCH / 4) {
+          *reinterpret_cast<float4*>(tb + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.bin + nbase) + lane);
+          *reinterpret_cast<float4*>(tb + NCH + lane * 4) =
+              __ldg(reinterpret_cast<const float4*>(p.d0 + static_cast<size_t>(tile_valid ? b : 0) * p.d0_row_stride + nbase) + lane);
+        }
+        __syncwarp();
+        ok = wait_acc(&tfull[0], 1, 313);
+        if (ok) {
+          const float4* b4 = reinterpret_cast<const float4*>(tb);
+          const float4* d4 = reinterpret_cast<const float4*>(tb + NCH);
+          uint8_t* const xt = wring;                          // 8 tiles of [R rows][32 fp32], then 4 tiles of [R rows][64 fp16]
+          uint8_t* const yt = wring + 8 * UNIT;
+          uint32_t o[2][16];
+          tmem_ld_32x16(tmem_base + tlane + cbase, o[0]);
+#pragma unroll
+          for (int pc = 0; pc < NCH / 16; ++pc) {
+            tmem_ld_wait();
+            if (pc + 1 < NCH / 16) tmem_ld_32x16(tmem_base + tlane + cbase + (pc + 1) * 16, o[(pc + 1) & 1]);
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+              uint32_t hy[4];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int i = c2 * 8 + e * 4, col = pc * 16 + i;
+                const float4 bb = b4[col >> 2], dn = d4[col >> 2];
+                float4 v;
+                v.x = fmaxf(__uint_as_float(o[pc & 1][i]) + bb.x, 0.f);
+                v.y = fmaxf(__uint_as_float(o[pc & 1][i + 1]) + bb.y, 0.f);
+                v.z = fmaxf(__uint_as_float(o[pc & 1][i + 2]) + bb.z, 0.f);
+                v.w = fmaxf(__uint_as_float(o[pc & 1][i + 3]) + bb.w, 0.f);
+                const int ch = nbase + col;                    // 4 channels = one 16-byte chunk of the fp32 tile ch >> 5
+                *reinterpret_cast<float4*>(xt + (ch >> 5) * UNIT + r * 128 + ((((ch & 31) >> 2) ^ (r & 7)) << 4)) = v;
+                hy[2 * e] = h2_bits(__floats2half2_rn(v.x + dn.x, v.y + dn.y));
+                hy[2 * e + 1] = h2_bits(__floats2half2_rn(v.z + dn.z, v.w + dn.w));
+              }
+              const int ch = nbase + pc * 16 + c2 * 8;
+              *reinterpret_cast<uint4*>(yt + (ch >> 6) * UNIT + r * 128 + ((((ch & 63) >> 3) ^ (r & 7)) << 4)) = make_uint4(hy[0], hy[1], hy[2], hy[3]);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdone);
+          if (warp == 4 && lane == 0) {
+            if (mbar_wait(sdone, 0, wd, 314)) {
+              for (int k = 0; k < 8; ++k) tma_store_3d(&p.tm_xst, xt + k * UNIT, k * 32, t0, bq);
+              for (int k = 0; k < 4; ++k) tma_store_3d(&p.tm_y0st, yt + k * UNIT, k * 64, t0, bq);
+              bulk_commit_group();
+              bulk_wait_group0();
+            }
+          }
+        }
+      }
+      if (tracer) DSX_STRACE(2, 253);
+    }
   }
 
   // ---- teardown ----
@@ -892,7 +1177,7 @@ static int launch_stack_t(dsx_handle* h, TcStackParams& prm, const Geom& g, cuda
 }
 
 // Layers [0, nl) of one evaluation (table row row0, weight set `wset`), one persistent launch per group of utterances.
-int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_b, int wset, cudaStream_t s) {
+int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_b, int wset, cudaStream_t s, const HeadArgs* head) {
   const ModelDev& m = h->m;
   const bool x2 = (h->precision == DSX_PREC_FP16X2);
   const bool sr = (h->precision == DSX_PREC_FP16S);
@@ -927,6 +1212,28 @@ int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_
   prm.status = h->status_dev;
   prm.budget_ns = 4000000000ull;
   prm.trace = h->trace_dev;
+  if (head && head->flags) {
+    DSX_CHECK(nl == m.L, DSX_E_INVALID, "the fused head needs the whole stack");
+    prm.head_flags = head->flags | TC_HEAD;
+    prm.tm_wh = h->tm_whead;
+    prm.tm_xst = h->tm_xst[ri];
+    prm.tm_y0st = h->tm_y0st[ri];
+    prm.xmel = head->x;
+    prm.xs = head->xs;
+    prm.eps_out = head->eps;
+    prm.noise = head->noise;
+    prm.seed = head->seed;
+    prm.offset = head->offset;
+    prm.b_off = h->batch_offset;
+    prm.c = head->c;
+    if (head->plms) prm.pl = *head->plms;
+    prm.bs = m.skip_b;
+    prm.bf = m.fin_b;
+    prm.bin = m.in_b;
+    prm.d0 = h->ws.DTAB + static_cast<size_t>(head->next_row0) * m.L * kC;
+    prm.d0_row_stride = head->row_per_b * m.L * kC;
+    prm.M = m.M;
+  }
   // halo packets: 32 KB per tile, zeroed once (sequence numbers start at 1 and only grow, so packets left behind by earlier
   // evaluations, other geometries or an aborted launch can never be mistaken for the current layer's)
   const size_t ll_bytes = static_cast<size_t>(g.B * (g.Tp / 64) + 2) * 4 * 512 * sizeof(uint4);

@@ -1586,16 +1586,17 @@ int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_ro
   DSX_CHECK(r == CUDA_SUCCESS, DSX_E_CUDA, "cuTensorMapEncodeTiled(2D) failed: %d", static_cast<int>(r));
   return DSX_OK;
 }
-// [B][T (stride Tp)][ch] fp16, box = 64 channels x box_frames frames x 1
-static int make_map_act(CUtensorMap* m, const void* base, int ch, int T, int Tp, int B, int box_frames = kTile) {
+// [B][T (stride Tp)][ch] fp16 (or fp32), box = 128 bytes of channels x box_frames frames x 1
+static int make_map_act(CUtensorMap* m, const void* base, int ch, int T, int Tp, int B, int box_frames = kTile, bool f32 = false) {
   PFN_tmapEncodeTiled enc = get_encode();
   DSX_CHECK(enc, DSX_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const cuuint64_t es_bytes = f32 ? 4 : 2;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(ch), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ch) * 2, static_cast<cuuint64_t>(Tp) * ch * 2};
-  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_frames), 1};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ch) * es_bytes, static_cast<cuuint64_t>(Tp) * ch * es_bytes};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / es_bytes), static_cast<cuuint32_t>(box_frames), 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DSX_CHECK(r == CUDA_SUCCESS, DSX_E_CUDA, "cuTensorMapEncodeTiled(3D) failed: %d", static_cast<int>(r));
   return DSX_OK;
@@ -1621,6 +1622,8 @@ int tc_prepare_maps(dsx_handle* h, const Geom& g) {
     const int rows = ri == 0 ? 128 : 64;
     DSX_TRY(make_map_act(&h->tm_y0s[ri], h->ws.Y, kC, g.T, g.Tp, g.B, rows + 16));
     DSX_TRY(make_map_act(&h->tm_zs[ri], h->ws.Z, kC, g.T, g.Tp, h->m.L * g.B, rows));
+    DSX_TRY(make_map_act(&h->tm_y0st[ri], h->ws.Y, kC, g.T, g.Tp, g.B, rows));
+    DSX_TRY(make_map_act(&h->tm_xst[ri], h->ws.X, kC, g.T, g.Tp, g.B, rows, true));
     for (int pl = 0; pl < 2; ++pl)
       DSX_TRY(make_map_act(&h->tm_s16s[ri][pl], h->ws.S16 + static_cast<size_t>(pl) * plane, kC, g.T, g.Tp, g.B, rows));
   }

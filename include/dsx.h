@@ -207,6 +207,8 @@ enum {
   DSX_OPT_GATE_APPROX = 7,  /* stack kernel: gate sigmoid(g) * tanh(f) with tanh.approx.f32 (1) or with ex2 / rcp to ~2e-7 (0);
                                -1 (default) = 1: its 2^-11 relative error is below the fp16 rounding of the gate output that
                                follows (K = 100 golden loop: 3.3e-4 either way in FP16S, 1.5e-4 / 1.6e-4 in FP16X2) */
+  DSX_OPT_FUSED_HEAD = 9,   /* 1 (default): the skip / output projections, the sampler update and the next input projection run
+                               inside the stack kernel's launch (one kernel per diffusion step); 0: separate head kernel */
   DSX_OPT_STACK_ROWS = 8,   /* stack kernel: frames per CTA.  0 (default) = 64 whenever the whole batch then fits the machine at once
                                (small batches: twice the CTAs, about half the time per layer), else 128; 64 / 128 force it */
   DSX_OPT_BATCH_OFFSET = 6  /* global index of this call's utterance 0: the in-kernel Philox noise of utterance b is drawn for

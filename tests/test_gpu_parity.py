@@ -364,6 +364,36 @@ def test_small_batch_mode_golden_loop(dsx, prec):
     s.close()
 
 
+@pytest.mark.parametrize("prec,rows", [("fp16s", 0), ("fp16x2", 128), ("fp16x2", 64)])
+def test_fused_head_matches_separate_head_kernel(dsx, prec, rows):
+    """ONE launch per diffusion step (head projections, sampler update and next input projection inside the stack kernel,
+    DSX_OPT_FUSED_HEAD = 1, the default) against the two-launch form (k_tc_head): DDPM with Philox and with injected noise,
+    PLMS incl. its two-evaluation warm-up step, a single evaluation (eps), ragged shapes, both tile heights."""
+    from diffsinger_b200 import _capi
+    S = O.make_schedule(O.linear_beta_schedule(1000, 0.02))
+    outs = {}
+    for fused in (0, 1):
+        s, dev = make_sampler(dsx, 4, prec, S)
+        s.set_option(_capi.OPT_FUSED_HEAD, fused)
+        s.set_option(_capi.OPT_STACK_ROWS, rows)
+        res = []
+        for B, T in ((2, 333), (3, 128), (1, 1000)):
+            cond, xT = rs_normal(13 + B, (B, 256, T)).to(dev), rs_normal(14 + T, (B, 1, 80, T)).to(dev)
+            noise = rs_normal(15, (6, B, 1, 80, T)).to(dev)
+            l0 = s.info(_capi.INFO_KERNEL_LAUNCHES)
+            res.append(s.sample_ddpm(xT, cond, 1000, 6, seed=5).cpu())
+            per_step = (s.info(_capi.INFO_KERNEL_LAUNCHES) - l0 - 5) / 6.0      # minus embed table (2), cond pack + projection (2), first in-projection
+            assert per_step == (1 if fused else 2), per_step
+            res.append(s.sample_ddpm(xT, cond, 6, 6, noise=noise).cpu())        # ends at t = 0
+            res.append(s.sample_plms(xT, cond, 300, 40).cpu())
+            res.append(s.diffnet_forward(xT, torch.full((B,), 17, dtype=torch.long, device=dev), cond).cpu())
+        outs[fused] = res
+        s.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.isfinite(b).all()
+        assert (a - b).abs().max() <= 2e-5 * max(1.0, a.abs().max().item()), (a - b).abs().max()
+
+
 @pytest.mark.parametrize("prec", ["fp16x2", "fp16x3"])
 def test_tuning_knobs_do_not_change_results(dsx, prec):
     """The L2 prefetch of the hoisted conditioner projection is a scheduling knob only: a DDPM loop is bit-identical with
