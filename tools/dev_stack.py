@@ -256,6 +256,8 @@ def trace():
             print(l, [int(a[0, 0, l * 4 + k] - base) for k in range(4)])
         print("end of skip GEMM issue (MMA thread)", int(a[0, 1, 250] - base), "| exit epilogue: enter", int(a[0, 2, 248] - base),
               "skip sum ready", int(a[0, 2, 249] - base), "done", int(a[0, 2, 250] - base), "| layer 19 G2 issued", int(a[0, 1, 19 * 8 + 6] - base))
+        print("fused head: MMA issue end", int(a[0, 1, 251] - base), "| epilogue: h tiles", int(a[0, 2, 251] - base), "mel phase",
+              int(a[0, 2, 252] - base), "x0 / y0 stored", int(a[0, 2, 253] - base))
         per_layer = (a[0, 1, 19 * 8] - a[0, 1, 1 * 8]) / 18.0
         print(f"{prec}: cycles per layer (MMA thread, layers 1..19): {per_layer:.0f}")
         s.close()
