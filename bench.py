@@ -109,26 +109,80 @@ def schedule_for(cfg):
 
 
 class ClockSampler:
-    """Samples SM clock / throttle reasons DURING the timed region with an nvidia-smi subprocess (the recipe's
-    clocks line); a separate process so the sampling never contends with the launching thread."""
+    """SM clock / throttle reasons / board power DURING the timed region: an NVML polling thread (5 ms period; the NVML
+    calls release the GIL and the timed loop only enqueues launches and waits), every sample time-stamped so that only
+    those between mark_start() and mark_end() count.  Falls back to an `nvidia-smi -lms` subprocess (the recipe's clocks
+    line) when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.path = f"/tmp/dsx_clocks_{os.getpid()}_{index}.csv"
-        self.proc = None
+        import threading
+        self.samples, self.t0, self.t1, self.mx = [], None, None, None
+        self.stop = threading.Event()
+        self.thread, self.proc = None, None
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                         stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
+            self.path = f"/tmp/dsx_clocks_{os.getpid()}_{index}.csv"
+            try:
+                self.f = open(self.path, "w")
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                              "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                             stderr=subprocess.DEVNULL)
+            except Exception:
+                self.proc = None
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop.is_set():
+            try:
+                clk = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                bits = int(reasons_fn(h))
+                try:
+                    watts = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    watts = None
+                self.samples.append((time.time(), clk, bits, watts))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
-        time.sleep(0.3)          # let the first samples land
+        if self.thread is None:
+            time.sleep(0.3)          # let the first nvidia-smi samples land
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def finish(self):
+        if self.t1 is None:
+            self.t1 = time.time()
+        if self.thread is not None:
+            self.stop.set()
+            self.thread.join(timeout=2)
+            inside = [x for x in self.samples if self.t0 <= x[0] <= self.t1] or self.samples
+            if not inside:
+                return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0}
+            bits = 0
+            for x in inside:
+                bits |= x[2]
+            watts = [x[3] for x in inside if x[3] is not None]
+            return {"sm_mhz": float(np.median([x[1] for x in inside])), "sm_min_mhz": float(min(x[1] for x in inside)),
+                    "sm_max_mhz": self.mx, "reasons": sorted(n for b, n in self.BITS.items() if bits & b),
+                    "samples": len(inside), "power_w": float(np.median(watts)) if watts else None,
+                    "how": "NVML, 5 ms period, samples inside the timed region only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         time.sleep(0.15)
@@ -159,7 +213,7 @@ class ClockSampler:
         # samples under load only (idle samples sit at the floor clock)
         load = [c for c in clk if c > 0.5 * (mx or 1)] or clk
         return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(clk)}
+                "samples": len(clk), "how": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -340,6 +394,8 @@ def timed_steps(arm, steps, warmup, world, dev, flush, gather_total=None, clocks
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
     l1 = arm.s.info(arm.capi.INFO_KERNEL_LAUNCHES)
+    if cs:
+        cs.mark_end()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

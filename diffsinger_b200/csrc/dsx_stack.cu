@@ -706,13 +706,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         *reinterpret_cast<float4*>(tb + lane * 4) =
             __ldg(reinterpret_cast<const float4*>(p.bskip + static_cast<size_t>(p.nl - 1) * kC + nbase) + lane);
       __syncwarp();
+      // (the exit / head epilogues run once per launch from a cold instruction cache -- ncu: no_instruction is their top
+      //  stall, and fully unrolled they took 3 x as long as the same work inside the layer loop: rolled loops, compact bodies)
       const float4* bs4 = reinterpret_cast<const float4*>(tb);
-      uint32_t o[2][16];
-      tmem_ld_32x16(tmem_base + tlane + Cfg::F1_COL + cbase, o[0]);
-#pragma unroll
+#pragma unroll 1
       for (int pc = 0; pc < NCH / 16; ++pc) {
+        uint32_t o[16];
+        tmem_ld_32x16(tmem_base + tlane + Cfg::F1_COL + cbase + pc * 16, o);
         tmem_ld_wait();
-        if (pc + 1 < NCH / 16) tmem_ld_32x16(tmem_base + tlane + Cfg::F1_COL + cbase + (pc + 1) * 16, o[(pc + 1) & 1]);
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           uint32_t hi[4], lo[4];
@@ -721,10 +722,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
             const int i = c2 * 8 + e * 4, col = pc * 16 + i;
             const float4 bb = bs4[col >> 2];
             float4 v;
-            v.x = __uint_as_float(o[pc & 1][i]) + bb.x;
-            v.y = __uint_as_float(o[pc & 1][i + 1]) + bb.y;
-            v.z = __uint_as_float(o[pc & 1][i + 2]) + bb.z;
-            v.w = __uint_as_float(o[pc & 1][i + 3]) + bb.w;
+            v.x = __uint_as_float(o[i]) + bb.x;
+            v.y = __uint_as_float(o[i + 1]) + bb.y;
+            v.z = __uint_as_float(o[i + 2]) + bb.z;
+            v.w = __uint_as_float(o[i + 3]) + bb.w;
             if (p.taps && row_valid) *reinterpret_cast<float4*>(p.SKIP + grow + col) = v;
             const float sa = v.x * p.inv_sqrt_l, sb = v.y * p.inv_sqrt_l, sc = v.z * p.inv_sqrt_l, sd = v.w * p.inv_sqrt_l;
             const __half2 h0 = __floats2half2_rn(sa, sb), h1 = __floats2half2_rn(sc, sd);
@@ -773,12 +774,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       ok = wait_acc(&tfull[0], 0, 311);
       if (ok) {
         const float4* b4 = reinterpret_cast<const float4*>(tb);
-        uint32_t o[2][16];
-        tmem_ld_32x16(tmem_base + tlane + cbase, o[0]);
-#pragma unroll
+#pragma unroll 1
         for (int pc = 0; pc < NCH / 16; ++pc) {
+          uint32_t o[16];
+          tmem_ld_32x16(tmem_base + tlane + cbase + pc * 16, o);
           tmem_ld_wait();
-          if (pc + 1 < NCH / 16) tmem_ld_32x16(tmem_base + tlane + cbase + (pc + 1) * 16, o[(pc + 1) & 1]);
 #pragma unroll
           for (int c2 = 0; c2 < 2; ++c2) {
             uint32_t hi[4], lo[4];
@@ -786,8 +786,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
             for (int e = 0; e < 2; ++e) {
               const int i = c2 * 8 + e * 4, col = pc * 16 + i;
               const float4 bb = b4[col >> 2];
-              const float a0 = fmaxf(__uint_as_float(o[pc & 1][i]) + bb.x, 0.f), a1 = fmaxf(__uint_as_float(o[pc & 1][i + 1]) + bb.y, 0.f);
-              const float a2 = fmaxf(__uint_as_float(o[pc & 1][i + 2]) + bb.z, 0.f), a3 = fmaxf(__uint_as_float(o[pc & 1][i + 3]) + bb.w, 0.f);
+              const float a0 = fmaxf(__uint_as_float(o[i]) + bb.x, 0.f), a1 = fmaxf(__uint_as_float(o[i + 1]) + bb.y, 0.f);
+              const float a2 = fmaxf(__uint_as_float(o[i + 2]) + bb.z, 0.f), a3 = fmaxf(__uint_as_float(o[i + 3]) + bb.w, 0.f);
               const __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
               const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
               hi[2 * e] = h2_bits(h0);
@@ -817,34 +817,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         const bool do_in = (p.head_flags & TC_INPROJ) != 0;
         const bool need_z = (p.head_flags & TC_UPDATE) && p.c.sigma != 0.f;
         const size_t xrow = static_cast<size_t>(tile_valid ? b : 0) * p.xs.b + static_cast<size_t>(t) * p.xs.t;
-#pragma unroll 1
-        for (int m0 = m_lo; m0 < m_hi; m0 += 8) {
-          uint32_t e8[8];
-          tmem_ld_32x8(tmem_base + tlane + Cfg::F1_COL + m0, e8);
-          float xv[8], zn[8];
+        const size_t erow = static_cast<size_t>(tile_valid ? b : 0) * p.M * p.T + t;
+        float xn[4];                                          // the next iteration's mel state, loaded one iteration ahead
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) xn[i] = row_valid ? p.xmel[xrow + static_cast<size_t>(m_lo + i) * p.xs.c] : 0.f;
+#pragma unroll 1
+        for (int m0 = m_lo; m0 < m_hi; m0 += 4) {
+          uint32_t e4[4];
+          tmem_ld_32x4(tmem_base + tlane + Cfg::F1_COL + m0, e4);
+          float xv[4], zn[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
             zn[i] = 0.f;
-            xv[i] = row_valid ? p.xmel[xrow + static_cast<size_t>(m0 + i) * p.xs.c] : 0.f;
+            xv[i] = xn[i];
+          }
+          if (m0 + 4 < m_hi) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xn[i] = row_valid ? p.xmel[xrow + static_cast<size_t>(m0 + 4 + i) * p.xs.c] : 0.f;
           }
           if (need_z && row_valid) {
             if (p.noise) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) zn[i] = p.noise[(static_cast<size_t>(b) * p.M + m0 + i) * p.T + t];
+              for (int i = 0; i < 4; ++i) zn[i] = p.noise[erow + static_cast<size_t>(m0 + i) * p.T];
             } else {
-#pragma unroll
-              for (int i4 = 0; i4 < 2; ++i4) {
-                const float4 z4 = philox_normal4(p.seed, p.offset, mel_noise_block(b + p.b_off, m0 + i4 * 4, t, p.M, p.T));
-                zn[i4 * 4] = z4.x; zn[i4 * 4 + 1] = z4.y; zn[i4 * 4 + 2] = z4.z; zn[i4 * 4 + 3] = z4.w;
-              }
+              const float4 z4 = philox_normal4(p.seed, p.offset, mel_noise_block(b + p.b_off, m0, t, p.M, p.T));
+              zn[0] = z4.x; zn[1] = z4.y; zn[2] = z4.z; zn[3] = z4.w;
             }
           }
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             const int m = m0 + i;
-            const float ev = __uint_as_float(e8[i]) + __ldg(p.bf + m);
-            const size_t ei = (static_cast<size_t>(tile_valid ? b : 0) * p.M + m) * p.T + t;
+            const float ev = __uint_as_float(e4[i]) + __ldg(p.bf + m);
+            const size_t ei = erow + static_cast<size_t>(m) * p.T;
             if ((p.head_flags & TC_WRITE_EPS) && row_valid) p.eps_out[ei] = ev;
             if (p.head_flags & TC_UPDATE) {                   // p_sample, the reference's fp32 operation order
               float xr = __fsub_rn(__fmul_rn(p.c.A, xv[i]), __fmul_rn(p.c.Bc, ev));
@@ -866,19 +871,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
               else p.xmel[xrow + static_cast<size_t>(m) * p.xs.c] = xv[i];
             }
           }
-          if (do_in) {                                        // 8 bins = one 16-byte chunk of row r in k-block m0 >> 6
-            uint32_t hi[4], lo[4];
+          if (do_in) {                                        // 4 bins = half a 16-byte chunk of row r in k-block m0 >> 6
+            uint32_t hi[2], lo[2];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < 2; ++e) {
               const float a0 = row_valid ? xv[2 * e] : 0.f, a1 = row_valid ? xv[2 * e + 1] : 0.f;
               const __half2 hh = __floats2half2_rn(a0, a1);
               const float2 hf = __half22float2(hh);
               hi[e] = h2_bits(hh);
               lo[e] = h2_bits(__floats2half2_rn(a0 - hf.x, a1 - hf.y));
             }
-            const int off = r * 128 + ((((m0 & 63) >> 3) ^ (r & 7)) << 4);
-            *reinterpret_cast<uint4*>(aslot(m0 >> 6) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(aslot(4 + (m0 >> 6)) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            const int off = r * 128 + ((((m0 & 63) >> 3) ^ (r & 7)) << 4) + (m0 & 4) * 2;
+            *reinterpret_cast<uint2*>(aslot(m0 >> 6) + off) = make_uint2(hi[0], hi[1]);
+            *reinterpret_cast<uint2*>(aslot(4 + (m0 >> 6)) + off) = make_uint2(lo[0], lo[1]);
           }
         }
         if (do_in) {
@@ -911,12 +916,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
           const float4* d4 = reinterpret_cast<const float4*>(tb + NCH);
           uint8_t* const xt = wring;                          // 8 tiles of [R rows][32 fp32], then 4 tiles of [R rows][64 fp16]
           uint8_t* const yt = wring + 8 * UNIT;
-          uint32_t o[2][16];
-          tmem_ld_32x16(tmem_base + tlane + cbase, o[0]);
-#pragma unroll
+#pragma unroll 1
           for (int pc = 0; pc < NCH / 16; ++pc) {
+            uint32_t o[16];
+            tmem_ld_32x16(tmem_base + tlane + cbase + pc * 16, o);
             tmem_ld_wait();
-            if (pc + 1 < NCH / 16) tmem_ld_32x16(tmem_base + tlane + cbase + (pc + 1) * 16, o[(pc + 1) & 1]);
 #pragma unroll
             for (int c2 = 0; c2 < 2; ++c2) {
               uint32_t hy[4];
@@ -925,10 +929,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
                 const int i = c2 * 8 + e * 4, col = pc * 16 + i;
                 const float4 bb = b4[col >> 2], dn = d4[col >> 2];
                 float4 v;
-                v.x = fmaxf(__uint_as_float(o[pc & 1][i]) + bb.x, 0.f);
-                v.y = fmaxf(__uint_as_float(o[pc & 1][i + 1]) + bb.y, 0.f);
-                v.z = fmaxf(__uint_as_float(o[pc & 1][i + 2]) + bb.z, 0.f);
-                v.w = fmaxf(__uint_as_float(o[pc & 1][i + 3]) + bb.w, 0.f);
+                v.x = fmaxf(__uint_as_float(o[i]) + bb.x, 0.f);
+                v.y = fmaxf(__uint_as_float(o[i + 1]) + bb.y, 0.f);
+                v.z = fmaxf(__uint_as_float(o[i + 2]) + bb.z, 0.f);
+                v.w = fmaxf(__uint_as_float(o[i + 3]) + bb.w, 0.f);
                 const int ch = nbase + col;                    // 4 channels = one 16-byte chunk of the fp32 tile ch >> 5
                 *reinterpret_cast<float4*>(xt + (ch >> 5) * UNIT + r * 128 + ((((ch & 31) >> 2) ^ (r & 7)) << 4)) = v;
                 hy[2 * e] = h2_bits(__floats2half2_rn(v.x + dn.x, v.y + dn.y));
@@ -946,7 +950,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
               for (int k = 0; k < 8; ++k) tma_store_3d(&p.tm_xst, xt + k * UNIT, k * 32, t0, bq);
               for (int k = 0; k < 4; ++k) tma_store_3d(&p.tm_y0st, yt + k * UNIT, k * 64, t0, bq);
               bulk_commit_group();
-              bulk_wait_group0();
+              bulk_wait_group_read0();          // the shared-memory source must outlive the copies; the writes complete with the grid
             }
           }
         }
