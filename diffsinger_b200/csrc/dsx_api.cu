@@ -718,10 +718,10 @@ int dsx_debug_read(dsx_handle* h, int which, float* out, int B, int T, void* str
 int dsx_debug_trace(dsx_handle* h, int enable, int64_t* out_host) {
   DSX_CHECK(h, DSX_E_INVALID, "null handle");
   DSX_CUDA(cudaSetDevice(h->device));
-  const size_t bytes = 6 * 256 * sizeof(long long);
+  const size_t bytes = 10 * 256 * sizeof(long long);       // [2][3][256] role stamps, then [256][4] per-CTA entry / exit
   if (out_host && h->trace_dev) {
     DSX_CUDA(cudaDeviceSynchronize());
-    DSX_CUDA(cudaMemcpy(out_host, h->trace_dev, bytes, cudaMemcpyDeviceToHost));
+    DSX_CUDA(cudaMemcpy(out_host, h->trace_dev, (enable == 2 ? 10 : 6) * 256 * sizeof(long long), cudaMemcpyDeviceToHost));
   }
   if (enable && !h->trace_dev) {
     DSX_CUDA(cudaMalloc(&h->trace_dev, bytes));

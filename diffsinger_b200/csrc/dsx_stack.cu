@@ -142,6 +142,10 @@ struct TcStackParams {
 template <int WP, int R>
 __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant__ TcStackParams p) {
   using Cfg = StackCfg<R>;
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 256) {      // debug timeline: per-CTA entry (wall clock ns, SM cycles)
+    p.trace[6 * 256 + blockIdx.x * 4] = static_cast<long long>(globaltimer_ns());
+    p.trace[6 * 256 + blockIdx.x * 4 + 1] = clock64();
+  }
   constexpr int G = kG;
   constexpr int WS = Cfg::WSLOTS;
   constexpr int AS = Cfg::ASLOTS;
@@ -967,6 +971,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<G>(tmem_base, 512);
+  }
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 256) {
+    p.trace[6 * 256 + blockIdx.x * 4 + 2] = static_cast<long long>(globaltimer_ns());
+    p.trace[6 * 256 + blockIdx.x * 4 + 3] = clock64();
   }
 }
 

@@ -221,7 +221,8 @@ enum {
 int dsx_debug_read(dsx_handle* h, int which, float* out, int B, int T, void* stream);
 /* Debug timeline of the residual-layer kernel: enable != 0 makes CTAs 0 and 1 of every following layer
  * launch record clock64 stamps ([2][3 roles: producer, MMA issuer, epilogue][256] int64); out_host (may be
- * NULL) receives the current buffer contents (6*256 int64) after synchronising the device. */
+ * NULL) receives the current buffer contents (6*256 int64) after synchronising the device.  enable == 2: out_host
+ * receives 10*256 int64, the extra [256][4] being per-CTA {globaltimer ns, clock64} at kernel entry and exit. */
 int dsx_debug_trace(dsx_handle* h, int enable, int64_t* out_host);
 /* Run only layers [0, n_layers) in the next dsx_diffnet_forward calls (<0: all). */
 int dsx_debug_set_layer_limit(dsx_handle* h, int n_layers);

@@ -238,11 +238,22 @@ def trace():
         s = make(1, prec, 1, O.make_schedule(O.linear_beta_schedule(100, 0.06)))
         xs = torch.randn(B, 1, 80, T, generator=gen).to(DEV)
         s.sample_ddpm(xs, cond, 100, 2, seed=1)          # the loop entry point: no debug taps, as in production
-        buf = (ctypes.c_int64 * (6 * 256))()
+        buf = (ctypes.c_int64 * (10 * 256))()
         _capi.check(_capi.lib.dsx_debug_trace(s._h, 1, None), "trace on")
         s.sample_ddpm(xs, cond, 100, 2, seed=1)
-        _capi.check(_capi.lib.dsx_debug_trace(s._h, 1, ctypes.cast(buf, ctypes.c_void_p)), "trace read")
-        a = np.array(buf[:], dtype=np.int64).reshape(2, 3, 256)
+        _capi.check(_capi.lib.dsx_debug_trace(s._h, 2, ctypes.cast(buf, ctypes.c_void_p)), "trace read")
+        full = np.array(buf[:], dtype=np.int64)
+        a = full[:6 * 256].reshape(2, 3, 256)
+        cta = full[6 * 256:].reshape(256, 4)
+        cta = cta[cta[:, 0] != 0]
+        if len(cta):
+            t_in, t_out = cta[:, 0], cta[:, 2]
+            cyc = cta[:, 3] - cta[:, 1]
+            ns = t_out - t_in
+            print(f"--- {prec}: {len(cta)} CTAs; wall ns: first entry -> last exit {int(t_out.max() - t_in.min())}, entry spread "
+                  f"{int(t_in.max() - t_in.min())}, exit spread {int(t_out.max() - t_out.min())}; per CTA ns median {int(np.median(ns))} "
+                  f"max {int(ns.max())}; cycles median {int(np.median(cyc))}; MHz inside the kernel {float(np.median(cyc / ns)) * 1e3:.0f}; "
+                  f"CTA 0: entry -> first G1 {int(a[0, 1, 0] - cta[0, 1])} cycles, x0 stored -> exit {int(cta[0, 3] - a[0, 2, 253])} cycles")
         out[prec] = a.tolist()
         base = a[0, 1, 0]
         print(f"--- {prec}: MMA thread (CTA 0) per layer: G1 start, centre taps issued, halo landed, G1 issued, G2 kb0 start, G2 kb2 start, G2 issued")

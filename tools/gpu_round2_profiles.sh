@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 evidence, one GPU call: bench lines of every BASELINE config + sweep, the reference arm, ncu launch lists and full
-# captures of the stack / head kernels.  Outputs land in gpurun_out/ (copied into profiles/ by hand).
+# captures of the fused stack kernel, its clock64 timeline, compute-sanitizer memcheck.  Outputs land in gpurun_out/ (copied into profiles/ by hand).
 mkdir -p gpurun_out
 P=${1:-fp16s}
 timeout 400 python bench.py --steps 5 --warmup 3 > gpurun_out/r02_bench_config2.json 2> gpurun_out/r02_bench_config2.err; echo "bench2 rc=$?"
@@ -13,7 +13,9 @@ for Q in fp16s fp16x2; do
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/r02_launches_$Q.csv python tools/ncu_target.py $Q 3 > /dev/null 2>&1
   timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_tc_stack -s 1 -c 1 -f -o gpurun_out/r02_ncu_stack_$Q python tools/ncu_target.py $Q 3 > gpurun_out/r02_ncu_stack_$Q.log 2>&1
 done
-timeout 600 ncu --set full --clock-control none -k regex:k_tc_head -s 2 -c 1 -f -o gpurun_out/r02_ncu_head_$P python tools/ncu_target.py $P 3 > gpurun_out/r02_ncu_head_$P.log 2>&1
+# (the head is part of k_tc_stack since the fusion: no separate head capture)
+timeout 300 python tools/dev_stack.py trace > gpurun_out/r02_stack_timeline.txt 2>&1
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/dev_stack.py quick > gpurun_out/r02_compute_sanitizer_memcheck.txt 2>&1; echo "memcheck rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r02_launches_config4_$P.csv python tools/ncu_target.py $P 3 4 > /dev/null 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > gpurun_out/r02_smi.txt
 ls -la gpurun_out | grep r02_
