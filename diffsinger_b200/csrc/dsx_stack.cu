@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
   constexpr int AS = Cfg::ASLOTS;
   constexpr int UNIT = Cfg::UNIT;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* wring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: keeps the address space visible to the compiler,
+  //  which otherwise emits generic LD / ST for every table load and tile store of the epilogues)
+  uint8_t* wring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* yslots = wring + Cfg::W_BYTES;
   uint8_t* zbuf = yslots + Cfg::Y_BYTES;
   float* tab = reinterpret_cast<float*>(zbuf + Cfg::Z_BYTES);
