@@ -580,17 +580,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float4 bg = cg[q % NB][e >> 1], bf = cf[q % NB][e >> 1];
-          const float g0 = __uint_as_float(g[2 * e]) + ((e & 1) ? bg.z : bg.x);
-          const float g1 = __uint_as_float(g[2 * e + 1]) + ((e & 1) ? bg.w : bg.y);
-          const float f0 = __uint_as_float(f[2 * e]) + ((e & 1) ? bf.z : bf.x);
-          const float f1 = __uint_as_float(f[2 * e + 1]) + ((e & 1) ? bf.w : bf.y);
+          const float2 gg = add2(make_float2(__uint_as_float(g[2 * e]), __uint_as_float(g[2 * e + 1])),
+                                 (e & 1) ? make_float2(bg.z, bg.w) : make_float2(bg.x, bg.y));
+          const float2 ff = add2(make_float2(__uint_as_float(f[2 * e]), __uint_as_float(f[2 * e + 1])),
+                                 (e & 1) ? make_float2(bf.z, bf.w) : make_float2(bf.x, bf.y));
           float z0, z1;
-          if (p.fast_act) {
-            z0 = sigmoid_fast(g0) * tanh_approx(f0);
-            z1 = sigmoid_fast(g1) * tanh_approx(f1);
+          if (p.fast_act) {                         // sigmoid_fast(g) * tanh_approx(f), two channels per instruction
+            const float2 hg = mul2(gg, make_float2(0.5f, 0.5f));
+            const float2 sg = fma2(make_float2(0.5f, 0.5f), make_float2(tanh_approx(hg.x), tanh_approx(hg.y)), make_float2(0.5f, 0.5f));
+            const float2 zz = mul2(sg, make_float2(tanh_approx(ff.x), tanh_approx(ff.y)));
+            z0 = zz.x;
+            z1 = zz.y;
           } else {
-            z0 = gate_acc(g0, f0);
-            z1 = gate_acc(g1, f1);
+            z0 = gate_acc(gg.x, ff.x);
+            z1 = gate_acc(gg.y, ff.y);
           }
           hz[e] = h2_bits(__floats2half2_rn(z0, z1));
         }
@@ -631,13 +634,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
             for (int e = 0; e < 2; ++e) {
               const int i = c2 * 8 + e * 4, col = pc * 16 + i;
               const float4 bias = bt[col >> 2], dn = dt[col >> 2];
-              const float x0 = (x[col] + (__uint_as_float(o[pc & 1][i]) + bias.x)) * 0.70710678118654752440f;
-              const float x1 = (x[col + 1] + (__uint_as_float(o[pc & 1][i + 1]) + bias.y)) * 0.70710678118654752440f;
-              const float x2 = (x[col + 2] + (__uint_as_float(o[pc & 1][i + 2]) + bias.z)) * 0.70710678118654752440f;
-              const float x3 = (x[col + 3] + (__uint_as_float(o[pc & 1][i + 3]) + bias.w)) * 0.70710678118654752440f;
-              x[col] = x0; x[col + 1] = x1; x[col + 2] = x2; x[col + 3] = x3;
-              hy[2 * e] = row_valid ? h2_bits(__floats2half2_rn(x0 + dn.x, x1 + dn.y)) : 0u;
-              hy[2 * e + 1] = row_valid ? h2_bits(__floats2half2_rn(x2 + dn.z, x3 + dn.w)) : 0u;
+              const float2 c2v = make_float2(0.70710678118654752440f, 0.70710678118654752440f);
+              const float2 xa = mul2(add2(make_float2(x[col], x[col + 1]),
+                                          add2(make_float2(__uint_as_float(o[pc & 1][i]), __uint_as_float(o[pc & 1][i + 1])),
+                                               make_float2(bias.x, bias.y))), c2v);
+              const float2 xb = mul2(add2(make_float2(x[col + 2], x[col + 3]),
+                                          add2(make_float2(__uint_as_float(o[pc & 1][i + 2]), __uint_as_float(o[pc & 1][i + 3])),
+                                               make_float2(bias.z, bias.w))), c2v);
+              x[col] = xa.x; x[col + 1] = xa.y; x[col + 2] = xb.x; x[col + 3] = xb.y;
+              const float2 ya = add2(xa, make_float2(dn.x, dn.y)), yb = add2(xb, make_float2(dn.z, dn.w));
+              hy[2 * e] = row_valid ? h2_bits(__floats2half2_rn(ya.x, ya.y)) : 0u;
+              hy[2 * e + 1] = row_valid ? h2_bits(__floats2half2_rn(yb.x, yb.y)) : 0u;
             }
             if (has_next) {
               // channel ch .. ch + 8 of row r: y k-block ch >> 6, 16-byte chunk (ch & 63) >> 3 of slot row 8 + r
