@@ -100,6 +100,7 @@ struct TcStackParams {
   int T, Tp, tiles_per_utt, B;   // tiles_per_utt: R-frame tiles per utterance (Tp / R)
   int tile0, tile_end;     // this launch covers tiles [tile0, tile_end) (whole utterances); CTA i -> tile tile0 + i
   int nl, L, cycle;        // layers [0, nl); dilation of layer l = 1 << (l % cycle)
+  const void* wbase;       // the array behind tm_w (rows of 64 fp16): L2 prefetch of the next layer's tiles
   int w_row0;              // first row of this evaluation's weight set in tm_w
   int w_layer_rows;        // rows per layer
   int w_sr;                // 0: hi / lo planes (64 tiles per layer); 1: single-plane stochastically rounded set (32 tiles per layer)
@@ -170,8 +171,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
   uint64_t* afull = lfin + 1;       // [AS] A tile of the skip GEMM landed (leader's barrier)
   uint64_t* aempty = afull + AS;    // [AS]
   uint64_t* sdone = aempty + AS;    // exit: this CTA's 8 epilogue warps have written the S16 tiles (local)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdone + 1);
-  static_assert((2 * Cfg::WSLOTS + 10 + 2 * Cfg::ASLOTS) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
+  uint64_t* yhalf = sdone + 1;      // R = 128: k-blocks 0 and 2 of y_{l+1} written (first half of epi2), 8 warps x 2 CTAs -> leader
+  uint64_t* zhalf = yhalf + 1;      // R = 128: z k-block 2 written (first half of chunk 1's gate epilogue), 8 warps x 2 CTAs -> leader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zhalf + 1);
+  static_assert((2 * Cfg::WSLOTS + 12 + 2 * Cfg::ASLOTS) * 8 + 4 <= Cfg::BAR_BYTES, "barrier area");
+  // Half-phase hand-overs (R = 128, where an epilogue warp owns two k-blocks of 64 channels): the MMA issuer starts the next
+  // layer's centre taps on k-blocks 0 / 2 of y while the epilogue warps are still writing k-blocks 1 / 3, and GEMM2's k-block 2
+  // while they are still gating k-block 3.  With 64-row tiles a warp owns ONE k-block, so nothing completes early.
+  constexpr bool kHalf = (R == 128);
+  // order of the centre-tap weight tiles of a layer (producers and issuer alike): (chunk, channel block)
+  // kHalf: (1,0) (1,2) (1,1) (1,3) (0,0) (0,1) (0,2) (0,3); otherwise chunk 0 then chunk 1, channel blocks in order
+  auto ctr_h = [](int i) -> int { return kHalf ? (i < 4 ? 1 : 0) : (i >> 2); };
+  auto ctr_cb = [](int i) -> int { return (kHalf && i < 4) ? ((i & 1) * 2 + (i >> 1)) : (i & 3); };
   auto aslot = [&](int s) -> uint8_t* { return s < 4 ? zbuf + s * UNIT : yslots + (s - 4) * UNIT; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -217,6 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
     mbar_init(zfree, 1);
     mbar_init(lfin, 1);
     mbar_init(sdone, kEpiWarps);
+    mbar_init(yhalf, kEpiWarps * G);
+    mbar_init(zhalf, kEpiWarps * G);
     for (int s = 0; s < AS; ++s) {
       mbar_init(&afull[s], 1);
       mbar_init(&aempty[s], 1);
@@ -248,32 +261,74 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       // ================================ activation producer ================================
       bool ok = true;
       const uint64_t z_policy = l2_policy_evict_last();   // z comes back for the skip GEMM: keep it in L2 ahead of the CP stream
-      auto cp_prefetch = [&](int l, int h) {             // HBM -> L2; the two CTAs of a pair share a 128-frame tile when R = 64
-        if (!p.cp_prefetch || l >= p.nl) return;
-        const char* src = reinterpret_cast<const char*>(p.CP + ((static_cast<size_t>(l) * p.cp_tiles + cp_tile) * 2 + h) * kCpChunk);
-        if (R == 128) {
-          for (int i = 0; i < 8; ++i) prefetch_l2_bulk(src + i * 16384, 16384);
-        } else {
-          for (int i = 0; i < 4; ++i) prefetch_l2_bulk(src + (cp_row0 ? 65536 : 0) + i * 16384, 16384);
+      // ---- L2 prefetch (cp.async.bulk.prefetch.L2, 16 KB pieces) ----
+      // CP of layer l + 1: 2 * NPF pieces per CTA (the two CTAs of a pair share a 128-frame tile when R = 64: half a chunk each),
+      // PACED over layer l while this thread waits for z_l.  Issued in one burst at the layer boundary (rounds 1-2) the 128
+      // CTAs' requests -- 33 MB -- queued at HBM in front of the next layer's first weight tiles: the centre-tap phase ran at
+      // 170-250 cycles per MMA instead of the 134 of the halo phase (timeline, profiles/README.md).
+      constexpr int NPF = (R == 128 ? 8 : 4);
+      constexpr long long kCpLead = 8000, kCpStep = 16000 / (2 * NPF);   // cycles: first piece after the z store, piece spacing
+      auto cp_piece = [&](int l, int i) {
+        const char* src = reinterpret_cast<const char*>(p.CP + ((static_cast<size_t>(l) * p.cp_tiles + cp_tile) * 2 + i / NPF) * kCpChunk);
+        prefetch_l2_bulk(src + (R == 64 && cp_row0 ? NPF * 16384 : 0) + (i % NPF) * 16384, 16384);
+      };
+      // weights of layer l: every CTA of the launch prefetches its share of the layer's tile block (all CTAs then load the
+      // same tiles by TMA, in lockstep: without this the first requester of every tile pays the HBM latency and a ring of
+      // WS tiles does not cover it)
+      auto w_prefetch = [&](int l) {
+        if (l >= p.nl || !p.wbase) return;
+        const size_t bytes = static_cast<size_t>(p.w_layer_rows) * 128;
+        size_t share = ((bytes + gridDim.x - 1) / gridDim.x + 15) & ~static_cast<size_t>(15);
+        if (share > 8 * 16384) share = 8 * 16384;
+        const size_t off = static_cast<size_t>(blockIdx.x) * share;
+        if (off >= bytes) return;
+        if (share > bytes - off) share = bytes - off;
+        const char* src = reinterpret_cast<const char*>(p.wbase) + (static_cast<size_t>(p.w_row0) + static_cast<size_t>(l) * p.w_layer_rows) * 128 + off;
+        while (share > 0) {
+          const uint32_t n = share > 16384 ? 16384u : static_cast<uint32_t>(share);
+          prefetch_l2_bulk(src, n);
+          src += n;
+          share -= n;
         }
       };
       // layer 0: the whole [8 | R | 8]-row slots come from Y buffer 0 (written by the input projection kernel)
+      DSX_STRACE(0, 0);
       if (prank == 0) mbar_arrive_expect_tx(y0full, G * Cfg::Y_BYTES);
       for (int cb = 0; cb < 4; ++cb) tma_load_3d<G>(&p.tm_y0, y0full, yslots + cb * Cfg::YSLOT, cb * 64, t0 - 8, bq, lead);
-      cp_prefetch(0, 0);
-      cp_prefetch(0, 1);
+      DSX_STRACE(0, 1);
+      w_prefetch(0);
+      w_prefetch(1);
+      if (p.cp_prefetch)
+        for (int i = 0; i < 2 * NPF; ++i) cp_piece(0, i);
+      DSX_STRACE(0, 2);
       for (int l = 0; l < p.nl && ok; ++l) {
         // z_l (complete once this CTA's epilogue warps are through chunk 1) -> Z[l] in HBM for the deferred skip GEMM;
-        // the z area may be overwritten (next layer's chunk 0) once the store has read it
-        ok = mbar_wait(zdone, l & 1, wd, 108);
+        // the z area may be overwritten (next layer's chunk 0) once the store has read it.  While waiting: CP of layer l + 1
+        int pf_i = (p.cp_prefetch && l + 1 < p.nl) ? 0 : 2 * NPF;
+        long long pf_next = clock64() + kCpLead;
+        uint32_t spins = 0;
+        while (!mbar_try_wait(zdone, l & 1)) {
+          if (pf_i < 2 * NPF && clock64() >= pf_next) {
+            cp_piece(l + 1, pf_i++);
+            pf_next += kCpStep;
+          }
+          if (((++spins) & 0x3ff) == 0) {
+            if (*(volatile int*)wd.status != 0) { ok = false; break; }
+            if (globaltimer_ns() > wd.deadline_ns) {
+              atomicCAS(wd.status, 0, 108);
+              ok = false;
+              break;
+            }
+          }
+        }
         if (!ok) break;
+        while (pf_i < 2 * NPF) cp_piece(l + 1, pf_i++);      // (a layer faster than the pacing: the rest at once)
         for (int kb = 0; kb < 4; ++kb) tma_store_3d_hint(&p.tm_z, zbuf + kb * UNIT, kb * 64, t0, l * p.B + zq, z_policy);
         bulk_commit_group();
         bulk_wait_group_read0();
         mbar_arrive(zfree);
         DSX_STRACE(0, l * 4 + 3);
-        cp_prefetch(l + 1, 0);                            // most of a layer ahead of the gate epilogue that reads it
-        cp_prefetch(l + 1, 1);
+        w_prefetch(l + 2);
       }
       // ---- deferred skip GEMM: A tiles = z of every layer, back from L2 / HBM (this tile's own stores) ----
       if (ok) {
@@ -306,9 +361,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         ++wi;
       };
       for (int l = 0; l < p.nl && ok; ++l) {
-        for (int h = 0; h < 2 && ok; ++h)                           // centre taps of both chunks first: they need no halo rows
-          for (int cb = 0; cb < 4 && ok; ++cb)
-            for (int pl = 0; pl < WP && ok; ++pl) load_w(w1_row(l, h, 1, cb, pl));
+        for (int i = 0; i < 8 && ok; ++i)                           // centre taps of both chunks first: they need no halo rows
+          for (int pl = 0; pl < WP && ok; ++pl) load_w(w1_row(l, ctr_h(i), 1, ctr_cb(i), pl));
         for (int h = 0; h < 2 && ok; ++h)
           for (int cb = 0; cb < 4 && ok; ++cb)
             for (int tap = 0; tap < 3 && ok; tap += 2)
@@ -375,16 +429,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         if (l == 0) {                                   // layer 0: the whole slots (centre rows too) arrive by TMA
           ok = mbar_wait(y0full, 0, wd, 206);
           tc_fence_after();
+        } else if (kHalf) {
+          wait_epi(yhalf, (l - 1) & 1, 208);            // first half of epi2 of layer l-1: k-blocks 0, 2 of y_l written
         } else {
           wait_epi(&tempty[0], 1, 201);                 // epi2 of layer l-1: F0 drained, centre rows of y_l written
         }
         DSX_STRACE(1, l * 8);
+        // centre taps.  F1 has been free since chunk 1's epilogue of layer l-1; with half-phase hand-over the first two tiles
+        // (chunk 1, k-blocks 0 and 2) are issued under the second half of epi2, and F0 is touched only after all of it
 #pragma unroll
-        for (int h = 0; h < 2; ++h)                     // centre taps (F1 has been free since chunk 1's epilogue of layer l-1)
-          for (int cb = 0; cb < 4 && ok; ++cb) {
-            const uint64_t a = umma_desc_sw128(smem_u32(yslots + cb * Cfg::YSLOT)) + static_cast<uint64_t>((8 * 128) >> 4);
-            for (int pl = 0; pl < WP && ok; ++pl) mma_tile(h == 0 ? tmem_base : dF1, a, h == 0 ? acc0 : acc1, 207);
-          }
+        for (int i = 0; i < 8; ++i) {
+          if (kHalf && i == 2 && l > 0) wait_epi(&tempty[0], 1, 201);
+          if (!ok) break;
+          const int h = ctr_h(i), cb = ctr_cb(i);
+          const uint64_t a = umma_desc_sw128(smem_u32(yslots + cb * Cfg::YSLOT)) + static_cast<uint64_t>((8 * 128) >> 4);
+          for (int pl = 0; pl < WP && ok; ++pl) mma_tile(h == 0 ? tmem_base : dF1, a, h == 0 ? acc0 : acc1, 207);
+        }
         DSX_STRACE(1, l * 8 + 1);
         if (l > 0 && ok) {                              // halo rows of this layer (from the neighbour tiles) are in the slots
           ok = mbar_wait(yhalo, (l - 1) & 1, wd, 206);
@@ -408,7 +468,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         uint32_t acc2 = 0;
         for (int kb = 0; kb < 4 && ok; ++kb) {
           if (kb == 0) wait_epi(&tempty[0], 0, 203);
-          if (kb == 2) wait_epi(&tempty[1], l & 1, 204);
+          if (kb == 2) wait_epi(kHalf ? zhalf : &tempty[1], l & 1, 204);   // kHalf: z k-block 2 is complete half a phase early
+          if (kb == 3 && kHalf) wait_epi(&tempty[1], l & 1, 204);
           if (!ok) break;
           if (kb == 0) DSX_STRACE(1, l * 8 + 4);
           if (kb == 2) DSX_STRACE(1, l * 8 + 5);
@@ -542,8 +603,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       const float* cpl = p.CP + (static_cast<size_t>(l) * p.cp_tiles + cp_tile) * 2 * kCpChunk + (cp_row0 + r) * 4;
       constexpr int NB = 3;
       float4 cg[NB][2], cf[NB][2];
-      auto chan = [&](int sp) { return (R == 128) ? wh * 64 + sp * 8 : ng * 64 + wh * 32 + sp * 8; };      // chunk-channel
-      auto tcol = [&](int sp) { return (R == 128) ? wh * 128 + sp * 8 : wh * 32 + sp * 8; };               // TMEM column of its gate
+      // R = 128: a warp takes 32 channels of the chunk's first k-block (sub-passes 0-3), then 32 of its second (4-7), so the
+      // first k-block of a chunk is complete -- over both warps of a quadrant -- half a phase early (zhalf)
+      auto chan = [&](int sp) { return (R == 128) ? (sp >> 2) * 64 + wh * 32 + (sp & 3) * 8 : ng * 64 + wh * 32 + sp * 8; };      // chunk-channel
+      auto tcol = [&](int sp) { return (R == 128) ? (sp >> 2) * 128 + wh * 32 + (sp & 3) * 8 : wh * 32 + sp * 8; };                // TMEM column of its gate
       auto cp_issue = [&](int q, float4* g4, float4* f4) {                               // q = chunk * NSP + sub-pass
         const float* cph = cpl + (q / NSP) * kCpChunk;
         const int c = chan(q % NSP);
@@ -601,6 +664,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         const int c = chan(sp);
         uint8_t* zrow = zbuf + (2 * h + (c >> 6)) * UNIT + r * 128;
         *reinterpret_cast<uint4*>(zrow + ((((c & 63) >> 3) ^ (r & 7)) << 4)) = make_uint4(hz[0], hz[1], hz[2], hz[3]);
+        if (kHalf && h == 1 && sp == NSP / 2 - 1) {     // z k-block 2 complete: GEMM2 may consume it under sub-passes 4-7
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(zhalf, lead);
+        }
         if (sp == NSP - 1) {
           release(&tempty[h]);
           if (h == 1 && lane == 0) mbar_arrive(zdone);    // (after the proxy fence + warp sync of release())
@@ -657,6 +725,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
                 asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(q + 1), "r"(v.z), "r"(seq_next), "r"(v.w), "r"(seq_next) : "memory");
               }
             }
+          }
+          if (kHalf && has_next && pc == NCH / 32 - 1) {   // this warp's first k-block of y_{l+1} (0 or 2) is written: the issuer
+            fence_proxy_async_smem();                     // starts the next layer's centre taps on it (-> F1) under the second half
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(yhalf, lead);
           }
         }
       }
@@ -1209,6 +1282,7 @@ int launch_tc_stack(dsx_handle* h, int nl, const Geom& g, int row0, int row_per_
   TcStackParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.tm_w = sr ? h->tm_wsr : h->tm_wstk;
+  prm.wbase = sr ? static_cast<const void*>(m.wsr) : static_cast<const void*>(m.wstk);
   prm.tm_y0 = h->tm_y0s[ri];
   prm.tm_z = h->tm_zs[ri];
   prm.tm_s16[0] = h->tm_s16s[ri][0];

@@ -193,6 +193,20 @@ def small():
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "dev_small.json"), "w"), indent=1)
 
 
+def k100():
+    """the K = 100 DDPM golden loop (injected noise) in the stack-kernel modes: max / mean |dx| against the live-reference golden"""
+    g = golden("ddpm_lj_K100.npz")
+    S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
+    cond, xT = torch.from_numpy(g["cond"]).to(DEV), torch.from_numpy(g["xT"]).to(DEV)
+    noise = rs_normal(int(g["noise_seed"]), (100,) + tuple(g["xT"].shape)).to(DEV)
+    for prec, sets in (("fp16s", 64), ("fp16x2", None), ("fp16", None)):
+        s = make(1, prec, 1, S, sets)
+        x0 = s.sample_ddpm(xT, cond, 100, 100, noise=noise).cpu().numpy()
+        d = np.abs(x0 - g["x0"])
+        print(f"ddpm K=100 {prec} sets={sets}: max {d.max():.3e} mae {d.mean():.3e}", flush=True)
+        s.close()
+
+
 def timing():
     S = O.make_schedule(O.linear_beta_schedule(100, 0.06))
     res = {}
@@ -262,7 +276,9 @@ def trace():
         print("epilogue (warp 4): per layer e1c0 [enter, acc ready, done], e1c1 [...], e2 [enter, ready, done]")
         for l in range(0, 6):
             print(l, [int(a[0, 2, l * 12 + k] - base) for k in range(9)])
-        print("producer 0: per layer [g1done seen, flags seen, halo issued, z stored]")
+        print("producer 0 (relative to the kernel's entry): y0 loads issued from", int(a[0, 0, 0] - cta[0, 1]), "to", int(a[0, 0, 1] - cta[0, 1]),
+              "| entry prefetches issued", int(a[0, 0, 2] - cta[0, 1]), "| first G1", int(a[0, 1, 0] - cta[0, 1]))
+        print("producer 0: per layer [-, -, -, z stored]")
         for l in range(1, 6):
             print(l, [int(a[0, 0, l * 4 + k] - base) for k in range(4)])
         print("end of skip GEMM issue (MMA thread)", int(a[0, 1, 250] - base), "| exit epilogue: enter", int(a[0, 2, 248] - base),
@@ -276,4 +292,4 @@ def trace():
 
 
 if __name__ == "__main__":
-    {"quick": quick, "small": small, "experiments": experiments, "parity": parity, "timing": timing, "trace": trace}[sys.argv[1]]()
+    {"quick": quick, "k100": k100, "small": small, "experiments": experiments, "parity": parity, "timing": timing, "trace": trace}[sys.argv[1]]()
