@@ -24,7 +24,9 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   float u1 = (static_cast<float>(a) + 1.0f) * 2.3283064365386963e-10f;
   float u2 = static_cast<float>(b) * 2.3283064365386963e-10f;
   // fast intrinsics (MUFU.LG2 / SIN / COS): |error| ~1e-6, far below what a sampler can resolve
-  float r = sqrtf(-2.0f * __logf(u1));
+  // (sqrt.approx: one MUFU; sqrtf() with IEEE rounding is a 15-instruction sequence with a slow-path call, per draw)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
   float s, c;
   __sincosf(6.283185307179586f * u2, &s, &c);
   return make_float2(r * c, r * s);

@@ -180,9 +180,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
   // while they are still gating k-block 3.  With 64-row tiles a warp owns ONE k-block, so nothing completes early.
   constexpr bool kHalf = (R == 128);
   // order of the centre-tap weight tiles of a layer (producers and issuer alike): (chunk, channel block)
-  // kHalf: (1,0) (1,2) (1,1) (1,3) (0,0) (0,1) (0,2) (0,3); otherwise chunk 0 then chunk 1, channel blocks in order
-  auto ctr_h = [](int i) -> int { return kHalf ? (i < 4 ? 1 : 0) : (i >> 2); };
-  auto ctr_cb = [](int i) -> int { return (kHalf && i < 4) ? ((i & 1) * 2 + (i >> 1)) : (i & 3); };
+  // (1,0) (1,2) (1,1) (1,3) (0,0) (0,1) (0,2) (0,3) -- for both tile heights (only the waits differ): the accumulation order
+  // decides the rounding, and 64-row and 128-row tiles stay bit-identical
+  auto ctr_h = [](int i) -> int { return i < 4 ? 1 : 0; };
+  auto ctr_cb = [](int i) -> int { return i < 4 ? ((i & 1) * 2 + (i >> 1)) : (i & 3); };
   auto aslot = [&](int s) -> uint8_t* { return s < 4 ? zbuf + s * UNIT : yslots + (s - 4) * UNIT; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -335,13 +336,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         bulk_wait_group0();                               // the stores are complete (visible to the loads below)
         ok = mbar_wait(lfin, 0, wd, 109);                 // no MMA reads the y / z areas any more
         uint32_t ai = 0;
+        // read once: evict_first, so that these 168 MB (config 2) do not flush the kernel's code and the next launch's entry
+        // state (X / Y0, written below) out of L2 -- every launch used to start with a cold layer 0
+        const uint64_t z_read_policy = l2_policy_evict_first();
         for (int l = p.nl - 1; l >= 0 && ok; --l)           // most recent layers first: their z is still in L2
           for (int kb = 0; kb < 4 && ok; ++kb, ++ai) {
             const uint32_t s = ai % AS;
             ok = mbar_wait(&aempty[s], ((ai / AS) & 1) ^ 1, wd, 110);
             if (!ok) break;
             if (prank == 0) mbar_arrive_expect_tx(&afull[s], G * UNIT);
-            tma_load_3d<G>(&p.tm_z, &afull[s], aslot(s), kb * 64, t0, l * p.B + zq, lead);
+            tma_load_3d_g2_hint(&p.tm_z, &afull[s], aslot(s), kb * 64, t0, l * p.B + zq, lead, z_read_policy);
           }
       }
     } else if ((warp == 2 || warp == 3) && lane == 0) {
@@ -572,8 +576,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
     };
     const uint64_t cp_policy = l2_policy_evict_first();
 
-    // residual stream of this thread's row: NCH channels, fp32, in registers for the whole stack
+    // residual stream of this thread's row: NCH channels, fp32, in registers for the whole stack.  First needed by epi2 of
+    // layer 0, ~35 k cycles in.  Issued at the kernel's entry these loads (128 KB per CTA, 16 MB over the machine) queued in
+    // front of the y0 and weight tiles the first MMAs wait for (entry -> first MMA 11-17 k cycles); issued after the first
+    // accumulator they delayed the first gate epilogue instead.  So: a fixed head start for the TMA loads of the producers.
     float x[NCH];
+    {
+      const long long t_go = clock64() + 5000;
+      while (clock64() < t_go) {}
+    }
 #pragma unroll
     for (int i = 0; i < NCH / 4; ++i) {
       const float4 v = *reinterpret_cast<const float4*>(p.X + grow + i * 4);
@@ -902,13 +913,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         const int t = t0 + r;
         const bool do_in = (p.head_flags & TC_INPROJ) != 0;
         const bool need_z = (p.head_flags & TC_UPDATE) && p.c.sigma != 0.f;
+        // Addressing by running pointers (ncu, round 2: 477 warp-instructions per 4 bins, a quarter of them 64-bit index
+        // arithmetic of the strided accesses) and warp-uniform branches on the launch's flags only: rows beyond T compute on
+        // zeros and are masked at the memory operations (predicated loads / stores instead of divergent blocks).
+        const bool upd = (p.head_flags & TC_UPDATE) != 0, plms = (p.head_flags & TC_PLMS) != 0, weps = (p.head_flags & TC_WRITE_EPS) != 0;
+        const size_t xc = static_cast<size_t>(p.xs.c), ec = static_cast<size_t>(p.T);       // bin strides: mel state, [B][M][T] arrays
         const size_t xrow = static_cast<size_t>(tile_valid ? b : 0) * p.xs.b + static_cast<size_t>(t) * p.xs.t;
         const size_t erow = static_cast<size_t>(tile_valid ? b : 0) * p.M * p.T + t;
+        float* xp = p.xmel + xrow + static_cast<size_t>(m_lo) * xc;                         // bins m0 .. m0 + 3 of this row
+        size_t eo = erow + static_cast<size_t>(m_lo) * ec;                                  // their index in the [B][M][T] arrays
+        const float* bfp = p.bf + m_lo;
+        size_t nblk = mel_noise_block(b + p.b_off, m_lo, t, p.M, p.T);                      // Philox block of the 4 bins (+T per step)
         float xn[4];                                          // the next iteration's mel state, loaded one iteration ahead
 #pragma unroll
-        for (int i = 0; i < 4; ++i) xn[i] = row_valid ? p.xmel[xrow + static_cast<size_t>(m_lo + i) * p.xs.c] : 0.f;
+        for (int i = 0; i < 4; ++i) xn[i] = row_valid ? xp[i * xc] : 0.f;
 #pragma unroll 1
-        for (int m0 = m_lo; m0 < m_hi; m0 += 4) {
+        for (int m0 = m_lo; m0 < m_hi; m0 += 4, xp += 4 * xc, eo += 4 * ec, bfp += 4, nblk += ec) {
           uint32_t e4[4];
           tmem_ld_32x4(tmem_base + tlane + Cfg::F1_COL + m0, e4);
           float xv[4], zn[4];
@@ -919,42 +939,54 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
           }
           if (m0 + 4 < m_hi) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) xn[i] = row_valid ? p.xmel[xrow + static_cast<size_t>(m0 + 4 + i) * p.xs.c] : 0.f;
+            for (int i = 0; i < 4; ++i) xn[i] = row_valid ? xp[(4 + i) * xc] : 0.f;
           }
-          if (need_z && row_valid) {
+          if (need_z) {
             if (p.noise) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) zn[i] = p.noise[erow + static_cast<size_t>(m0 + i) * p.T];
+              for (int i = 0; i < 4; ++i) zn[i] = row_valid ? p.noise[eo + i * ec] : 0.f;
             } else {
-              const float4 z4 = philox_normal4(p.seed, p.offset, mel_noise_block(b + p.b_off, m0, t, p.M, p.T));
+              const float4 z4 = philox_normal4(p.seed, p.offset, nblk);
               zn[0] = z4.x; zn[1] = z4.y; zn[2] = z4.z; zn[3] = z4.w;
             }
           }
+          const float4 bf4 = __ldg(reinterpret_cast<const float4*>(bfp));
+          const float bfv[4] = {bf4.x, bf4.y, bf4.z, bf4.w};
           tmem_ld_wait();
+          float ev[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int m = m0 + i;
-            const float ev = __uint_as_float(e4[i]) + __ldg(p.bf + m);
-            const size_t ei = erow + static_cast<size_t>(m) * p.T;
-            if ((p.head_flags & TC_WRITE_EPS) && row_valid) p.eps_out[ei] = ev;
-            if (p.head_flags & TC_UPDATE) {                   // p_sample, the reference's fp32 operation order
-              float xr = __fsub_rn(__fmul_rn(p.c.A, xv[i]), __fmul_rn(p.c.Bc, ev));
+          for (int i = 0; i < 4; ++i) ev[i] = __uint_as_float(e4[i]) + bfv[i];
+          if (weps) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (row_valid) p.eps_out[eo + i * ec] = ev[i];
+          }
+          if (upd) {                                          // p_sample, the reference's fp32 operation order
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float xr = __fsub_rn(__fmul_rn(p.c.A, xv[i]), __fmul_rn(p.c.Bc, ev[i]));
               xr = fminf(fmaxf(xr, -1.f), 1.f);
               const float mean = __fadd_rn(__fmul_rn(p.c.c1, xr), __fmul_rn(p.c.c2, xv[i]));
               xv[i] = __fadd_rn(mean, __fmul_rn(p.c.sigma, zn[i]));
-              if (row_valid) p.xmel[xrow + static_cast<size_t>(m) * p.xs.c] = xv[i];
+              if (row_valid) xp[i * xc] = xv[i];
             }
-            if ((p.head_flags & TC_PLMS) && row_valid) {      // linear multistep combination + get_x_pred (k_plms_update)
-              float comb = __fmul_rn(p.pl.c.w0, ev);
-              if (p.pl.h1) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w1, p.pl.h1[ei]));
-              if (p.pl.h2) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w2, p.pl.h2[ei]));
-              if (p.pl.h3) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w3, p.pl.h3[ei]));
+          }
+          if (plms) {                                         // linear multistep combination + get_x_pred (k_plms_update)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const size_t ei = eo + i * ec;
+              float comb = __fmul_rn(p.pl.c.w0, ev[i]);
+              if (p.pl.h1) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w1, row_valid ? p.pl.h1[ei] : 0.f));
+              if (p.pl.h2) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w2, row_valid ? p.pl.h2[ei] : 0.f));
+              if (p.pl.h3) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w3, row_valid ? p.pl.h3[ei] : 0.f));
               const float ep = __fdiv_rn(comb, p.pl.c.denom);
               const float inner = __fsub_rn(__fmul_rn(p.pl.c.kx, xv[i]), __fmul_rn(p.pl.c.ke, ep));
               xv[i] = __fadd_rn(xv[i], __fmul_rn(p.pl.c.a_diff, inner));
-              if (p.pl.eps_store) p.pl.eps_store[ei] = ev;
-              if (p.pl.x_out) p.pl.x_out[ei] = xv[i];
-              else p.xmel[xrow + static_cast<size_t>(m) * p.xs.c] = xv[i];
+              if (row_valid) {
+                if (p.pl.eps_store) p.pl.eps_store[ei] = ev[i];
+                if (p.pl.x_out) p.pl.x_out[ei] = xv[i];
+                else xp[i * xc] = xv[i];
+              }
             }
           }
           if (do_in) {                                        // 4 bins = half a 16-byte chunk of row r in k-block m0 >> 6
