@@ -53,7 +53,7 @@ CONFIGS = {
 }
 NOTES = {"fp16": "single MMA pass, fp16 round-to-nearest operands, tanh.approx gate: mel MAE 7e-5, max |d| 1.6e-3 after 100 steps (tests)",
          "fp16s": "single MMA pass, weights stochastically rounded into 64 sets cycled over the steps (unbiased, decorrelated weight "
-                  "rounding), conditioner projection exact: max |d| 3.3e-4 after 100 steps (tests)",
+                  "rounding), conditioner projection exact: max |d| 2.6e-4 after 100 steps (tests)",
          "fp16x2": "weights hi/lo split, 2 MMA passes, conditioner projection exact: max |d| 1.6e-4 after 100 steps (tests)",
          "fp16x3": "hi/lo split of both operands, 3 MMA passes: max |d| 1.4e-5 after 100 steps (tests)",
          "fp32": "CUDA-core fp32 path"}

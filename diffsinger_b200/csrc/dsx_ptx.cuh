@@ -185,17 +185,6 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, voi
   }
 }
 
-// the cta_group::2 form with an L2 cache policy (read-once streams: evict_first keeps them from displacing what stays)
-__device__ __forceinline__ void tma_load_3d_g2_hint(const void* tmap, uint64_t* bar, void* dst, int c0, int c1, int c2, uint32_t lead,
-                                                    uint64_t policy) {
-  uint32_t lead_bar = mapa(smem_u32(bar), lead);
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, "
-      "%4, %5}], [%2], %6;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(lead_bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
-      : "memory");
-}
-
 // TMA store of one box shared::cta -> global (bulk async-group completion)
 __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"

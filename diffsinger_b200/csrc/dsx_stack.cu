@@ -336,16 +336,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         bulk_wait_group0();                               // the stores are complete (visible to the loads below)
         ok = mbar_wait(lfin, 0, wd, 109);                 // no MMA reads the y / z areas any more
         uint32_t ai = 0;
-        // read once: evict_first, so that these 168 MB (config 2) do not flush the kernel's code and the next launch's entry
-        // state (X / Y0, written below) out of L2 -- every launch used to start with a cold layer 0
-        const uint64_t z_read_policy = l2_policy_evict_first();
         for (int l = p.nl - 1; l >= 0 && ok; --l)           // most recent layers first: their z is still in L2
           for (int kb = 0; kb < 4 && ok; ++kb, ++ai) {
             const uint32_t s = ai % AS;
             ok = mbar_wait(&aempty[s], ((ai / AS) & 1) ^ 1, wd, 110);
             if (!ok) break;
             if (prank == 0) mbar_arrive_expect_tx(&afull[s], G * UNIT);
-            tma_load_3d_g2_hint(&p.tm_z, &afull[s], aslot(s), kb * 64, t0, l * p.B + zq, lead, z_read_policy);
+            tma_load_3d<G>(&p.tm_z, &afull[s], aslot(s), kb * 64, t0, l * p.B + zq, lead);
           }
       }
     } else if ((warp == 2 || warp == 3) && lane == 0) {
@@ -927,19 +924,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         float xn[4];                                          // the next iteration's mel state, loaded one iteration ahead
 #pragma unroll
         for (int i = 0; i < 4; ++i) xn[i] = row_valid ? xp[i * xc] : 0.f;
+        // PNDM: the eps history (up to three [B][M][T] arrays) likewise -- loaded inside the iteration, after the TMEM wait, the
+        // three streams were a serial L2 / HBM round trip per 4 bins (ncu launch list: 447 us per PNDM launch against 375 us for
+        // a DDPM one)
+        const float* const hp[3] = {plms ? p.pl.h1 : nullptr, plms ? p.pl.h2 : nullptr, plms ? p.pl.h3 : nullptr};
+        float hn[3][4];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hn[j][i] = (hp[j] && row_valid) ? hp[j][eo + i * ec] : 0.f;
 #pragma unroll 1
         for (int m0 = m_lo; m0 < m_hi; m0 += 4, xp += 4 * xc, eo += 4 * ec, bfp += 4, nblk += ec) {
           uint32_t e4[4];
           tmem_ld_32x4(tmem_base + tlane + Cfg::F1_COL + m0, e4);
-          float xv[4], zn[4];
+          float xv[4], zn[4], hv[3][4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             zn[i] = 0.f;
             xv[i] = xn[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) hv[j][i] = hn[j][i];
           }
           if (m0 + 4 < m_hi) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) xn[i] = row_valid ? xp[(4 + i) * xc] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) hn[j][i] = (hp[j] && row_valid) ? hp[j][eo + (4 + i) * ec] : 0.f;
           }
           if (need_z) {
             if (p.noise) {
@@ -976,9 +988,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
             for (int i = 0; i < 4; ++i) {
               const size_t ei = eo + i * ec;
               float comb = __fmul_rn(p.pl.c.w0, ev[i]);
-              if (p.pl.h1) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w1, row_valid ? p.pl.h1[ei] : 0.f));
-              if (p.pl.h2) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w2, row_valid ? p.pl.h2[ei] : 0.f));
-              if (p.pl.h3) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w3, row_valid ? p.pl.h3[ei] : 0.f));
+              if (hp[0]) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w1, hv[0][i]));
+              if (hp[1]) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w2, hv[1][i]));
+              if (hp[2]) comb = __fadd_rn(comb, __fmul_rn(p.pl.c.w3, hv[2][i]));
               const float ep = __fdiv_rn(comb, p.pl.c.denom);
               const float inner = __fsub_rn(__fmul_rn(p.pl.c.kx, xv[i]), __fmul_rn(p.pl.c.ke, ep));
               xv[i] = __fadd_rn(xv[i], __fmul_rn(p.pl.c.a_diff, inner));

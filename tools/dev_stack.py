@@ -2,7 +2,7 @@
 
     python tools/dev_stack.py parity      # golden / oracle parity of every mode, old kernel vs new kernel
     python tools/dev_stack.py timing      # config-2 loop timings per mode and kernel
-    python tools/dev_stack.py trace       # clock64 timeline of one evaluation (CTA 0 / 1)
+    python tools/dev_stack.py trace [B T] # clock64 timeline of one evaluation (CTA 0 / 1); default 16 x 1024
 """
 import json
 import os
@@ -242,7 +242,7 @@ def timing():
 
 def trace():
     import ctypes
-    B, T = 16, 1024
+    B, T = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (16, 1024)     # e.g. `trace 1 512`: 64-frame tiles
     gen = torch.Generator().manual_seed(1)
     cond = torch.randn(B, T, 256, generator=gen).transpose(1, 2).to(DEV)
     x = torch.randn(B, 1, 80, T, generator=gen).to(DEV)

@@ -3,12 +3,14 @@
 # captures of the fused stack kernel, its clock64 timeline, compute-sanitizer memcheck.  Outputs land in gpurun_out/ (copied into profiles/ by hand).
 mkdir -p gpurun_out
 P=${1:-fp16s}
+timeout 700 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/r02_gpu_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/r02_gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02_smoke.log 2>&1; tail -1 gpurun_out/r02_smoke.log
 timeout 400 python bench.py --steps 5 --warmup 3 > gpurun_out/r02_bench_config2.json 2> gpurun_out/r02_bench_config2.err; echo "bench2 rc=$?"
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2> /dev/null; echo "ref rc=$?"
 for C in 1 3 4; do
   timeout 600 python bench.py --config $C --steps 2 --warmup 3 --no-extra > gpurun_out/r02_bench_config$C.json 2> gpurun_out/r02_bench_config$C.err; echo "bench$C rc=$?"
 done
-timeout 900 python bench.py --config sweep --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_sweep.json 2> gpurun_out/r02_bench_sweep.err; echo "sweep rc=$?"
+timeout 600 python bench.py --config sweep --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_sweep.json 2> gpurun_out/r02_bench_sweep.err; echo "sweep rc=$?"
 for Q in fp16s fp16x2; do
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/r02_launches_$Q.csv python tools/ncu_target.py $Q 3 > /dev/null 2>&1
   timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_tc_stack -s 1 -c 1 -f -o gpurun_out/r02_ncu_stack_$Q python tools/ncu_target.py $Q 3 > gpurun_out/r02_ncu_stack_$Q.log 2>&1
