@@ -71,6 +71,12 @@ struct StackCfg {
   static constexpr int REGS_LOW = 56, REGS_HIGH = 224;     // setmaxnreg targets: 128 * 56 + 256 * 224 = 64512 = 384 * 168 (the
                                                             // CTA's register pool is its launch allocation)
   static constexpr int F1_COL = (R == 128) ? 256 : 128;     // TMEM column of the second accumulator
+  // The skip-sum accumulator.  R = 128: F1 itself (TMEM is full: two N = 256 accumulators of 256 columns), so the skip GEMM is
+  // DEFERRED to one K = L * 256 contraction after the last layer.  R = 64: an N = 256 accumulator takes 128 columns, columns
+  // 256-383 are free -- the skip half of every layer accumulates there right after its GEMM2, in the tensor pipe's idle time
+  // under the residual epilogue: no deferred GEMM (54 k of 491 k cycles per launch at B = 1, T = 512) and no z round trip.
+  static constexpr int SKIP_COL = 256;
+  static constexpr bool SKIP_IN_LAYER = (R == 64);
   static constexpr int NCH = R;                             // channels (N indices) per epilogue thread in epi2 / exit
   static constexpr int NSP = R / 16;                        // gate sub-passes (8 channels each) per chunk and thread
   static_assert(R == 128 || R == 64, "rows per CTA");
@@ -324,19 +330,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         }
         if (!ok) break;
         while (pf_i < 2 * NPF) cp_piece(l + 1, pf_i++);      // (a layer faster than the pacing: the rest at once)
-        for (int kb = 0; kb < 4; ++kb) tma_store_3d_hint(&p.tm_z, zbuf + kb * UNIT, kb * 64, t0, l * p.B + zq, z_policy);
-        bulk_commit_group();
-        bulk_wait_group_read0();
-        mbar_arrive(zfree);
+        if (!Cfg::SKIP_IN_LAYER) {
+          for (int kb = 0; kb < 4; ++kb) tma_store_3d_hint(&p.tm_z, zbuf + kb * UNIT, kb * 64, t0, l * p.B + zq, z_policy);
+          bulk_commit_group();
+          bulk_wait_group_read0();
+          mbar_arrive(zfree);
+        }                                                    // (SKIP_IN_LAYER: the issuer's commit after the skip MMAs frees z)
         DSX_STRACE(0, l * 4 + 3);
         w_prefetch(l + 2);
       }
       // ---- deferred skip GEMM: A tiles = z of every layer, back from L2 / HBM (this tile's own stores) ----
-      if (ok) {
+      if (ok && !Cfg::SKIP_IN_LAYER) {
         bulk_wait_group0();                               // the stores are complete (visible to the loads below)
         ok = mbar_wait(lfin, 0, wd, 109);                 // no MMA reads the y / z areas any more
         uint32_t ai = 0;
-        for (int l = p.nl - 1; l >= 0 && ok; --l)           // most recent layers first: their z is still in L2
+        for (int l = 0; l < p.nl && ok; ++l)                // (ascending: the summation order of the in-layer form)
           for (int kb = 0; kb < 4 && ok; ++kb, ++ai) {
             const uint32_t s = ai % AS;
             ok = mbar_wait(&aempty[s], ((ai / AS) & 1) ^ 1, wd, 110);
@@ -370,10 +378,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
               for (int pl = 0; pl < WP && ok; ++pl) load_w(w1_row(l, h, tap, cb, pl));
         for (int kb = 0; kb < 4 && ok; ++kb)
           for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, 0, kb, pl));
+        if (Cfg::SKIP_IN_LAYER)                                       // the skip half of this layer, right after its GEMM2
+          for (int kb = 0; kb < 4 && ok; ++kb)
+            for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, 1, kb, pl));
       }
-      for (int l = p.nl - 1; l >= 0 && ok; --l)                      // skip GEMM (same order as its A tiles)
-        for (int kb = 0; kb < 4 && ok; ++kb)
-          for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, 1, kb, pl));
+      if (!Cfg::SKIP_IN_LAYER)
+        for (int l = 0; l < p.nl && ok; ++l)                          // deferred skip GEMM (same order as its A tiles)
+          for (int kb = 0; kb < 4 && ok; ++kb)
+            for (int pl = 0; pl < WP && ok; ++pl) load_w(w2_row(l, 1, kb, pl));
       if (p.head_flags) {
         // fused head: 128-row tiles of the whead pack (hi plane, lo plane per k-block).  The N = 256 operand of a pair is
         // [leader's tile | peer's tile]: the row halves of skip_projection / input_projection, twice the same tile for
@@ -402,7 +414,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       // ================================ MMA issuer (pair leader) ================================
       constexpr uint32_t idesc = umma_idesc_f16(R * G, 256);
       const uint32_t dF1 = tmem_base + Cfg::F1_COL;
-      uint32_t wi = 0;
+      const uint32_t dSkip = tmem_base + Cfg::SKIP_COL;
+      uint32_t wi = 0, accs = 0;
       bool ok = true;
       auto mma_tile = [&](uint32_t d, uint64_t a, uint32_t& acc, int code) {   // one weight tile of the global order
         const uint32_t s = wi % WS;
@@ -479,20 +492,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
         }
         if (ok) umma_commit<G>(&tfull[0], pair_mask);
         DSX_STRACE(1, l * 8 + 6);
-      }
-      // ---- deferred skip GEMM -> F1 (free since chunk 1's epilogue of the last layer) ----
-      if (ok) umma_commit<G>(lfin, pair_mask);
-      uint32_t ai = 0, accs = 0;
-      for (int l = p.nl - 1; l >= 0 && ok; --l)
-        for (int kb = 0; kb < 4 && ok; ++kb, ++ai) {
-          const uint32_t s = ai % AS;
-          ok = mbar_wait(&afull[s], (ai / AS) & 1, wd, 209);
-          if (!ok) break;
-          tc_fence_after();
-          const uint64_t a = umma_desc_sw128(smem_u32(aslot(s)));
-          for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dF1, a, accs, 210);
-          if (ok) umma_commit<G>(&aempty[s], pair_mask);
+        if (Cfg::SKIP_IN_LAYER) {
+          // skip half of this layer -> its own accumulator, under the residual epilogue (z is complete: GEMM2's k-block 3 waited
+          // for it); the z area is free for the next layer's gate epilogue once these MMAs have read it
+          for (int kb = 0; kb < 4 && ok; ++kb) {
+            const uint64_t z = umma_desc_sw128(smem_u32(zbuf + kb * UNIT));
+            for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dSkip, z, accs, 210);
+          }
+          if (ok) umma_commit<G>(zfree, pair_mask);
         }
+      }
+      if (!Cfg::SKIP_IN_LAYER) {
+        // ---- deferred skip GEMM -> F1 (free since chunk 1's epilogue of the last layer), layers in ascending order: the
+        //      same summation order as the in-layer form of the 64-row tiles ----
+        if (ok) umma_commit<G>(lfin, pair_mask);
+        uint32_t ai = 0;
+        for (int l = 0; l < p.nl && ok; ++l)
+          for (int kb = 0; kb < 4 && ok; ++kb, ++ai) {
+            const uint32_t s = ai % AS;
+            ok = mbar_wait(&afull[s], (ai / AS) & 1, wd, 209);
+            if (!ok) break;
+            tc_fence_after();
+            const uint64_t a = umma_desc_sw128(smem_u32(aslot(s)));
+            for (int pl = 0; pl < WP && ok; ++pl) mma_tile(dSkip, a, accs, 210);
+            if (ok) umma_commit<G>(&aempty[s], pair_mask);
+          }
+      }
       if (ok) umma_commit<G>(&tfull[1], pair_mask);
       DSX_STRACE(1, 250);
       if (p.head_flags && ok) {
@@ -806,7 +831,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
 #pragma unroll 1
       for (int pc = 0; pc < NCH / 16; ++pc) {
         uint32_t o[16];
-        tmem_ld_32x16(tmem_base + tlane + Cfg::F1_COL + cbase + pc * 16, o);
+        tmem_ld_32x16(tmem_base + tlane + Cfg::SKIP_COL + cbase + pc * 16, o);
         tmem_ld_wait();
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
@@ -1300,13 +1325,18 @@ static int launch_stack_t(dsx_handle* h, TcStackParams& prm, const Geom& g, cuda
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = StackCfg<R>::SMEM_BYTES;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    // Cooperative: the tiles of an utterance wait for each other's halo packets, so every CTA of the launch must be resident at
+    // once.  The grid is sized for an idle device (stack_occupancy); if another stream or process holds SMs, a cooperative launch
+    // waits for them (or fails at launch) instead of starting a partial grid that would spin until the watchdog.
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     DSX_CUDA(cudaLaunchKernelEx(&cfg, k_tc_stack<WP, R>, prm));
     h->launches++;
     h->stack_launches++;
