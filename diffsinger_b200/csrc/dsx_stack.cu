@@ -1325,18 +1325,16 @@ static int launch_stack_t(dsx_handle* h, TcStackParams& prm, const Geom& g, cuda
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = StackCfg<R>::SMEM_BYTES;
     cfg.stream = s;
-    // Cooperative: the tiles of an utterance wait for each other's halo packets, so every CTA of the launch must be resident at
-    // once.  The grid is sized for an idle device (stack_occupancy); if another stream or process holds SMs, a cooperative launch
-    // waits for them (or fails at launch) instead of starting a partial grid that would spin until the watchdog.
-    cudaLaunchAttribute attr[2];
+    // (Not a cooperative launch: Nsight Compute cannot replay a cooperative cluster launch -- `LaunchFailed` -- and a launch that
+    //  cannot be profiled is worse than the documented requirement that the device is not shared while a step runs,
+    //  INTEGRATION.md section 3; a lost peer ends in the in-kernel watchdog, and the handle stays usable.)
+    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeCooperative;
-    attr[1].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 2;
+    cfg.numAttrs = 1;
     DSX_CUDA(cudaLaunchKernelEx(&cfg, k_tc_stack<WP, R>, prm));
     h->launches++;
     h->stack_launches++;

@@ -61,7 +61,9 @@ def test_diffnet_forward_golden(dsx, cycle, prec, group):
     B, _, M, T = g["spec"].shape
     x_last = s.debug_read(0, B, T).cpu().numpy()       # [B,T,C]
     skip = s.debug_read(1, B, T).cpu().numpy()
-    tol = {"fp32": 2e-4, "fp16x3": 2e-4, "fp16x2": 1.5e-3, "fp16s": 3e-3, "fp16": 1e-2}[prec]
+    # one evaluation, max |d eps| against the live-reference golden; measured on B200 (cycle 4): fp16x2 2.9e-4, fp16s 5.2e-4,
+    # fp16 4.8e-4 -- bounds at ~2.5 x that (the sampling loops below hold the north_star tolerance itself)
+    tol = {"fp32": 2e-4, "fp16x3": 2e-4, "fp16x2": 7.5e-4, "fp16s": 1.3e-3, "fp16": 1.3e-3}[prec]
     assert np.abs(eps - g["eps"]).max() < tol
     assert np.abs(x_last[1].T - g["x20_b1"]).max() < tol * 5
     assert np.abs(skip[0].T - g["skip_sum_b0"]).max() < tol * 20     # |skip_sum| ~ 10
