@@ -622,7 +622,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       //      an L2 round trip each; one table per warp: no cross-warp barrier) ----
       __syncwarp();
       if (lane < NCH / 4) {
-        *reinterpret_cast<float4*>(tb + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.b2 + static_cast<size_t>(l) * 512 + nbase) + lane);
+        // (the bias already scaled by 1 / sqrt 2: epi2 is x <- fma(x, c, fma(o, c, b c)), two packed FMAs per channel pair)
+        float4 bl = __ldg(reinterpret_cast<const float4*>(p.b2 + static_cast<size_t>(l) * 512 + nbase) + lane);
+        bl.x *= 0.70710678118654752440f; bl.y *= 0.70710678118654752440f; bl.z *= 0.70710678118654752440f; bl.w *= 0.70710678118654752440f;
+        *reinterpret_cast<float4*>(tb + lane * 4) = bl;
         *reinterpret_cast<float4*>(tb + NCH + lane * 4) =
             has_next ? __ldg(reinterpret_cast<const float4*>(dbase + static_cast<size_t>(l + 1) * kC + nbase) + lane)
                      : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -710,7 +713,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
       }
       if (!ok) break;
 
-      // ---- epi2: x <- (x + D2res + b) / sqrt2 in registers; y_{l+1} = fp16(x + d_{l+1}) -> next layer's A tiles ----
+      // ---- epi2: x <- (x + D2res + b) / sqrt2 in registers (two packed FMAs per channel pair, the bias pre-scaled);
+      //      y_{l+1} = fp16(x + d_{l+1}) -> next layer's A tiles ----
       if (tracer) DSX_STRACE(2, l * 12 + 6);
       ok = wait_acc(&tfull[0], 1, 303);
       if (!ok) break;
@@ -736,12 +740,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_stack(const __grid_constant_
               const int i = c2 * 8 + e * 4, col = pc * 16 + i;
               const float4 bias = bt[col >> 2], dn = dt[col >> 2];
               const float2 c2v = make_float2(0.70710678118654752440f, 0.70710678118654752440f);
-              const float2 xa = mul2(add2(make_float2(x[col], x[col + 1]),
-                                          add2(make_float2(__uint_as_float(o[pc & 1][i]), __uint_as_float(o[pc & 1][i + 1])),
-                                               make_float2(bias.x, bias.y))), c2v);
-              const float2 xb = mul2(add2(make_float2(x[col + 2], x[col + 3]),
-                                          add2(make_float2(__uint_as_float(o[pc & 1][i + 2]), __uint_as_float(o[pc & 1][i + 3])),
-                                               make_float2(bias.z, bias.w))), c2v);
+              const float2 xa = fma2(make_float2(x[col], x[col + 1]), c2v,
+                                     fma2(make_float2(__uint_as_float(o[pc & 1][i]), __uint_as_float(o[pc & 1][i + 1])), c2v,
+                                          make_float2(bias.x, bias.y)));
+              const float2 xb = fma2(make_float2(x[col + 2], x[col + 3]), c2v,
+                                     fma2(make_float2(__uint_as_float(o[pc & 1][i + 2]), __uint_as_float(o[pc & 1][i + 3])), c2v,
+                                          make_float2(bias.z, bias.w)));
               x[col] = xa.x; x[col + 1] = xa.y; x[col + 2] = xb.x; x[col + 3] = xb.y;
               const float2 ya = add2(xa, make_float2(dn.x, dn.y)), yb = add2(xb, make_float2(dn.z, dn.w));
               hy[2 * e] = row_valid ? h2_bits(__floats2half2_rn(ya.x, ya.y)) : 0u;

@@ -5,4 +5,3 @@ timeout 200 python tools/dev_stack.py quick > gpurun_out/dev_quick.log 2>&1; ech
 timeout 200 python tools/dev_stack.py k100 2>&1 | grep "ddpm K"
 timeout 200 python tools/dev_stack.py trace > gpurun_out/dev_trace.log 2>&1; echo "trace rc=$?"; grep -E "cycles per layer|CTAs|fused head|end of skip" gpurun_out/dev_trace.log
 timeout 700 python -m pytest tests -q -x -m gpu --timeout 300 > gpurun_out/dev_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/dev_tests.log
-timeout 300 python bench.py --steps 3 --warmup 3 --no-extra --no-cpu-baseline > gpurun_out/dev_bench.json 2> gpurun_out/dev_bench.err; echo "bench rc=$?"; cat gpurun_out/dev_bench.json
