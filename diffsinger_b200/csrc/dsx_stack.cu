@@ -29,8 +29,14 @@
 //                 per-layer bias / FiLM vectors (1 KB per epilogue warp) | barriers]; the deferred skip GEMM streams its A
 // tiles (z of every layer) through the z and y areas.
 // TMEM: F0, F1 (256 columns each).
-// Small batches run the same kernel with 64 rows per CTA (UMMA M = 128: twice the CTAs, about half the time per layer), see
-// StackCfg.
+// Small batches run the same kernel with 64 rows per CTA (UMMA M = 128: twice the CTAs; the accumulators then take 128 TMEM
+// columns each, so the skip half gets a third accumulator and is summed inside the layers instead of deferred), see StackCfg.
+//
+// Scheduling (what the clock64 timelines in profiles/ led to): the next layer's centre taps and GEMM2's k-block 2 start
+// half an epilogue phase early (yhalf / zhalf: an epilogue warp finishes its first 64-channel k-block, signals, then does its
+// second); the L2 prefetch of the conditioner stream is PACED over the layer and every CTA prefetches its share of the weight
+// block two layers ahead, so that the first weight tiles of a layer do not queue at HBM behind a 33 MB prefetch burst; the
+// epilogue warps load x only after the producers' first TMA loads are on their way.
 // Roles (384 threads): warp 0 lane 0 = activation producer (layer-0 slots, z stores, CP prefetch, A tiles of the skip GEMM),
 // warps 2, 3 lane 0 = weight producers, warp 1 lane 0 of the pair leader = MMA issuer, warps 4-11 = epilogue (thread = frame
 // row = TMEM lane, two warps per lane quadrant split the 256 columns).  setmaxnreg moves registers from warps 0-3 to the
